@@ -1,0 +1,140 @@
+/* vvgpu — C ABI of the B200-native particle hot path for vvflow (libvvhd).
+ *
+ * The reference has no plugin/FFI interface; the boundary is the C++ class surface that
+ * utils/vvflow/vvflow.cpp:201-208,246-257 instantiates and calls once per time step. Each
+ * entry point below names the reference member it replaces (paths relative to the reference
+ * tree). Adapter classes with the reference's own names (vvflow_b200/host/vvgpu_adapter.hpp)
+ * forward to these calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions: every call returns 0 on success or a negative VVGPU_E* code (vvgpu_strerror
+ * gives the text, vvgpu_last_error the detail); no exception crosses the boundary. One
+ * context owns one CUDA device and is driven from one host thread. All pointers are HOST
+ * pointers unless the name ends in _dev. Plain pointers and sizes only.
+ */
+#ifndef VVGPU_H
+#define VVGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vvgpu_ctx vvgpu_ctx;
+
+enum {
+    VVGPU_OK = 0,
+    VVGPU_EINVAL = -1,   /* bad argument (the reference throws std::invalid_argument) */
+    VVGPU_ESTATE = -2,   /* call out of order, e.g. epsilon before tree_build ("tree is not built") */
+    VVGPU_ECUDA = -3,    /* CUDA runtime error; no CPU fallback exists */
+    VVGPU_ENOMEM = -4,
+    VVGPU_ELIMIT = -5    /* an internal capacity (tree depth, traversal stack) was exceeded */
+};
+
+/* TObj, libvvhd/headers/TObj.hpp:10-16 — 48 bytes: r.x r.y g v.x v.y _1_eps */
+typedef struct { double x, y, g, vx, vy, ieps; } vvgpu_obj;
+
+/* TAtt, libvvhd/headers/TBody.hpp:17-58 — the fields the hot path reads */
+typedef struct {
+    double rx, ry;       /* TObj::r  (segment centre) */
+    double cx, cy;       /* corner */
+    double dlx, dly;     /* dl */
+    double g;            /* attached circulation */
+    double ieps;         /* TObj::_1_eps = 3/|dl| (TBody.cpp:209) */
+    int32_t slip;
+    int32_t body;        /* index into the bodies array */
+} vvgpu_seg;
+
+/* the TBody state the hot path reads: get_axis(), _cofm, _min_rect_*, _min_disc_r2,
+ * isInsideValid(), speed_slae (libvvhd/headers/TBody.hpp, src/TBody.cpp:238-246) */
+typedef struct {
+    double axis_x, axis_y, cofm_x, cofm_y;
+    double bl_x, bl_y, tr_x, tr_y, disc_r2;
+    double speed_x, speed_y, speed_o;   /* speed_slae */
+    int32_t inside_valid;
+    int32_t first_seg, n_seg;           /* this body's range in the segment array */
+    int32_t _pad;
+} vvgpu_body;
+
+enum { VVGPU_LIST_VORTEX = 0 };  /* heat / streak lists: SURVEY.md §8(f) row 3, not built yet */
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int vvgpu_create(int device, vvgpu_ctx** out);
+void vvgpu_destroy(vvgpu_ctx* ctx);
+const char* vvgpu_strerror(int code);
+const char* vvgpu_last_error(const vvgpu_ctx* ctx);
+
+/* ---- state in / out (Space::VortexList, Space::BodyList; libvvhd/headers/TSpace.hpp:38-44) */
+int vvgpu_set_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t n);
+/* 24-byte (x,y,g) records as Space::load_list_bin reads them (TSpace.cpp:161-175); v,_1_eps = 0 */
+int vvgpu_set_particles_xyg(vvgpu_ctx* ctx, int list, const double* xyg, size_t n);
+int vvgpu_particle_count(vvgpu_ctx* ctx, int list, size_t* n);
+/* current device order (after tree_build: the reference's in-place permuted order) */
+int vvgpu_get_particles(vvgpu_ctx* ctx, int list, vvgpu_obj* out, size_t cap, size_t* n);
+/* orig[i] = index, in the order of the last set_particles call, of the particle now at i */
+int vvgpu_get_permutation(vvgpu_ctx* ctx, int list, int32_t* orig, size_t cap);
+int vvgpu_set_bodies(vvgpu_ctx* ctx, const vvgpu_seg* segs, size_t nseg, const vvgpu_body* bodies, size_t nbody);
+
+/* ---- stree (libvvhd/headers/TSortedTree.hpp:60-92) -------------------------------------- */
+/* stree::stree + stree::build(includeV, includeB, .) — TSortedTree.cpp:221-265.
+ * include_mask bit0 = vortexes, bit1 = bodies. Building a built tree returns VVGPU_ESTATE
+ * (the reference prints "Tree is already built" and returns). */
+int vvgpu_tree_build(vvgpu_ctx* ctx, int far_criteria, double min_node_size, double max_node_size,
+                     unsigned include_mask);
+int vvgpu_tree_destroy(vvgpu_ctx* ctx);                 /* stree::destroy, :267-273 */
+int vvgpu_tree_counts(vvgpu_ctx* ctx, size_t* n_nodes, size_t* n_leaves, size_t* depth);
+/* Nodes in DFS pre-order (child 1 first). dbl: 10 per node (x y h w CMp.x CMp.y CMp.g CMm.x CMm.y CMm.g);
+ * idx: 8 per node (vfirst vlast nseg ch1 ch2 leaf_index sfirst depth), -1 where n/a.
+ * Serves stree::getBottomNodes()/findNode() to host code (:275-303). */
+int vvgpu_tree_export(vvgpu_ctx* ctx, double* dbl, int64_t* idx, size_t cap_nodes);
+/* per-leaf interaction lists exactly as snode::FindNearNodes (:199-217) builds them, CSR:
+ * near -> leaf indices, far -> pre-order node ids, both in DFS order. Pass idx == NULL to get
+ * only the ptr arrays (sizes n_leaves+1). */
+int vvgpu_tree_lists(vvgpu_ctx* ctx, int64_t* near_ptr, int64_t* near_idx, size_t near_cap, int64_t* far_ptr,
+                     int64_t* far_idx, size_t far_cap);
+/* segment ids held by each leaf's bllist (CSR, n_leaves+1 / nseg) */
+int vvgpu_tree_leaf_segments(vvgpu_ctx* ctx, int64_t* ptr, int64_t* idx, size_t cap);
+/* near pairs (targets g!=0 x sources g!=0 over near leaves, self included) and far-node visits:
+ * the "interactions" of the headline metric */
+int vvgpu_count_interactions(vvgpu_ctx* ctx, double* near_pairs, double* far_nodes);
+
+/* ---- MEpsilonFast::CalcEpsilonFast(merge), MEpsilonFast.cpp:11-63; Merged() -> *merged ---- */
+int vvgpu_epsilon(vvgpu_ctx* ctx, int merge, int* merged);
+/* ---- MConvectiveFast::process_all_lists, MConvectiveFast.cpp:36-114. inf_* = S->inf_speed(),
+ * dt = S->dt (sink epsilon, :160), sinks = Space::SourceList as (x,y,g) triples -------------- */
+int vvgpu_convective(vvgpu_ctx* ctx, double inf_vx, double inf_vy, double dt, const double* sinks_xyg,
+                     size_t nsink);
+/* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
+ * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
+int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);
+/* ---- MFlowmove::move_and_clean particle part, MFlowmove.cpp:107-144,194-199. dt_eff is the
+ * collision-shortened step (:25-57, computed by the caller). Outputs (may be NULL) are the
+ * increments to TBody::fdt_dead (x,y,o per body), TBody::g_dead, TAtt::gsum (per segment). ---- */
+int vvgpu_move_and_clean(vvgpu_ctx* ctx, double dt_eff, double remove_eps, int remove_in_body,
+                         double* fdt_dead_xyo, double* g_dead, double* gsum_delta, size_t* cleaned);
+
+/* ---- multi-GPU (target-sharded, source-replicated) -------------------------- */
+/* This context computes epsilon/convective/diffusive only for its slice of the leaf groups
+ * (balanced by near-pair count); the caller all-gathers the slices between phases. */
+int vvgpu_set_shard(vvgpu_ctx* ctx, int rank, int nranks);
+/* particle range [*first, *last) this rank owns after tree_build */
+int vvgpu_shard_range(vvgpu_ctx* ctx, size_t* first, size_t* last);
+/* device pointers of the SoA arrays (x y g vx vy ieps), for NCCL all-gathers by the host layer */
+int vvgpu_particle_arrays_dev(vvgpu_ctx* ctx, int list, double** arrays6, size_t* n);
+/* tell the context that ieps / (x,y,g) of non-owned particles were filled in by the caller */
+int vvgpu_after_exchange(vvgpu_ctx* ctx, int phase);
+int vvgpu_stream(vvgpu_ctx* ctx, void** cuda_stream);
+int vvgpu_synchronize(vvgpu_ctx* ctx);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+enum { VVGPU_T_BUILD = 0, VVGPU_T_LISTS, VVGPU_T_EPS, VVGPU_T_CONV, VVGPU_T_DIFF, VVGPU_T_MOVE, VVGPU_T_COUNT };
+/* CUDA-event milliseconds of the last call of each phase; launches = kernels launched since the
+ * last vvgpu_phase_times call */
+int vvgpu_phase_times(vvgpu_ctx* ctx, double* ms, uint64_t* launches);
+/* FP64 DFMA micro-benchmark: achieved TFLOP/s of a register-resident FMA chain on this device */
+int vvgpu_fp64_peak(vvgpu_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

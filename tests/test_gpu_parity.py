@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): tree build, particle order, interaction lists, epsilon and merge
+decisions BIT-EXACT; velocities and integral sums within 1e-10 relative, in fp64.
+The oracle here is oracle/port (C restatement, itself pinned bit-exact to the compiled reference
+by tests/test_oracle_port.py); where oracle/_ref travelled to the box the reference build is
+checked directly as well.
+"""
+import numpy as np
+import pytest
+
+import cases
+from cases import relerr, same
+
+pytestmark = pytest.mark.gpu
+
+VTOL = 1e-10  # relative tolerance on velocities / integral sums stated by north_star
+
+
+def run_pair(ctx, port, xyg, bodies=(), merge=True, re=600.0, dt=0.05, inf=(1.0, 0.0), far=8, stop=None):
+    """Drive oracle and GPU through the hot path (vvflow.cpp:246-257), comparing after every phase."""
+    bodies = list(bodies)
+    mn, mx = cases.tree_params(bodies)
+    pb = cases.port_bodies(port, bodies)
+    P = port.Port(xyg=xyg, bodies=pb)
+    from vvflow_b200 import vvhd
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    S.re, S.dt, S.inf_vx, S.inf_vy = re, dt, inf[0], inf[1]
+    tr = vvhd.TSortedTree(S, far, mn, mx)
+    eps, conv, diff, flow = vvhd.MEpsilonFast(S, tr), vvhd.MConvectiveFast(S, tr), vvhd.MDiffusiveFast(S, tr), vvhd.MFlowmove(S)
+    out = {}
+    try:
+        # ---- tree
+        P.tree_build(far, mn, mx)
+        tr.build()
+        d1, i1, nl1 = P.tree_export()
+        d2, i2, nl2 = ctx.tree_export()
+        assert nl1 == nl2 and d1.shape == d2.shape, (nl1, nl2, d1.shape, d2.shape)
+        assert same(d2[:, :4], d1[:, :4]), "node boxes differ"
+        assert same(i2[:, [0, 1, 2, 3, 4, 5]], i1[:, [0, 1, 6, 7, 8, 9]]), "node ranges / children / leaf order differ"
+        assert same(d2[:, 4:], d1[:, 4:]), "centres of mass differ"
+        assert same(S.VortexList[:, :3], P.rec48()[:, :3]), "permuted particle order differs"
+        assert same(ctx.get_permutation(), P.orig[: P.n]), "permutation differs"
+        l1, l2 = P.tree_lists(), ctx.tree_lists()
+        for a, b, name in zip(l2, l1, ("near_ptr", "near_idx", "far_ptr", "far_idx")):
+            assert same(a, b), f"interaction lists differ: {name}"
+        if bodies:
+            s1, s2 = P.tree_leaf_segments(), ctx.tree_leaf_segments()
+            assert same(s2[0], s1[0]) and same(s2[1], s1[1]), "leaf segment lists differ"
+        np1, nf1 = P.count_interactions()
+        np2, nf2 = ctx.count_interactions()
+        assert np1 == np2 and nf1 == nf2, ("group lists disagree with per-leaf lists", np1, np2, nf1, nf2)
+        out["near_pairs"], out["far_nodes"], out["leaves"] = np2, nf2, nl2
+        if stop == "tree":
+            return out
+        # ---- epsilon (+ merge)
+        m1 = P.epsilon(merge)
+        eps.CalcEpsilonFast(merge)
+        assert eps.Merged() == m1, ("merge count", eps.Merged(), m1)
+        a, b = S.VortexList, P.rec48()
+        assert same(a[:, :3], b[:, :3]), "merged positions / circulations differ"
+        assert same(a[:, 5], b[:, 5]), f"epsilon differs, max rel {relerr(a[:, 5], b[:, 5])}"
+        out["merged"] = m1
+        if stop == "eps":
+            return out
+        # ---- convective
+        P.convective(inf[0], inf[1], dt)
+        conv.process_all_lists()
+        a, b = S.VortexList, P.rec48()
+        out["conv_err"] = relerr(a[:, 3:5], b[:, 3:5])
+        assert out["conv_err"] <= VTOL, ("convective velocity", out["conv_err"])
+        # ---- diffusive
+        if np.isfinite(re):
+            P.diffusive(re)
+            diff.process_vort_list()
+            a, b = S.VortexList, P.rec48()
+            out["diff_err"] = relerr(a[:, 3:5], b[:, 3:5])
+            assert out["diff_err"] <= VTOL, ("diffusive velocity", out["diff_err"])
+            if bodies:
+                fr = np.concatenate([bd.fric for bd in bodies])
+                out["fric_err"] = relerr(fr, pb.a["fric"])
+                assert out["fric_err"] <= VTOL, ("fric", out["fric_err"])
+        # ---- move and clean
+        P.tree_destroy()
+        tr.destroy()
+        n1, c1 = P.move_and_clean(dt)
+        c2 = flow.move_and_clean(True)
+        a, b = S.VortexList, P.rec48()
+        assert a.shape[0] == n1 and c2 == c1, ("survivors / cleaned", a.shape[0], n1, c2, c1)
+        assert same(a[:, 2], b[:, 2]) and same(a[:, 5], b[:, 5]), "survivor g / eps differ"
+        assert same(a[:, 3:5], b[:, 3:5]), "v not zeroed"
+        out["pos_err"] = relerr(a[:, :2], b[:, :2])
+        assert out["pos_err"] <= VTOL
+        if bodies:
+            gs = np.concatenate([bd.gsum for bd in bodies])
+            assert relerr(gs, pb.a["gsum"]) <= VTOL
+            fd = np.concatenate([bd.fdt_dead for bd in bodies])
+            assert relerr(fd, pb.a["fdt_dead"][: fd.shape[0]]) <= VTOL
+            gd = np.array([bd.g_dead for bd in bodies])
+            assert relerr(gd, pb.a["g_dead"][: gd.shape[0]]) <= VTOL
+        return out
+    finally:
+        if tr.built:
+            tr.destroy()
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 33, 100, 1000, 5000])
+def test_small_clouds(ctx, port, n):
+    run_pair(ctx, port, cases.cloud(n, "gauss", "same", seed=n))
+
+
+def test_empty(ctx, port):
+    from vvflow_b200 import vvhd
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = np.zeros((0, 3))
+    tr = vvhd.TSortedTree(S, 8, 0.0)
+    tr.build()
+    assert ctx.tree_counts()[:2] == (1, 1)
+    vvhd.MEpsilonFast(S, tr).CalcEpsilonFast(True)
+    vvhd.MConvectiveFast(S, tr).process_all_lists()
+    vvhd.MDiffusiveFast(S, tr).process_vort_list()
+    tr.destroy()
+    assert vvhd.MFlowmove(S).move_and_clean(True) == 0
+    assert S.VortexList.shape == (0, 6)
+
+
+def test_gauss_same_sign_100k(ctx, port):
+    out = run_pair(ctx, port, cases.cloud(100_000, "gauss", "same", seed=7), re=1000.0, dt=0.005)
+    assert out["merged"] == 0
+
+
+def test_uniform_same_sign_50k(ctx, port):
+    run_pair(ctx, port, cases.cloud(50_000, "uniform", "same", seed=8), re=1000.0, dt=0.005)
+
+
+def test_duplicates_and_lines(ctx, port):
+    """coincident particles, particles on a line (degenerate boxes), zero-circulation particles"""
+    rng = np.random.default_rng(5)
+    a = cases.cloud(3000, "gauss", "same", seed=5)
+    a[:500, :2] = a[500:1000, :2]           # exact duplicates
+    a[1000:1500, 1] = 0.25                  # a horizontal line
+    a[1500:1600, 2] = 0.0                   # g == 0: skipped as source and as target
+    a[1600:1700, :2] = 1.5                  # 100 coincident
+    run_pair(ctx, port, a)
+    b = np.zeros((40, 3)); b[:, 0] = rng.uniform(0, 1, 40); b[:, 2] = 1.0  # all on y = 0
+    run_pair(ctx, port, b)
+
+
+@pytest.mark.parametrize("n,seed", [(200, 1), (2000, 2), (20000, 3)])
+def test_mixed_sign_merge(ctx, port, n, seed):
+    """BASELINE config 5b: order-dependent merging, ~23 % of the particles merge"""
+    out = run_pair(ctx, port, cases.cloud(n, "gauss", "mixed", seed=seed))
+    assert out["merged"] > 0
+
+
+def test_merge_disabled(ctx, port):
+    out = run_pair(ctx, port, cases.cloud(3000, "gauss", "mixed", seed=9), merge=False, re=float("inf"))
+    assert out["merged"] == 0
+
+
+@pytest.mark.parametrize("n,sign", [(300, "same"), (8000, "mixed"), (30000, "mixed")])
+def test_cylinder(ctx, port, n, sign):
+    """BASELINE config 1 geometry: cylinder R=0.5 with 350 segments, particles in a shell around it
+    (wall epsilon restriction, wall merge criterion, segment diffusion + fric, in-body removal)."""
+    body = cases.cylinder(0.5, 350)
+    out = run_pair(ctx, port, cases.around_cylinder(n, sign=sign, seed=n), bodies=[body])
+    assert out["merged"] >= 0
+
+
+def test_two_cylinders_moving(ctx, port):
+    """BASELINE config 4 geometry: two tandem cylinders, one with speed_slae != 0 and slip segments
+    (body_list_influence incl. the linear-source term)"""
+    b1 = cases.cylinder(0.5, 200, 0.0, 0.0)
+    b2 = cases.cylinder(0.5, 200, 2.0, 0.0)
+    b2.speed_slae = np.array([0.1, -0.05, 0.2])
+    b2.slip[:20] = 1
+    b2.g[:20] = 0.01
+    b2.axis = np.array([2.0, 0.0])
+    rng = np.random.default_rng(11)
+    n = 6000
+    xyg = np.zeros((n, 3))
+    xyg[:, 0] = rng.uniform(-1, 3.5, n); xyg[:, 1] = rng.uniform(-1.2, 1.2, n)
+    xyg[:, 2] = rng.uniform(-1, 1, n) / n
+    # a few particles hugging a segment of the moving body (exercise the near branch)
+    xyg[:50, 0] = 2.0 + 0.5005 * np.cos(np.linspace(0, 1, 50)); xyg[:50, 1] = 0.5005 * np.sin(np.linspace(0, 1, 50))
+    run_pair(ctx, port, xyg, bodies=[b1, b2])
+
+
+def test_against_reference_build(ctx, ref):
+    """same comparison directly against the reference's own compiled code, where it travelled"""
+    xyg = cases.cloud(20000, "gauss", "mixed", seed=21)
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    r.set_list(xyg)
+    mn, mx = r.tree_params(8)
+    r.tree_build()
+    from vvflow_b200 import vvhd
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.re, S.dt, S.inf_vx = 600.0, 0.05, 1.0
+    tr = vvhd.TSortedTree(S, 8, mn, mx)
+    tr.build()
+    assert same(S.VortexList[:, :3], r.get_list48()[:, :3])
+    m = r.epsilon(True)
+    e = vvhd.MEpsilonFast(S, tr); e.CalcEpsilonFast(True)
+    assert e.Merged() == m
+    assert same(S.VortexList[:, [0, 1, 2, 5]], r.get_list48()[:, [0, 1, 2, 5]])
+    r.convective(); vvhd.MConvectiveFast(S, tr).process_all_lists()
+    r.diffusive(); vvhd.MDiffusiveFast(S, tr).process_vort_list()
+    assert relerr(S.VortexList[:, 3:5], r.get_list48()[:, 3:5]) <= VTOL
+    r.tree_destroy(); tr.destroy()
+    r.move_and_clean(True); vvhd.MFlowmove(S).move_and_clean(True)
+    assert S.VortexList.shape == r.get_list48().shape
+    assert relerr(S.VortexList[:, :2], r.get_list48()[:, :2]) <= VTOL
+
+
+def test_error_behaviour(ctx):
+    """call-order errors mirror the reference (TSortedTree.cpp:234,286-288; MFlowmove.cpp:20-22)"""
+    from vvflow_b200 import capi, vvhd
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = cases.cloud(100)
+    tr = vvhd.TSortedTree(S, 8, 0.0)
+    with pytest.raises(capi.VVGpuError):
+        ctx.epsilon(True)           # tree is not built
+    with pytest.raises(ValueError):
+        tr.findNode((0.0, 0.0))
+    tr.build()
+    with pytest.raises(capi.VVGpuError):
+        ctx.tree_build()            # already built
+    with pytest.raises(capi.VVGpuError):
+        ctx.set_particles(np.zeros((3, 6)))
+    assert tr.findNode((0.0, 0.0)) >= 0
+    tr.destroy()
+    with pytest.raises(ValueError):
+        vvhd.MFlowmove(S).move_and_clean(True, collision=None)
+
+
+def test_properties_at_scale(ctx):
+    """BASELINE config 2 size (N = 1M): size-independent properties instead of a CPU oracle run.
+    permutation is a bijection; leaves tile the array; every particle lies inside its leaf box;
+    sum of g is conserved; velocity of a same-sign blob has the right circulation sense."""
+    from vvflow_b200 import vvhd
+    n = 1_000_000
+    xyg = cases.cloud(n, "gauss", "equal", seed=12345)
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.re, S.dt, S.inf_vx = 1000.0, 0.005, 0.0
+    tr = vvhd.TSortedTree(S, 8, 0.0)
+    tr.build()
+    perm = ctx.get_permutation()
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    v = S.VortexList
+    assert np.array_equal(v[:, :3], xyg[perm])
+    leaves = tr.getBottomNodes()
+    first, last = leaves[:, 4].astype(np.int64), leaves[:, 5].astype(np.int64)
+    assert first[0] == 0 and last[-1] == n and np.array_equal(first[1:], last[:-1])
+    assert np.max(last - first) < 16
+    lid = np.repeat(np.arange(leaves.shape[0]), last - first)
+    assert np.all(np.abs(v[:, 0] - leaves[lid, 0]) <= 0.5 * leaves[lid, 3] * (1 + 1e-15) + 1e-300)
+    assert np.all(np.abs(v[:, 1] - leaves[lid, 1]) <= 0.5 * leaves[lid, 2] * (1 + 1e-15) + 1e-300)
+    e = vvhd.MEpsilonFast(S, tr); e.CalcEpsilonFast(True)
+    assert e.Merged() == 0
+    vvhd.MConvectiveFast(S, tr).process_all_lists()
+    v = S.VortexList
+    assert np.all(np.isfinite(v)) and np.all(v[:, 5] > 0)
+    # Lamb-Oseen: azimuthal velocity u_theta(r) = G/(2 pi r) * (1 - exp(-r^2/2)), total G = 1
+    r = np.hypot(v[:, 0], v[:, 1])
+    ut = (-v[:, 1] * v[:, 3] + v[:, 0] * v[:, 4]) / r
+    sel = (r > 0.5) & (r < 2.0)
+    exact = (1 - np.exp(-r[sel] ** 2 / 2)) / (2 * np.pi * r[sel])
+    assert abs(np.mean(ut[sel] / exact) - 1) < 0.02
+    tr.destroy()
+    vvhd.MFlowmove(S).move_and_clean(True)
+    assert S.VortexList.shape[0] == n and abs(np.sum(S.VortexList[:, 2]) - 1.0) < 1e-9
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN)
+def test_golden_fixtures(ctx, name):
+    """the CUDA path against the vectors generated from the reference's own compiled code"""
+    from vvflow_b200 import vvhd
+    d = cases.golden(name)
+    bodies = cases.golden_bodies(d)
+    far, mn, mx = d["tree_params"]
+    re, dt, ivx, ivy = d["params"]
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = d["in48"]
+    S.BodyList = bodies
+    S.re, S.dt, S.inf_vx, S.inf_vy = re, dt, ivx, ivy
+    tr = vvhd.TSortedTree(S, int(far), mn, mx)
+    tr.build()
+    try:
+        dbl, idx, nl = ctx.tree_export()
+        assert nl == d["n_leaves"][0]
+        assert same(dbl, d["tree_dbl"])
+        assert same(idx[:, [0, 1, 2, 3, 4, 5]], d["tree_idx"][:, [0, 1, 6, 7, 8, 9]])
+        for a, k in zip(ctx.tree_lists(), ("near_ptr", "near_idx", "far_ptr", "far_idx")):
+            assert same(a, d[k]), k
+        assert same(S.VortexList, d["after_build"])
+        assert ctx.count_interactions() == (d["interactions"][0], d["interactions"][1])
+        e = vvhd.MEpsilonFast(S, tr); e.CalcEpsilonFast(True)
+        assert e.Merged() == d["merged"][0]
+        assert same(S.VortexList, d["after_eps"])
+        vvhd.MConvectiveFast(S, tr).process_all_lists()
+        assert relerr(S.VortexList[:, 3:5], d["after_conv"][:, 3:5]) <= VTOL
+        vvhd.MDiffusiveFast(S, tr).process_vort_list()
+        assert relerr(S.VortexList[:, 3:5], d["after_diff"][:, 3:5]) <= VTOL
+        if bodies:
+            fr = np.concatenate([b.fric for b in bodies])
+            assert relerr(fr, d["seg_after_diff"][:, 8] - d["seg_in"][:, 8]) <= 1e-9
+    finally:
+        tr.destroy()
+    cleaned = vvhd.MFlowmove(S).move_and_clean(True)
+    assert cleaned == d["cleaned"][0]
+    a = S.VortexList
+    assert a.shape == d["after_move"].shape
+    assert same(a[:, 2], d["after_move"][:, 2])
+    assert relerr(a[:, :2], d["after_move"][:, :2]) <= VTOL
+    if bodies:
+        gs = np.concatenate([b.gsum for b in bodies])
+        assert relerr(gs, d["seg_after_move"][:, 7] - d["seg_in"][:, 7]) <= 1e-9
+        assert relerr(bodies[0].fdt_dead, d["body_after_move"][0, 13:16] - d["body_in"][0, 13:16]) <= 1e-9

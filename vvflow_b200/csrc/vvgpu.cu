@@ -1,0 +1,914 @@
+// libvvgpu.so — context, host-side orchestration and the C ABI declared in include/vvgpu.h.
+// Device code lives in the vvgpu_*.cuh headers next to this file. There is no CPU fallback:
+// every entry point either runs the CUDA kernels or returns an error.
+#include "../../include/vvgpu.h"
+#include "vvgpu_move.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace vv;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <class T>
+    T* get(size_t n, bool* ok) {
+        size_t need = n * sizeof(T);
+        if (need == 0) need = sizeof(T);
+        if (need > bytes) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            size_t want = need + need / 4 + 256;
+            if (cudaMalloc(&p, want) != cudaSuccess) { bytes = 0; *ok = false; return nullptr; }
+            bytes = want;
+        }
+        return (T*)p;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct PSet {  // one SoA particle set
+    Buf x, y, g, vx, vy, ie, orig;
+    Particles view() const { return Particles{x.as<double>(), y.as<double>(), g.as<double>(), vx.as<double>(), vy.as<double>(), ie.as<double>()}; }
+    bool ensure(size_t n) {
+        bool ok = true;
+        x.get<double>(n, &ok); y.get<double>(n, &ok); g.get<double>(n, &ok);
+        vx.get<double>(n, &ok); vy.get<double>(n, &ok); ie.get<double>(n, &ok); orig.get<int>(n, &ok);
+        return ok;
+    }
+    void release() { x.release(); y.release(); g.release(); vx.release(); vy.release(); ie.release(); orig.release(); }
+};
+
+}  // namespace
+
+struct vvgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    cudaEvent_t ev0[VVGPU_T_COUNT], ev1[VVGPU_T_COUNT];
+    bool ev_valid[VVGPU_T_COUNT] = {};
+    int* h_pinned = nullptr;  // small pinned scratch for read-backs
+
+    // particles (vortex list)
+    size_t n = 0;
+    PSet ps[2];
+    int cur = 0;
+    Buf stage;  // AoS staging
+
+    // bodies
+    int nseg = 0, nbody = 0;
+    Buf s_rx, s_ry, s_cx, s_cy, s_dlx, s_dly, s_g, s_ie, s_slip, s_body, b_first, b_prop;
+    bool any_body_flow = false;
+    Buf d_fric, d_gsum, d_fdt, d_gdead, d_cleaned;
+
+    // tree
+    bool built = false;
+    int tn = 0, tnseg = 0;  // objects included in the built tree
+    int nnodes = 0, nleaves = 0, depth = 0, ngroups = 0;
+    double farc = 8;
+    std::vector<int> lvl;
+    Buf t_x, t_y, t_h, t_w, t_bb, t_first, t_last, t_sfirst, t_slast, t_ch1, t_parent, t_depth, t_status, t_axis,
+        t_nl, t_nn, t_lstart, t_pre, t_cmp, t_cmm, t_leafnode, t_pnode, t_snode[2], t_segperm[2], t_perm, t_tmpR;
+    int segcur = 0;
+    Buf scan_part, scan_out, flags;
+    Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
+    Buf g_ptr, g_leaf, g_mask, g_count, taylor, farcount, d_err;
+    bool lists_ready = false;
+    long long nentries = 0;
+    // epsilon
+    Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged;
+    Buf mA[6], mB[6];
+    Buf d_sinks, d_pairs;
+
+    // shard
+    int rank = 0, nranks = 1;
+    int shard_g0 = 0, shard_g1 = 0;
+
+    TreeDev T() {
+        TreeDev t;
+        t.x = t_x.as<double>(); t.y = t_y.as<double>(); t.h = t_h.as<double>(); t.w = t_w.as<double>();
+        t.bb = t_bb.as<u64>();
+        t.first = t_first.as<int>(); t.last = t_last.as<int>(); t.sfirst = t_sfirst.as<int>(); t.slast = t_slast.as<int>();
+        t.ch1 = t_ch1.as<int>(); t.parent = t_parent.as<int>(); t.depth = t_depth.as<int>();
+        t.status = t_status.as<unsigned char>(); t.axis = t_axis.as<unsigned char>();
+        t.nl = t_nl.as<int>(); t.nn = t_nn.as<int>(); t.lstart = t_lstart.as<int>(); t.pre = t_pre.as<int>();
+        t.cmp = t_cmp.as<double>(); t.cmm = t_cmm.as<double>();
+        t.leaf_node = t_leafnode.as<int>();
+        t.pnode = t_pnode.as<int>(); t.snode = t_snode[segcur].as<int>();
+        return t;
+    }
+    LeafDev Lv() {
+        return LeafDev{l_first.as<int>(), l_last.as<int>(), l_sfirst.as<int>(), l_slast.as<int>(), l_cx.as<double>(),
+                       l_cy.as<double>(), l_h.as<double>(), l_w.as<double>(), l_node.as<int>()};
+    }
+    GroupLists Gv() { return GroupLists{g_ptr.as<long long>(), g_leaf.as<int>(), g_mask.as<u32>()}; }
+    NearArgs near_args() {
+        NearArgs a;
+        a.P = ps[cur].view(); a.L = Lv(); a.G = Gv(); a.nleaves = nleaves; a.g0 = shard_g0;
+        a.seg_perm = t_segperm[segcur].as<int>();
+        a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
+        return a;
+    }
+};
+
+namespace {
+
+int fail(vvgpu_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(c, VVGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+#define CKLAUNCH()                                                                                   \
+    do {                                                                                             \
+        c->launches++;                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                                         \
+        if (e_ != cudaSuccess) return fail(c, VVGPU_ECUDA, std::string("launch: ") + cudaGetErrorString(e_) + " at " + std::to_string(__LINE__)); \
+    } while (0)
+#define NEED(ptr)                                                                                    \
+    do {                                                                                             \
+        if (!ok) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");                                  \
+    } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+struct PhaseTimer {
+    vvgpu_ctx* c; int ph;
+    PhaseTimer(vvgpu_ctx* c, int ph): c(c), ph(ph) { cudaEventRecord(c->ev0[ph], c->stream); }
+    ~PhaseTimer() { cudaEventRecord(c->ev1[ph], c->stream); c->ev_valid[ph] = true; }
+};
+
+// exclusive scan of a flag functor over [0,n) into c->scan_out (n+1 entries)
+template <class F>
+int scan_flags(vvgpu_ctx* c, F f, long long n, u32* out) {
+    bool ok = true;
+    int tiles = cdiv(std::max<long long>(n, 1), kScanTile);
+    u32* part = c->scan_part.get<u32>(tiles + 1, &ok);
+    NEED(part);
+    if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(u32), c->stream)); return 0; }
+    k_scan_reduce<<<tiles, kScanThreads, 0, c->stream>>>(f, n, part); CKLAUNCH();
+    k_scan_partials<<<1, 1024, 0, c->stream>>>(part, tiles); CKLAUNCH();
+    k_scan_apply<<<tiles, kScanThreads, 0, c->stream>>>(f, n, part, out); CKLAUNCH();
+    return 0;
+}
+
+int read_u32(vvgpu_ctx* c, const u32* d, u32* h) {
+    CK(cudaMemcpyAsync(c->h_pinned, d, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *h = *(u32*)c->h_pinned;
+    return 0;
+}
+
+constexpr int kMaxDepth = 4096;
+
+int alloc_tree(vvgpu_ctx* c, size_t cap, size_t n, size_t nseg) {
+    bool ok = true;
+    c->t_x.get<double>(cap, &ok); c->t_y.get<double>(cap, &ok); c->t_h.get<double>(cap, &ok); c->t_w.get<double>(cap, &ok);
+    c->t_bb.get<u64>(4 * cap, &ok);
+    c->t_first.get<int>(cap, &ok); c->t_last.get<int>(cap, &ok); c->t_sfirst.get<int>(cap, &ok); c->t_slast.get<int>(cap, &ok);
+    c->t_ch1.get<int>(cap, &ok); c->t_parent.get<int>(cap, &ok); c->t_depth.get<int>(cap, &ok);
+    c->t_status.get<unsigned char>(cap, &ok); c->t_axis.get<unsigned char>(cap, &ok);
+    c->t_pnode.get<int>(n, &ok); c->t_perm.get<int>(n, &ok); c->t_tmpR.get<int>(n, &ok);
+    for (int k = 0; k < 2; k++) { c->t_snode[k].get<int>(nseg, &ok); c->t_segperm[k].get<int>(nseg, &ok); }
+    c->scan_out.get<u32>(std::max(std::max(n, nseg), cap) + 2, &ok);
+    c->flags.get<u32>(std::max(n, cap) + 2, &ok);
+    NEED(ok);
+    return 0;
+}
+
+int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_node, unsigned mask) {
+    const int n = (mask & 1u) ? (int)c->n : 0;
+    const int nseg = (mask & 2u) ? c->nseg : 0;
+    cudaStream_t st = c->stream;
+    PSet& P = c->ps[c->cur];
+    const size_t cap = 2 * ((size_t)n + nseg) + 2;
+    int rc = alloc_tree(c, cap, n, nseg);
+    if (rc) return rc;
+    c->segcur = 0;
+    c->tn = n; c->tnseg = nseg; c->farc = (double)far_criteria;
+    TreeDev T = c->T();
+    BuildParams bp{min_node, max_node};
+    double *px = P.x.as<double>(), *py = P.y.as<double>(), *pg = P.g.as<double>();
+    const double *sx = c->s_rx.as<double>(), *sy = c->s_ry.as<double>();
+    int* perm = c->t_perm.as<int>();
+    u32* G = c->scan_out.as<u32>();
+    u32* splitflag = c->flags.as<u32>();
+
+    k_tree_init_root<<<1, 1, 0, st>>>(T, n, nseg); CKLAUNCH();
+    if (n) { CK(cudaMemsetAsync(T.pnode, 0, sizeof(int) * n, st)); k_iota<<<cdiv(n, 256), 256, 0, st>>>(perm, n); CKLAUNCH(); }
+    if (nseg) { CK(cudaMemsetAsync(T.snode, 0, sizeof(int) * nseg, st)); k_iota<<<cdiv(nseg, 256), 256, 0, st>>>(c->t_segperm[0].as<int>(), nseg); CKLAUNCH(); }
+    if (n + nseg) { k_tree_bbox<<<cdiv(n + nseg, 256), 256, 0, st>>>(T, px, py, n, sx, sy, c->t_segperm[0].as<int>(), nseg); CKLAUNCH(); }
+
+    c->lvl.clear();
+    c->lvl.push_back(0); c->lvl.push_back(1);
+    for (int d = 0;; d++) {
+        if (d > kMaxDepth) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels (degenerate input)");
+        const int a0 = c->lvl[d], a1 = c->lvl[d + 1], na = a1 - a0;
+        k_tree_decide<<<cdiv(na, 128), 128, 0, st>>>(T, a0, a1, bp, splitflag); CKLAUNCH();
+        rc = scan_flags(c, FlagArray{splitflag}, na, G);
+        if (rc) return rc;
+        k_tree_assign<<<cdiv(na, 128), 128, 0, st>>>(T, a0, a1, G); CKLAUNCH();
+        u32 nsplit = 0;
+        rc = read_u32(c, G + na, &nsplit);
+        if (rc) return rc;
+        if (nsplit == 0) break;
+        if ((size_t)a1 + 2 * (size_t)nsplit > cap) return fail(c, VVGPU_ELIMIT, "node capacity exceeded");
+        if (n) {
+            rc = scan_flags(c, PartFlag{T, px, py}, n, G);
+            if (rc) return rc;
+            k_tree_partition<<<cdiv(n, 256), 256, 0, st>>>(T, n, G, c->t_tmpR.as<int>()); CKLAUNCH();
+            k_tree_swap<<<cdiv(n, 256), 256, 0, st>>>(T, n, G, c->t_tmpR.as<int>(), px, py, pg, perm); CKLAUNCH();
+            k_tree_relabel<<<cdiv(n, 256), 256, 0, st>>>(T, n, G); CKLAUNCH();
+        }
+        if (nseg) {
+            const int* pin = c->t_segperm[c->segcur].as<int>();
+            rc = scan_flags(c, SegFlag{T, sx, sy, pin}, nseg, G);
+            if (rc) return rc;
+            k_tree_seg_scatter<<<cdiv(nseg, 256), 256, 0, st>>>(T, nseg, G, pin, c->t_segperm[c->segcur ^ 1].as<int>(),
+                                                               c->t_snode[c->segcur ^ 1].as<int>()); CKLAUNCH();
+            c->segcur ^= 1;
+            T = c->T();
+        }
+        k_tree_bbox<<<cdiv(n + nseg, 256), 256, 0, st>>>(T, px, py, n, sx, sy, c->t_segperm[c->segcur].as<int>(), nseg); CKLAUNCH();
+        c->lvl.push_back(a1 + 2 * (int)nsplit);
+    }
+    c->nnodes = c->lvl.back();
+    c->depth = (int)c->lvl.size() - 2;
+    const int nn = c->nnodes;
+    bool ok = true;
+    c->t_nl.get<int>(nn, &ok); c->t_nn.get<int>(nn, &ok); c->t_lstart.get<int>(nn, &ok); c->t_pre.get<int>(nn, &ok);
+    c->t_cmp.get<double>(3 * (size_t)nn, &ok); c->t_cmm.get<double>(3 * (size_t)nn, &ok);
+    c->t_leafnode.get<int>(nn, &ok);
+    NEED(ok);
+    T = c->T();
+    for (int d = c->depth; d >= 0; d--) {
+        int a0 = c->lvl[d], a1 = c->lvl[d + 1];
+        k_tree_up<<<cdiv(a1 - a0, 128), 128, 0, st>>>(T, a0, a1, px, py, pg); CKLAUNCH();
+    }
+    for (int d = 0; d <= c->depth; d++) {
+        int a0 = c->lvl[d], a1 = c->lvl[d + 1];
+        k_tree_down<<<cdiv(a1 - a0, 128), 128, 0, st>>>(T, a0, a1); CKLAUNCH();
+    }
+    u32 nl = 0;
+    rc = read_u32(c, (const u32*)T.nl, &nl);
+    if (rc) return rc;
+    c->nleaves = (int)nl;
+    c->ngroups = cdiv(c->nleaves, kGroupLeaves);
+    // the rest of each TObj follows the permutation
+    if (n) {
+        PSet& Q = c->ps[c->cur ^ 1];
+        if (!Q.ensure(c->n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+        k_tree_gather_rest<<<cdiv(n, 256), 256, 0, st>>>(n, perm, P.vx.as<double>(), P.vy.as<double>(), P.ie.as<double>(),
+                                                        P.orig.as<int>(), Q.vx.as<double>(), Q.vy.as<double>(),
+                                                        Q.ie.as<double>(), Q.orig.as<int>()); CKLAUNCH();
+        std::swap(P.vx, Q.vx); std::swap(P.vy, Q.vy); std::swap(P.ie, Q.ie); std::swap(P.orig, Q.orig);
+    }
+    // leaf records
+    c->l_first.get<int>(nl, &ok); c->l_last.get<int>(nl, &ok); c->l_sfirst.get<int>(nl, &ok); c->l_slast.get<int>(nl, &ok);
+    c->l_cx.get<double>(nl, &ok); c->l_cy.get<double>(nl, &ok); c->l_h.get<double>(nl, &ok); c->l_w.get<double>(nl, &ok);
+    c->l_node.get<int>(nl, &ok);
+    NEED(ok);
+    k_leaf_fill<<<cdiv(nl, 128), 128, 0, st>>>(T, c->Lv(), (int)nl); CKLAUNCH();
+    c->built = true;
+    c->lists_ready = false;
+    return 0;
+}
+
+constexpr int kStackCap = 1024;
+size_t trav_smem(int cap) { return (size_t)kTravWarps * ((size_t)cap * sizeof(int2) + (4 * 32 + 32 * 6) * sizeof(double)); }
+
+int lists_impl(vvgpu_ctx* c) {
+    if (c->lists_ready) return 0;
+    cudaStream_t st = c->stream;
+    bool ok = true;
+    const int ng = c->ngroups, nl = c->nleaves;
+    u32* gcount = c->g_count.get<u32>(ng + 1, &ok);
+    c->g_ptr.get<long long>(ng + 1, &ok);
+    double* taylor = c->taylor.get<double>(4 * (size_t)nl, &ok);
+    double* farcount = c->farcount.get<double>(nl, &ok);
+    int* derr = c->d_err.get<int>(1, &ok);
+    c->scan_out.get<u32>(ng + 2, &ok);
+    NEED(ok);
+    TreeDev T = c->T();
+    LeafDev L = c->Lv();
+    int cap = kStackCap;
+    size_t smem = trav_smem(cap);
+    CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
+    CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
+    CK(cudaMemsetAsync(derr, 0, sizeof(int), st));
+    const int grid = cdiv(ng, kTravWarps);
+    k_traverse<false><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr); CKLAUNCH();
+    u32* gs = c->scan_out.as<u32>();
+    int rc = scan_flags(c, FlagArray{gcount}, ng, gs);
+    if (rc) return rc;
+    u32 total = 0;
+    rc = read_u32(c, gs + ng, &total);
+    if (rc) return rc;
+    u32 e = 0;
+    rc = read_u32(c, (u32*)derr, &e);
+    if (rc) return rc;
+    if (e) return fail(c, VVGPU_ELIMIT, "near/far traversal stack overflow");
+    c->nentries = total;
+    c->g_leaf.get<int>(total, &ok); c->g_mask.get<u32>(total, &ok);
+    NEED(ok);
+    k_group_ptr<<<cdiv(ng + 1, 256), 256, 0, st>>>(gs, c->g_ptr.as<long long>(), ng); CKLAUNCH();
+    k_traverse<true><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr); CKLAUNCH();
+    c->lists_ready = true;
+    // shard: contiguous slices of groups balanced by entry count (a proxy for near pairs)
+    c->shard_g0 = 0; c->shard_g1 = ng;
+    if (c->nranks > 1) {
+        std::vector<long long> ptr(ng + 1);
+        CK(cudaMemcpyAsync(ptr.data(), c->g_ptr.p, sizeof(long long) * (ng + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        auto cut = [&](int r) {
+            long long want = (long long)((double)total * r / c->nranks);
+            return (int)(std::lower_bound(ptr.begin(), ptr.end(), want) - ptr.begin());
+        };
+        c->shard_g0 = (c->rank == 0) ? 0 : std::min(cut(c->rank), ng);
+        c->shard_g1 = (c->rank == c->nranks - 1) ? ng : std::min(cut(c->rank + 1), ng);
+    }
+    return 0;
+}
+
+template <class Op>
+int launch_near(vvgpu_ctx* c, Op op) {
+    int ng = c->shard_g1 - c->shard_g0;
+    if (ng <= 0) return 0;
+    k_near<Op><<<ng, kNearThreads, 0, c->stream>>>(c->near_args(), op); CKLAUNCH();
+    return 0;
+}
+
+MergeState mstate(Buf* b) {
+    return MergeState{b[0].as<int>(), b[1].as<int>(), b[2].as<int>(), b[3].as<double>(), b[4].as<double>(), b[5].as<double>()};
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+const char* vvgpu_strerror(int code) {
+    switch (code) {
+        case VVGPU_OK: return "ok";
+        case VVGPU_EINVAL: return "invalid argument";
+        case VVGPU_ESTATE: return "call out of order (tree not built / already built)";
+        case VVGPU_ECUDA: return "CUDA error";
+        case VVGPU_ENOMEM: return "out of device memory";
+        case VVGPU_ELIMIT: return "internal capacity exceeded";
+        default: return "unknown error";
+    }
+}
+const char* vvgpu_last_error(const vvgpu_ctx* c) { return c ? c->err.c_str() : ""; }
+
+int vvgpu_create(int device, vvgpu_ctx** out) {
+    if (!out) return VVGPU_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VVGPU_ECUDA;  // no CPU fallback
+    if (device < 0 || device >= ndev) return VVGPU_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return VVGPU_ECUDA;
+    vvgpu_ctx* c = new vvgpu_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
+    for (int k = 0; k < VVGPU_T_COUNT; k++) { cudaEventCreate(&c->ev0[k]); cudaEventCreate(&c->ev1[k]); }
+    if (cudaMallocHost((void**)&c->h_pinned, 256) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
+    *out = c;
+    return VVGPU_OK;
+}
+
+void vvgpu_destroy(vvgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Buf* all[] = {&c->stage, &c->s_rx, &c->s_ry, &c->s_cx, &c->s_cy, &c->s_dlx, &c->s_dly, &c->s_g, &c->s_ie, &c->s_slip,
+                  &c->s_body, &c->b_first, &c->b_prop, &c->d_fric, &c->d_gsum, &c->d_fdt, &c->d_gdead, &c->d_cleaned,
+                  &c->t_x, &c->t_y, &c->t_h, &c->t_w, &c->t_bb, &c->t_first, &c->t_last, &c->t_sfirst, &c->t_slast,
+                  &c->t_ch1, &c->t_parent, &c->t_depth, &c->t_status, &c->t_axis, &c->t_nl, &c->t_nn, &c->t_lstart,
+                  &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode, &c->t_pnode, &c->t_snode[0], &c->t_snode[1],
+                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags,
+                  &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
+                  &c->g_ptr, &c->g_leaf, &c->g_mask, &c->g_count, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
+                  &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs};
+    for (Buf* b : all) b->release();
+    for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
+    c->ps[0].release(); c->ps[1].release();
+    for (int k = 0; k < VVGPU_T_COUNT; k++) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int set_particles_common(vvgpu_ctx* c, int list, const void* src, size_t n, int rec_doubles) {
+    if (!c || list != VVGPU_LIST_VORTEX || (!src && n)) return fail(c, VVGPU_EINVAL, "set_particles: bad argument");
+    if (n > (size_t)std::numeric_limits<int>::max() / 4) return fail(c, VVGPU_EINVAL, "set_particles: too many particles");
+    if (c->built) return fail(c, VVGPU_ESTATE, "set_particles while the tree is built (the tree holds positions into the list)");
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* st = c->stage.get<double>(n * rec_doubles, &ok);
+    if (!ok || !c->ps[c->cur].ensure(n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    c->n = n;
+    if (n) {
+        CK(cudaMemcpyAsync(st, src, n * rec_doubles * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (rec_doubles == 6) k_unpack48<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
+        else k_unpack24<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
+        CKLAUNCH();
+        CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `src`
+    }
+    return 0;
+}
+int vvgpu_set_particles(vvgpu_ctx* c, int list, const vvgpu_obj* objs, size_t n) {
+    return set_particles_common(c, list, objs, n, 6);
+}
+int vvgpu_set_particles_xyg(vvgpu_ctx* c, int list, const double* xyg, size_t n) {
+    return set_particles_common(c, list, xyg, n, 3);
+}
+int vvgpu_particle_count(vvgpu_ctx* c, int list, size_t* n) {
+    if (!c || !n || list != VVGPU_LIST_VORTEX) return fail(c, VVGPU_EINVAL, "particle_count: bad argument");
+    *n = c->n;
+    return 0;
+}
+int vvgpu_get_particles(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t cap, size_t* n) {
+    if (!c || list != VVGPU_LIST_VORTEX) return fail(c, VVGPU_EINVAL, "get_particles: bad argument");
+    if (n) *n = c->n;
+    if (!out) return 0;
+    if (cap < c->n) return fail(c, VVGPU_EINVAL, "get_particles: buffer too small");
+    if (!c->n) return 0;
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* st = c->stage.get<double>(c->n * 6, &ok);
+    NEED(ok);
+    k_pack48<<<cdiv(c->n, 256), 256, 0, c->stream>>>((int)c->n, c->ps[c->cur].view(), st); CKLAUNCH();
+    CK(cudaMemcpyAsync(out, st, c->n * 48, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vvgpu_get_permutation(vvgpu_ctx* c, int list, int32_t* orig, size_t cap) {
+    if (!c || list != VVGPU_LIST_VORTEX || !orig || cap < c->n) return fail(c, VVGPU_EINVAL, "get_permutation: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (c->n) CK(cudaMemcpyAsync(orig, c->ps[c->cur].orig.p, c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vvgpu_set_bodies(vvgpu_ctx* c, const vvgpu_seg* segs, size_t nseg, const vvgpu_body* bodies, size_t nbody) {
+    if (!c || (nseg && !segs) || (nbody && !bodies)) return fail(c, VVGPU_EINVAL, "set_bodies: bad argument");
+    if (c->built) return fail(c, VVGPU_ESTATE, "set_bodies while the tree is built");
+    CK(cudaSetDevice(c->device));
+    std::vector<double> col[8];
+    std::vector<int> slip(nseg), body(nseg), bfirst(nbody + 1, 0);
+    for (auto& v : col) v.resize(nseg);
+    for (size_t i = 0; i < nseg; i++) {
+        const vvgpu_seg& s = segs[i];
+        col[0][i] = s.rx; col[1][i] = s.ry; col[2][i] = s.cx; col[3][i] = s.cy; col[4][i] = s.dlx; col[5][i] = s.dly;
+        col[6][i] = s.g; col[7][i] = s.ieps; slip[i] = s.slip; body[i] = s.body;
+        if (s.body < 0 || (size_t)s.body >= nbody) return fail(c, VVGPU_EINVAL, "set_bodies: segment with bad body index");
+    }
+    std::vector<double> bprop(16 * std::max<size_t>(nbody, 1), 0.0);
+    c->any_body_flow = false;
+    for (size_t b = 0; b < nbody; b++) {
+        const vvgpu_body& B = bodies[b];
+        if (B.first_seg < 0 || B.n_seg < 0 || (size_t)B.first_seg + B.n_seg > nseg ||
+            (b && B.first_seg != bfirst[b])) return fail(c, VVGPU_EINVAL, "set_bodies: bodies must tile the segment array in order");
+        bfirst[b] = B.first_seg; bfirst[b + 1] = B.first_seg + B.n_seg;
+        double* p = &bprop[16 * b];
+        p[0] = B.axis_x; p[1] = B.axis_y; p[2] = B.cofm_x; p[3] = B.cofm_y; p[4] = B.bl_x; p[5] = B.bl_y;
+        p[6] = B.tr_x; p[7] = B.tr_y; p[8] = B.disc_r2; p[9] = B.speed_x; p[10] = B.speed_y; p[11] = B.speed_o;
+        p[12] = B.inside_valid ? 1 : 0;
+        bool any_slip = false;
+        for (int s = bfirst[b]; s < bfirst[b + 1]; s++) any_slip |= slip[s] != 0;
+        p[13] = any_slip ? 1 : 0;
+        bool moving = !(std::fabs(B.speed_x) + std::fabs(B.speed_y) + std::fabs(B.speed_o) < 1E-10);
+        if (any_slip || moving) c->any_body_flow = true;
+    }
+    if (nbody && (size_t)bfirst[nbody] != nseg) return fail(c, VVGPU_EINVAL, "set_bodies: bodies must cover all segments");
+    bool ok = true;
+    Buf* dst[8] = {&c->s_rx, &c->s_ry, &c->s_cx, &c->s_cy, &c->s_dlx, &c->s_dly, &c->s_g, &c->s_ie};
+    for (int k = 0; k < 8; k++) {
+        double* d = dst[k]->get<double>(nseg, &ok);
+        NEED(ok);
+        if (nseg) CK(cudaMemcpyAsync(d, col[k].data(), nseg * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    int* d1 = c->s_slip.get<int>(nseg, &ok); int* d2 = c->s_body.get<int>(nseg, &ok);
+    int* d3 = c->b_first.get<int>(nbody + 1, &ok); double* d4 = c->b_prop.get<double>(bprop.size(), &ok);
+    c->d_fric.get<double>(nseg, &ok); c->d_gsum.get<double>(nseg, &ok);
+    c->d_fdt.get<double>(3 * std::max<size_t>(nbody, 1), &ok); c->d_gdead.get<double>(std::max<size_t>(nbody, 1), &ok);
+    NEED(ok);
+    if (nseg) {
+        CK(cudaMemcpyAsync(d1, slip.data(), nseg * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d2, body.data(), nseg * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMemcpyAsync(d3, bfirst.data(), (nbody + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d4, bprop.data(), bprop.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->nseg = (int)nseg; c->nbody = (int)nbody;
+    return 0;
+}
+
+int vvgpu_tree_build(vvgpu_ctx* c, int far_criteria, double min_node, double max_node, unsigned include_mask) {
+    if (!c) return VVGPU_EINVAL;
+    if (c->built) return fail(c, VVGPU_ESTATE, "Tree is already built");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    {
+        PhaseTimer t(c, VVGPU_T_BUILD);
+        rc = tree_build_impl(c, far_criteria, min_node, max_node, include_mask);
+    }
+    if (rc) return rc;
+    {
+        PhaseTimer t(c, VVGPU_T_LISTS);
+        rc = lists_impl(c);
+    }
+    if (rc) { c->built = false; return rc; }
+    return 0;
+}
+
+int vvgpu_tree_destroy(vvgpu_ctx* c) {
+    if (!c) return VVGPU_EINVAL;
+    c->built = false; c->lists_ready = false;
+    c->nnodes = c->nleaves = c->ngroups = 0;
+    return 0;
+}
+
+int vvgpu_tree_counts(vvgpu_ctx* c, size_t* n_nodes, size_t* n_leaves, size_t* depth) {
+    if (!c) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (n_nodes) *n_nodes = c->nnodes;
+    if (n_leaves) *n_leaves = c->nleaves;
+    if (depth) *depth = c->depth;
+    return 0;
+}
+
+int vvgpu_tree_export(vvgpu_ctx* c, double* dbl, int64_t* idx, size_t cap_nodes) {
+    if (!c || !dbl || !idx) return fail(c, VVGPU_EINVAL, "tree_export: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (cap_nodes < (size_t)c->nnodes) return fail(c, VVGPU_EINVAL, "tree_export: buffer too small");
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    const size_t nn = c->nnodes;
+    double* st = c->stage.get<double>(nn * 18, &ok);
+    NEED(ok);
+    long long* si = (long long*)(st + nn * 10);
+    k_tree_export<<<cdiv(nn, 128), 128, 0, c->stream>>>(c->T(), (int)nn, st, si); CKLAUNCH();
+    CK(cudaMemcpyAsync(dbl, st, nn * 10 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(idx, si, nn * 8 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vvgpu_tree_lists(vvgpu_ctx* c, int64_t* near_ptr, int64_t* near_idx, size_t near_cap, int64_t* far_ptr,
+                     int64_t* far_idx, size_t far_cap) {
+    if (!c || !near_ptr || !far_ptr) return fail(c, VVGPU_EINVAL, "tree_lists: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int nl = c->nleaves;
+    bool ok = true;
+    Buf bn, bf, bnp, bfp, bni, bfi;
+    u32* ncount = bn.get<u32>(nl + 1, &ok); u32* fcount = bf.get<u32>(nl + 1, &ok);
+    u32* nptr = bnp.get<u32>(nl + 2, &ok); u32* fptr = bfp.get<u32>(nl + 2, &ok);
+    int* derr = c->d_err.get<int>(1, &ok);
+    int rc = 0;
+    std::vector<u32> hn(nl + 1), hf(nl + 1);
+    auto cleanup = [&]() { bn.release(); bf.release(); bnp.release(); bfp.release(); bni.release(); bfi.release(); };
+    if (!ok) { cleanup(); return fail(c, VVGPU_ENOMEM, "cudaMalloc failed"); }
+    cudaMemsetAsync(derr, 0, sizeof(int), st);
+    k_lists_dfs<false><<<cdiv(nl, 128), 128, 0, st>>>(c->T(), c->Lv(), nl, c->farc, ncount, fcount, nullptr, nullptr, nullptr, nullptr, derr);
+    c->launches++;
+    rc = scan_flags(c, FlagArray{ncount}, nl, nptr);
+    if (!rc) rc = scan_flags(c, FlagArray{fcount}, nl, fptr);
+    if (rc) { cleanup(); return rc; }
+    cudaMemcpyAsync(hn.data(), nptr, sizeof(u32) * (nl + 1), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hf.data(), fptr, sizeof(u32) * (nl + 1), cudaMemcpyDeviceToHost, st);
+    int herr = 0;
+    cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); return fail(c, VVGPU_ECUDA, "tree_lists: sync failed"); }
+    if (herr) { cleanup(); return fail(c, VVGPU_ELIMIT, "tree_lists: tree deeper than the export stack"); }
+    for (int i = 0; i <= nl; i++) { near_ptr[i] = hn[i]; far_ptr[i] = hf[i]; }
+    if (near_idx && far_idx) {
+        if (near_cap < hn[nl] || far_cap < hf[nl]) { cleanup(); return fail(c, VVGPU_EINVAL, "tree_lists: buffers too small"); }
+        long long* ni = bni.get<long long>(hn[nl], &ok); long long* fi = bfi.get<long long>(hf[nl], &ok);
+        if (!ok) { cleanup(); return fail(c, VVGPU_ENOMEM, "cudaMalloc failed"); }
+        k_lists_dfs<true><<<cdiv(nl, 128), 128, 0, st>>>(c->T(), c->Lv(), nl, c->farc, ncount, fcount, nptr, fptr, ni, fi, derr);
+        c->launches++;
+        if (hn[nl]) cudaMemcpyAsync(near_idx, ni, sizeof(long long) * hn[nl], cudaMemcpyDeviceToHost, st);
+        if (hf[nl]) cudaMemcpyAsync(far_idx, fi, sizeof(long long) * hf[nl], cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { cleanup(); return fail(c, VVGPU_ECUDA, "tree_lists: sync failed"); }
+    }
+    cleanup();
+    return 0;
+}
+
+int vvgpu_tree_leaf_segments(vvgpu_ctx* c, int64_t* ptr, int64_t* idx, size_t cap) {
+    if (!c || !ptr) return fail(c, VVGPU_EINVAL, "tree_leaf_segments: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    const int nl = c->nleaves;
+    std::vector<int> sf(nl), sl(nl), perm(c->tnseg);
+    CK(cudaMemcpyAsync(sf.data(), c->l_sfirst.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sl.data(), c->l_slast.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->stream));
+    if (c->tnseg) CK(cudaMemcpyAsync(perm.data(), c->t_segperm[c->segcur].p, sizeof(int) * c->tnseg, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int64_t p = 0;
+    for (int l = 0; l < nl; l++) {
+        ptr[l] = p;
+        for (int k = sf[l]; k < sl[l]; k++) {
+            if (idx) { if ((size_t)p >= cap) return fail(c, VVGPU_EINVAL, "tree_leaf_segments: buffer too small"); idx[p] = perm[k]; }
+            p++;
+        }
+    }
+    ptr[nl] = p;
+    return 0;
+}
+
+int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes) {
+    if (!c) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    const int ng = c->ngroups, nl = c->nleaves;
+    double* d = c->d_pairs.get<double>(ng + 1, &ok);
+    NEED(ok);
+    k_count_pairs<<<std::max(ng, 1), 128, 0, c->stream>>>(c->Lv(), nl, ng, c->Gv(), c->ps[c->cur].g.as<double>(), d); CKLAUNCH();
+    std::vector<double> h(ng), f(nl);
+    CK(cudaMemcpyAsync(h.data(), d, sizeof(double) * ng, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(f.data(), c->farcount.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double s = 0, t = 0;
+    for (double v : h) s += v;
+    for (double v : f) t += v;
+    if (near_pairs) *near_pairs = s;
+    if (far_nodes) *far_nodes = t;
+    return 0;
+}
+
+int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
+    if (!c) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    PhaseTimer t(c, VVGPU_T_EPS);
+    cudaStream_t st = c->stream;
+    if (merged) *merged = 0;
+    const int n = c->tn, nl = c->nleaves;
+    if (n == 0) return 0;
+    bool ok = true;
+    PSet& P = c->ps[c->cur];
+    const bool walls = c->tnseg > 0;
+    double *lcrit = nullptr, *lrestr = nullptr;
+    if (walls || merge) {
+        lcrit = c->lcrit.get<double>(nl, &ok); lrestr = c->lrestr.get<double>(nl, &ok);
+        int* latt = c->latt.get<int>(nl, &ok);
+        NEED(ok);
+        BodySegs B{c->tnseg, walls ? c->nbody : 0, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_dlx.as<double>(),
+                   c->s_dly.as<double>(), c->b_first.as<int>()};
+        k_leaf_wall<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->Gv(), c->t_segperm[c->segcur].as<int>(), B, merge, lcrit, lrestr, latt); CKLAUNCH();
+    }
+    int* dchg = c->d_changed.get<int>(2, &ok);
+    NEED(ok);
+    if (!merge) {
+        EpsOp<false> op{MergeState{}, MergeState{}, nullptr, lrestr, nullptr, P.ie.as<double>(), dchg};
+        return launch_near(c, op);
+    }
+    // merge replay is order-dependent: every rank replays it over ALL groups (it is replicated, not sharded)
+    struct ShardGuard {
+        vvgpu_ctx* c; int g0, g1;
+        ShardGuard(vvgpu_ctx* c): c(c), g0(c->shard_g0), g1(c->shard_g1) { c->shard_g0 = 0; c->shard_g1 = c->ngroups; }
+        ~ShardGuard() { c->shard_g0 = g0; c->shard_g1 = g1; }
+    } guard(c);
+    // merging: iterate the tentative solution to its fixed point (see MergeState in vvgpu_near.cuh)
+    double* ietmp = c->ie_tmp.get<double>(n, &ok);
+    unsigned char* dyn = c->dyn.get<unsigned char>(n, &ok);
+    for (int k = 0; k < 3; k++) { c->mA[k].get<int>(n, &ok); c->mB[k].get<int>(n, &ok); }
+    for (int k = 3; k < 6; k++) { c->mA[k].get<double>(n, &ok); c->mB[k].get<double>(n, &ok); }
+    NEED(ok);
+    CK(cudaMemcpyAsync(ietmp, P.ie.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    bool haveA = false;
+    int rounds = 0;
+    for (;; rounds++) {
+        if (rounds > n + 2) return fail(c, VVGPU_ELIMIT, "merge fixed point did not converge");
+        MergeState A = haveA ? mstate(c->mA) : MergeState{};
+        MergeState B = mstate(c->mB);
+        k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH();
+        CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
+        EpsOp<false> op{A, B, lcrit, lrestr, dyn, ietmp, dchg};
+        int rc = launch_near(c, op);
+        if (rc) return rc;
+        u32 changed = 0;
+        rc = read_u32(c, (u32*)dchg, &changed);
+        if (rc) return rc;
+        if (!changed) break;  // B reproduces A
+        for (int k = 0; k < 6; k++) std::swap(c->mA[k], c->mB[k]);
+        haveA = true;
+        k_merge_dyn<<<cdiv(n, 256), 256, 0, st>>>(n, mstate(c->mA), dyn); CKLAUNCH();
+    }
+    if (!haveA) {  // no merge anywhere: every epsilon is final
+        std::swap(c->ie_tmp, P.ie);
+        return 0;
+    }
+    // epsilon of the initiators at their merged position (the recursive epsv call, :169), then commit
+    MergeState A = mstate(c->mA);
+    EpsOp<true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
+    int rc = launch_near(c, opf);
+    if (rc) return rc;
+    std::swap(c->ie_tmp, P.ie);  // absorbed-before-turn particles kept their old value in ie_tmp (never written)
+    CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
+    k_merge_apply<<<cdiv(n, 256), 256, 0, st>>>(n, A, P.x.as<double>(), P.y.as<double>(), P.g.as<double>(), dchg); CKLAUNCH();
+    u32 nm = 0;
+    rc = read_u32(c, (u32*)dchg, &nm);
+    if (rc) return rc;
+    if (merged) *merged = (int)nm;
+    return 0;
+}
+
+int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, const double* sinks_xyg, size_t nsink) {
+    if (!c || (nsink && !sinks_xyg)) return fail(c, VVGPU_EINVAL, "convective: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    PhaseTimer t(c, VVGPU_T_CONV);
+    if (c->tn == 0) return 0;
+    bool ok = true;
+    double* ds = c->d_sinks.get<double>(3 * nsink, &ok);
+    NEED(ok);
+    if (nsink) CK(cudaMemcpyAsync(ds, sinks_xyg, 3 * nsink * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ConvOp op{inf_vx, inf_vy, dt * k1_Pi, c->taylor.as<double>(), ds, (int)nsink};
+    int rc = launch_near(c, op);
+    if (rc) return rc;
+    if (c->any_body_flow && c->nbody) {
+        BodyFull B{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                   c->s_dlx.as<double>(), c->s_dly.as<double>(), c->s_g.as<double>(), c->s_ie.as<double>(),
+                   c->s_slip.as<int>(), c->b_first.as<int>(), c->b_prop.as<double>()};
+        k_body_influence<<<cdiv(c->tn, 128), 128, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), B); CKLAUNCH();
+    }
+    if (nsink) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
+    if (!c) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    {
+        PhaseTimer t(c, VVGPU_T_DIFF);
+        if (c->nseg) CK(cudaMemsetAsync(c->d_fric.p, 0, sizeof(double) * c->nseg, c->stream));
+        if (c->tn) {
+            DiffOp op{re, c->d_fric.as<double>()};
+            int rc = launch_near(c, op);
+            if (rc) return rc;
+        }
+    }
+    if (fric_out && c->nseg) {
+        CK(cudaMemcpyAsync(fric_out, c->d_fric.p, sizeof(double) * c->nseg, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int vvgpu_move_and_clean(vvgpu_ctx* c, double dt_eff, double remove_eps, int remove_in_body, double* fdt_dead_xyo,
+                         double* g_dead, double* gsum_delta, size_t* cleaned) {
+    if (!c) return VVGPU_EINVAL;
+    if (c->built) return fail(c, VVGPU_ESTATE, "move_and_clean while the tree is built (call tree_destroy first, vvflow.cpp:255-257)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int n = (int)c->n;
+    bool ok = true;
+    unsigned long long* dcl = c->d_cleaned.get<unsigned long long>(1, &ok);
+    c->d_fdt.get<double>(3 * std::max(c->nbody, 1), &ok); c->d_gdead.get<double>(std::max(c->nbody, 1), &ok);
+    c->d_gsum.get<double>(std::max(c->nseg, 1), &ok);
+    u32* keep = c->flags.get<u32>(n + 2, &ok);
+    u32* scan = c->scan_out.get<u32>(n + 2, &ok);
+    PSet& P = c->ps[c->cur];
+    PSet& Q = c->ps[c->cur ^ 1];
+    if (!ok || !Q.ensure(n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    u32 nkeep = 0;
+    {
+        PhaseTimer t(c, VVGPU_T_MOVE);
+        CK(cudaMemsetAsync(dcl, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(c->d_fdt.p, 0, sizeof(double) * 3 * std::max(c->nbody, 1), st));
+        CK(cudaMemsetAsync(c->d_gdead.p, 0, sizeof(double) * std::max(c->nbody, 1), st));
+        CK(cudaMemsetAsync(c->d_gsum.p, 0, sizeof(double) * std::max(c->nseg, 1), st));
+        if (n) {
+            BodyGeom B{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                       c->b_first.as<int>(), c->b_prop.as<double>()};
+            k_move_flag<<<cdiv(n, 256), 256, 0, st>>>(n, P.view(), dt_eff, remove_eps, remove_in_body, B, keep, c->d_fdt.as<double>(),
+                                                     c->d_gdead.as<double>(), c->d_gsum.as<double>(), dcl); CKLAUNCH();
+            int rc = scan_flags(c, FlagArray{keep}, n, scan);
+            if (rc) return rc;
+            k_move_compact<<<cdiv(n, 256), 256, 0, st>>>(n, scan, P.view(), P.orig.as<int>(), Q.view(), Q.orig.as<int>()); CKLAUNCH();
+            rc = read_u32(c, scan + n, &nkeep);
+            if (rc) return rc;
+            c->cur ^= 1;
+            c->n = nkeep;
+        }
+    }
+    if (fdt_dead_xyo && c->nbody) CK(cudaMemcpyAsync(fdt_dead_xyo, c->d_fdt.p, sizeof(double) * 3 * c->nbody, cudaMemcpyDeviceToHost, st));
+    if (g_dead && c->nbody) CK(cudaMemcpyAsync(g_dead, c->d_gdead.p, sizeof(double) * c->nbody, cudaMemcpyDeviceToHost, st));
+    if (gsum_delta && c->nseg) CK(cudaMemcpyAsync(gsum_delta, c->d_gsum.p, sizeof(double) * c->nseg, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_pinned + 16, dcl, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (cleaned) *cleaned = (size_t) * (unsigned long long*)(c->h_pinned + 16);
+    return 0;
+}
+
+int vvgpu_set_shard(vvgpu_ctx* c, int rank, int nranks) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, VVGPU_EINVAL, "set_shard: bad argument");
+    if (c->built) return fail(c, VVGPU_ESTATE, "set_shard while the tree is built");
+    c->rank = rank; c->nranks = nranks;
+    return 0;
+}
+int vvgpu_shard_range(vvgpu_ctx* c, size_t* first, size_t* last) {
+    if (!c || !first || !last) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    int lf = c->shard_g0 * kGroupLeaves, ll = std::min(c->shard_g1 * kGroupLeaves, c->nleaves);
+    int a = 0, b = 0;
+    if (lf < ll) {
+        CK(cudaMemcpyAsync(c->h_pinned, c->l_first.as<int>() + lf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_pinned + 1, c->l_last.as<int>() + (ll - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        a = c->h_pinned[0]; b = c->h_pinned[1];
+    } else if (c->nleaves) {
+        // empty slice: place it at the boundary so that slices still tile [0,n)
+        int at = std::min(lf, c->nleaves - 1);
+        CK(cudaMemcpyAsync(c->h_pinned, (lf >= c->nleaves ? c->l_last.as<int>() : c->l_first.as<int>()) + at, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        a = b = c->h_pinned[0];
+    }
+    *first = a; *last = b;
+    return 0;
+}
+int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* n) {
+    if (!c || list != VVGPU_LIST_VORTEX || !arrays6) return VVGPU_EINVAL;
+    Particles p = c->ps[c->cur].view();
+    arrays6[0] = p.x; arrays6[1] = p.y; arrays6[2] = p.g; arrays6[3] = p.vx; arrays6[4] = p.vy; arrays6[5] = p.ie;
+    if (n) *n = c->n;
+    return 0;
+}
+int vvgpu_after_exchange(vvgpu_ctx* c, int) { return c ? 0 : VVGPU_EINVAL; }
+int vvgpu_stream(vvgpu_ctx* c, void** s) {
+    if (!c || !s) return VVGPU_EINVAL;
+    *s = (void*)c->stream;
+    return 0;
+}
+int vvgpu_synchronize(vvgpu_ctx* c) {
+    if (!c) return VVGPU_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vvgpu_phase_times(vvgpu_ctx* c, double* ms, uint64_t* launches) {
+    if (!c) return VVGPU_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < VVGPU_T_COUNT; k++) {
+        float f = 0;
+        if (c->ev_valid[k]) cudaEventElapsedTime(&f, c->ev0[k], c->ev1[k]);
+        if (ms) ms[k] = f;
+    }
+    if (launches) *launches = c->launches;
+    c->launches = 0;
+    return 0;
+}
+
+int vvgpu_fp64_peak(vvgpu_ctx* c, double* tflops) {
+    if (!c || !tflops) return VVGPU_EINVAL;
+    CK(cudaSetDevice(c->device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+    bool ok = true;
+    double* out = c->stage.get<double>((size_t)blocks * threads, &ok);
+    NEED(ok);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a, c->stream);
+        k_fp64_peak<<<blocks, threads, 0, c->stream>>>(out, iters); c->launches++;
+        cudaEventRecord(b, c->stream);
+        CK(cudaEventSynchronize(b));
+        float msf = 0;
+        cudaEventElapsedTime(&msf, a, b);
+        double fl = 2.0 * 8 * (double)iters * blocks * threads;
+        if (rep) best = std::max(best, fl / (msf * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

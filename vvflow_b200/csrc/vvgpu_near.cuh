@@ -1,0 +1,574 @@
+// K3 / K4 / K5 — the three near-field passes over the same pair set:
+//   EpsOp   MEpsilonFast::epsv + merge decision        (libvvhd/src/MEpsilonFast.cpp:128-173)
+//   ConvOp  MConvectiveFast::near_nodes_influence      (libvvhd/src/MConvectiveFast.cpp:116-137)
+//           + the per-particle assembly of process_all_lists (:76-86)
+//   DiffOp  MDiffusiveFast::process_vort_list          (libvvhd/src/MDiffusiveFast.cpp:8-48,93-123)
+//
+// One CTA owns one group of 32 consecutive leaves. Its targets are a contiguous slice of the
+// permuted particle array (one target per thread, in chunks of kNearThreads); the group's near
+// source leaves are streamed through shared memory in tiles and every thread walks the tile with
+// broadcast loads. A source leaf is applied to a target only if the leaf's bit is set in the
+// entry's mask, i.e. exactly the (leaf, near leaf) pairs of the reference; a warp skips entries
+// none of its leaves see.
+#pragma once
+#include "vvgpu_lists.cuh"
+
+namespace vv {
+
+constexpr int kNearThreads = 256;
+constexpr int kNearEB = 64;     // list entries per batch
+constexpr int kNearTS = 1024;   // source particles per shared-memory tile
+
+struct Particles {
+    double *x, *y, *g, *vx, *vy, *ie;
+};
+
+struct NearArgs {
+    Particles P;
+    LeafDev L;
+    GroupLists G;
+    int nleaves;
+    int g0;  // first group of this launch (shard offset)
+    // segments (diffusive / epsilon wall terms)
+    const int* seg_perm;
+    const double *srx, *sry, *sdlx, *sdly;
+};
+
+struct NearShared {
+    double2 sxy[kNearTS];
+    double2 sab[kNearTS];
+    int epre[kNearEB + 1];
+    int epf[kNearEB];
+    u32 emk[kNearEB];
+    int esf[kNearEB], esl[kNearEB];
+    int bounds[kGroupLeaves + 1];
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
+    __shared__ NearShared S;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = A.g0 + blockIdx.x;
+    const int l0 = g * kGroupLeaves;
+    const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
+    __syncthreads();
+    const int t0 = S.bounds[0], t1 = S.bounds[nl];
+    const long long e0 = A.G.ptr[g], e1 = A.G.ptr[g + 1];
+
+    for (int tb = t0; tb < t1; tb += kNearThreads) {
+        const int i = tb + tid;
+        const bool inrange = i < t1;
+        int lt = 0;
+        if (inrange) {  // largest k with bounds[k] <= i
+            int lo = 0, hi = nl - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (S.bounds[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            lt = lo;
+        }
+        typename Op::Tgt tg;
+        const bool live = op.init(tg, A, i, l0 + lt, inrange);
+        // leaves covered by this warp's live targets
+        int ltmin = live ? lt : 64, ltmax = live ? lt : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ltmin = min(ltmin, __shfl_xor_sync(0xffffffffu, ltmin, o));
+            ltmax = max(ltmax, __shfl_xor_sync(0xffffffffu, ltmax, o));
+        }
+        u32 wmask = 0;
+        if (ltmax >= 0) {
+            u32 hi = (ltmax == 31) ? 0xffffffffu : ((1u << (ltmax + 1)) - 1u);
+            wmask = hi & ~((1u << ltmin) - 1u);
+        }
+        const u32 mybit = 1u << lt;
+
+        for (long long eb = e0; eb < e1; eb += kNearEB) {
+            const int ne = (int)min((long long)kNearEB, e1 - eb);
+            __syncthreads();  // everyone is done with the previous batch / tile
+            if (tid < 32) {
+                int c[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    int e = 2 * tid + k;
+                    c[k] = 0;
+                    if (e < ne) {
+                        int sl = A.G.leaf[eb + e];
+                        int f = A.L.first[sl];
+                        c[k] = A.L.last[sl] - f;
+                        S.epf[e] = f;
+                        S.emk[e] = A.G.mask[eb + e];
+                        S.esf[e] = A.L.sfirst[sl];
+                        S.esl[e] = A.L.slast[sl];
+                    }
+                }
+                int s = c[0] + c[1], inc = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                int ex = inc - s;
+                S.epre[2 * tid] = ex;
+                S.epre[2 * tid + 1] = ex + c[0];
+                if (tid == 31) S.epre[kNearEB] = inc;
+            }
+            __syncthreads();
+            const int total = S.epre[ne];
+            for (int s0 = 0; s0 < total; s0 += kNearTS) {
+                if (s0 > 0) __syncthreads();
+                const int nsrc = min(kNearTS, total - s0);
+                for (int k = tid; k < nsrc; k += kNearThreads) {
+                    int F = s0 + k;
+                    int lo = 0, hi = ne - 1;  // largest e with epre[e] <= F
+                    while (lo < hi) {
+                        int mid = (lo + hi + 1) >> 1;
+                        if (S.epre[mid] <= F) lo = mid; else hi = mid - 1;
+                    }
+                    int j = S.epf[lo] + (F - S.epre[lo]);
+                    op.stage(A, j, S.sxy[k], S.sab[k]);
+                }
+                __syncthreads();
+                if (wmask) {
+                    for (int e = 0; e < ne; e++) {
+                        const u32 m = S.emk[e];
+                        if (!(m & wmask)) continue;
+                        int k0 = max(S.epre[e], s0) - s0, k1 = min(S.epre[e + 1], s0 + kNearTS) - s0;
+                        if (k0 >= k1) continue;
+                        if (live && (m & mybit)) {
+                            const int jbase = S.epf[e] + (s0 + k0 - S.epre[e]);
+                            op.run(tg, A, &S.sxy[k0], &S.sab[k0], k1 - k0, jbase);
+                        }
+                    }
+                }
+            }
+            if (Op::kSegments && wmask) {
+                for (int e = 0; e < ne; e++) {
+                    const u32 m = S.emk[e];
+                    if (S.esl[e] > S.esf[e] && live && (m & mybit)) op.segments(tg, A, S.esf[e], S.esl[e]);
+                }
+            }
+        }
+        if (live) op.finish(tg, A, i, l0 + lt);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K4
+struct ConvOp {
+    static constexpr bool kSegments = false;
+    double inf_vx, inf_vy, eps2_div_srcg;
+    const double* taylor;  // 4 per leaf
+    const double* sinks;   // (x,y,g) triples
+    int nsink;
+    struct Tgt { double x, y, rx, ry; };
+
+    __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
+        t.rx = t.ry = 0; t.x = t.y = 0;
+        if (!inrange) return false;
+        if (A.P.g[i] == 0) return false;  // `if (!lobj->g) continue`, MConvectiveFast.cpp:78
+        t.x = A.P.x[i]; t.y = A.P.y[i];
+        return true;
+    }
+    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
+        double g = A.P.g[j];
+        xy = make_double2(A.P.x[j], A.P.y[j]);
+        // eps^2 = sqr(1./_1_eps) of the SOURCE (:119); a g==0 source is skipped by the reference (:130)
+        double e = 1. / A.P.ie[j];
+        ab = (g == 0) ? make_double2(0., 1.) : make_double2(g, e * e);
+    }
+    // rotl(dr) * g / (|dr|^2 + eps^2): reciprocal by rcp.approx + one third-order correction
+    // (relative error ~ e0^3, e0 <= 2^-20: below 1 ulp; exactness is not required of velocities)
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
+                                        int) const {
+        double rx = t.rx, ry = t.ry;
+        const double tx = t.x, ty = t.y;
+#pragma unroll 4
+        for (int k = 0; k < n; k++) {
+            double2 p = xy[k], q = ab[k];
+            double dx = tx - p.x, dy = ty - p.y;
+            double den = fma(dx, dx, fma(dy, dy, q.y));
+            double r0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
+            double e = fma(-den, r0, 1.0);
+            double e2 = fma(e, e, e);
+            double gr = q.x * r0;
+            double w = fma(gr, e2, gr);
+            rx = fma(-dy, w, rx);
+            ry = fma(dx, w, ry);
+        }
+        t.rx = rx; t.ry = ry;
+    }
+    __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
+    __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
+        double vx = inf_vx + t.rx * k1_2Pi, vy = inf_vy + t.ry * k1_2Pi;
+        if (nsink) {  // sink_list_influence, :153-170
+            double sx = 0, sy = 0;
+            for (int k = 0; k < nsink; k++) {
+                double dx = t.x - sinks[3 * k], dy = t.y - sinks[3 * k + 1], sg = sinks[3 * k + 2];
+                double q = sg / (dx * dx + dy * dy + eps2_div_srcg * fabs(sg));
+                sx += dx * q; sy += dy * q;
+            }
+            vx += sx * k1_2Pi; vy += sy * k1_2Pi;
+        }
+        const double* T = taylor + 4ll * leaf;  // :84-85
+        double dlx = t.x - A.L.cx[leaf], dly = t.y - A.L.cy[leaf];
+        vx += T[0] + T[2] * dlx + T[3] * dly;
+        vy += T[1] + T[3] * dlx - T[2] * dly;
+        A.P.vx[i] += vx;
+        A.P.vy[i] += vy;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ K5
+struct DiffOp {
+    static constexpr bool kSegments = true;
+    double re;
+    double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
+    struct Tgt { double x, y, ie, ie2, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
+
+    __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
+        t.S1 = t.S2x = t.S2y = t.S0 = t.S3x = t.S3y = 0;
+        t.x = t.y = t.ie = t.ie2 = t.g = 0; t.pos = false;
+        if (!inrange) return false;
+        double g = A.P.g[i];
+        if (g == 0) return false;
+        t.x = A.P.x[i]; t.y = A.P.y[i]; t.g = g; t.ie = A.P.ie[i]; t.ie2 = t.ie * t.ie; t.pos = g > 0;
+        return true;
+    }
+    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
+        xy = make_double2(A.P.x[j], A.P.y[j]);
+        ab = make_double2(A.P.g[j], 0.);
+    }
+    // vortex_influence, :93-105. The cut-off decision `-|dr|*_1_eps < -8` is replayed exactly;
+    // a squared-distance pre-test with a 1e-6 safety margin rejects the ~95 % of pairs far outside.
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
+                                        int) const {
+        for (int k = 0; k < n; k++) {
+            double2 p = xy[k];
+            double sg = ab[k].x;
+            if (sg == 0 || ((sg > 0) != t.pos)) continue;  // same sign only (:95); NaN g never matches
+            double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
+            double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+            if (d2 * t.ie2 > 64.0001) continue;
+            if (VV_ADD(fabs(dx), fabs(dy)) < 1E-10) continue;  // TVec::iszero
+            double drabs = sqrt(d2);
+            double exparg = -VV_MUL(drabs, t.ie);
+            if (exparg < -8.) continue;
+            double i1tmp = sg * exp(exparg);
+            double q = i1tmp / drabs;
+            t.S2x = fma(dx, q, t.S2x);
+            t.S2y = fma(dy, q, t.S2y);
+            t.S1 += i1tmp;
+        }
+    }
+    // segment_influence, :107-123
+    __device__ __forceinline__ void segments(Tgt& t, const NearArgs& A, int sf, int sl) const {
+        for (int k = sf; k < sl; k++) {
+            int s = A.seg_perm[k];
+            double dx = VV_SUB(t.x, A.srx[s]), dy = VV_SUB(t.y, A.sry[s]);
+            double drabs2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+            double drabs = sqrt(drabs2);
+            double exparg = -VV_MUL(drabs, t.ie);
+            if (exparg < -8.) continue;
+            double expres = exp(exparg);
+            double dSx = -A.sdly[s], dSy = A.sdlx[s];
+            t.S3x += dSx * expres; t.S3y += dSy * expres;
+            t.S0 += (drabs * t.ie + 1) / drabs2 * (dx * dSx + dy * dSy) * expres;
+            atomicAdd(&fric[s], t.ie2 * t.g * expres * sqrt(dSx * dSx + dSy * dSy));
+        }
+    }
+    __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int) const {
+        double S1 = t.S1;
+        if ((sgn(S1) != sgn(t.g)) || (fabs(S1) < fabs(0.1 * t.g))) S1 = 0.1 * t.g;  // :41
+        double k2 = t.ie / (re * S1);
+        double vx = k2 * t.S2x, vy = k2 * t.S2y;
+        double S0 = t.S0;
+        if (S0 > kPi) S0 = kPi;
+        double k3 = t.ie2 / (re * (k2Pi - S0));
+        vx += k3 * t.S3x; vy += k3 * t.S3y;
+        A.P.vx[i] += vx;
+        A.P.vy[i] += vy;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ K3
+// Merge bookkeeping ("timeline"): the reference processes particles in array order and a merge
+// (MergeVortexes, MEpsilonFast.cpp:111-126) changes what LATER particles see. A tentative solution
+// says, per particle q: init[q] (q merges when its turn comes), part[q] (with whom), (nx,ny,ng)[q]
+// (its state afterwards) and absby[q] (index of the initiator that absorbed q, INT_MAX if none).
+// A target i then sees source q as: skipped if absby[q] < i; post-merge state if init[q] && q < i;
+// original state otherwise. EpsOp recomputes every particle's outcome under the tentative solution;
+// the host iterates until the solution reproduces itself, which is the sequential result (the
+// prefix of correct outcomes grows by at least one particle per round).
+struct MergeState {
+    int* absby;
+    int* init;
+    int* part;
+    double *nx, *ny, *ng;
+};
+constexpr int kNoAbs = 0x7fffffff;
+
+template <bool FINAL>
+struct EpsOp {
+    static constexpr bool kSegments = false;
+    MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
+    MergeState B_;      // recomputed solution (decision mode only)
+    const double* lcrit;   // per leaf merge_criteria_sq (NaN: never merge)
+    const double* lrestr;  // per leaf eps_restriction
+    const unsigned char* dyn;  // per particle: has a timeline entry in A_
+    double* ie_out;
+    int* changed;
+    struct Tgt { double x, y, r1, r2; int i, i1, i2; };
+
+    __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
+        t.r1 = t.r2 = DBL_MAX; t.i1 = t.i2 = -1; t.i = i; t.x = t.y = 0;
+        if (!inrange) return false;
+        if (A.P.g[i] == 0) return false;  // MEpsilonFast.cpp:51
+        if (A_.absby) {
+            if (FINAL) {
+                if (!A_.init[i]) return false;
+                t.x = A_.nx[i]; t.y = A_.ny[i];
+                return true;
+            }
+            if (A_.absby[i] < i) {  // absorbed before its turn: g == 0 by then, _1_eps stays as it was
+                if (A_.init[i]) atomicAdd(changed, 1);
+                ie_out[i] = A.P.ie[i];
+                return false;
+            }
+        }
+        t.x = A.P.x[i]; t.y = A.P.y[i];
+        return true;
+    }
+    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
+        xy = make_double2(A.P.x[j], A.P.y[j]);
+        ab = make_double2(A.P.g[j], (A_.absby && dyn[j]) ? 1. : 0.);
+    }
+    // state of source j as target i sees it; false = not a neighbour candidate
+    __device__ __forceinline__ bool seen(int j, int i, double& sx, double& sy, double& sg) const {
+        int ab = A_.absby[j];
+        if (FINAL ? (ab <= i) : (ab < i)) return false;
+        if (A_.init[j] && j < i) { sx = A_.nx[j]; sy = A_.ny[j]; sg = A_.ng[j]; }
+        return sg != 0;
+    }
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
+                                        int jbase) const {
+        for (int k = 0; k < n; k++) {
+            const int j = jbase + k;
+            double sx = xy[k].x, sy = xy[k].y, sg = ab[k].x;
+            if (sg == 0 || j == t.i) continue;  // :140
+            if (ab[k].y != 0 && !seen(j, t.i, sx, sy, sg)) continue;
+            double dx = VV_SUB(t.x, sx), dy = VV_SUB(t.y, sy);
+            double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+            // two smallest in (distance, index) order == the reference's first-seen-wins scan (:143-151)
+            if (d < t.r1 || (d == t.r1 && j < t.i1)) {
+                t.r2 = t.r1; t.i2 = t.i1; t.r1 = d; t.i1 = j;
+            } else if (d < t.r2 || (d == t.r2 && j < t.i2)) {
+                t.r2 = d; t.i2 = j;
+            }
+        }
+    }
+    __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
+    __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
+        const double restr = lrestr ? lrestr[leaf] : 0.;
+        double eps;
+        if (t.i1 < 0) eps = DBL_MIN;           // :155
+        else if (t.i2 < 0) eps = sqrt(t.r1);   // :157
+        else {
+            eps = sqrt(t.r2);
+            const double crit = lcrit ? lcrit[leaf] : __longlong_as_double(0x7ff8000000000000ll);
+            if (!FINAL && !isnan(crit)) {
+                // neighbour states as seen (for the sign rule and the merged position)
+                double x1 = A.P.x[t.i1], y1 = A.P.y[t.i1], g1 = A.P.g[t.i1];
+                double x2 = 0, y2 = 0, g2 = A.P.g[t.i2];
+                if (A_.absby) { seen(t.i1, i, x1, y1, g1); seen(t.i2, i, x2, y2, g2); }
+                const double gi = A.P.g[i];
+                if ((t.r1 < crit) || ((sgn(g1) == sgn(g2)) && (sgn(g1) != sgn(gi)))) {  // :162-166
+                    // MergeVortexes(lv, lv1), :111-126
+                    double nx = t.x, ny = t.y;
+                    if (sgn(gi) == sgn(g1)) {
+                        double r = 1. / VV_ADD(gi, g1);
+                        nx = VV_MUL(VV_ADD(VV_MUL(t.x, gi), VV_MUL(x1, g1)), r);
+                        ny = VV_MUL(VV_ADD(VV_MUL(t.y, gi), VV_MUL(y1, g1)), r);
+                    } else if (fabs(gi) < fabs(g1)) { nx = x1; ny = y1; }
+                    double ng = VV_ADD(gi, g1);
+                    bool diff = true;
+                    if (A_.absby && A_.init[i] && A_.part[i] == t.i1 &&
+                        __double_as_longlong(A_.nx[i]) == __double_as_longlong(nx) &&
+                        __double_as_longlong(A_.ny[i]) == __double_as_longlong(ny) &&
+                        __double_as_longlong(A_.ng[i]) == __double_as_longlong(ng)) diff = false;
+                    B_.init[i] = 1; B_.part[i] = t.i1; B_.nx[i] = nx; B_.ny[i] = ny; B_.ng[i] = ng;
+                    atomicMin(&B_.absby[t.i1], i);
+                    if (diff) atomicAdd(changed, 1);
+                    return;  // its epsilon comes from the FINAL pass at the merged position
+                }
+            }
+        }
+        if (!FINAL && A_.absby && A_.init[i]) atomicAdd(changed, 1);  // assumed a merge that does not happen
+        ie_out[i] = 1.0 / std_max(eps, restr);  // :52
+    }
+};
+
+// write the converged merges back into the particle arrays
+__global__ void k_merge_apply(int n, MergeState M, double* x, double* y, double* g, int* nmerged) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool ini = M.init[i] != 0;
+    if (ini) { x[i] = M.nx[i]; y[i] = M.ny[i]; g[i] = M.ng[i]; }
+    if (M.absby[i] != kNoAbs) g[i] = 0;
+    unsigned b = __ballot_sync(__activemask(), ini);
+    if (ini && (threadIdx.x & 31) == (__ffs(b) - 1)) atomicAdd(nmerged, __popc(b));
+}
+__global__ void k_merge_clear(int n, MergeState M) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    M.absby[i] = kNoAbs; M.init[i] = 0; M.part[i] = -1;
+}
+__global__ void k_merge_dyn(int n, MergeState M, unsigned char* dyn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dyn[i] = (M.init[i] != 0 || M.absby[i] != kNoAbs) ? 1 : 0;
+}
+
+// Per-leaf wall parameters of CalcEpsilonFast (MEpsilonFast.cpp:26-47) with nearestBodySegment
+// (:214-253). One thread per leaf; the 32 leaves of a group read the same list entries.
+struct BodySegs {
+    int nseg, nbody;
+    const double *rx, *ry, *dlx, *dly;
+    const int* bfirst;  // nbody + 1
+};
+__global__ void k_leaf_wall(LeafDev L, int nleaves, GroupLists G, const int* __restrict__ seg_perm, BodySegs B,
+                            int merge, double* lcrit, double* lrestr, int* latt) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    const int g = l / kGroupLeaves;
+    const u32 bit = 1u << (l % kGroupLeaves);
+    const double px = L.cx[l], py = L.cy[l];
+    double res = DBL_MAX;
+    int att = -1, aleaf = 0x7fffffff, apos = 0x7fffffff;
+    // nearest among the segments of the near leaves; ties resolve to the first in (leaf, list) order,
+    // which is the order the reference scans them in (strict `<`, :229)
+    for (long long e = G.ptr[g]; e < G.ptr[g + 1]; e++) {
+        if (!(G.mask[e] & bit)) continue;
+        int sl = G.leaf[e];
+        for (int k = L.sfirst[sl]; k < L.slast[sl]; k++) {
+            int s = seg_perm[k];
+            double dx = VV_SUB(px, B.rx[s]), dy = VV_SUB(py, B.ry[s]);
+            double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+            if (d < res || (d == res && att >= 0 && (sl < aleaf || (sl == aleaf && k < apos)))) {
+                res = d; att = s; aleaf = sl; apos = k;
+            }
+        }
+    }
+    if (att < 0) {
+        for (int ib = 0; ib < B.nbody; ib++) {
+            for (int s = B.bfirst[ib]; s < B.bfirst[ib + 1]; s++) {
+                double dx = VV_SUB(px, B.rx[s]), dy = VV_SUB(py, B.ry[s]);
+                double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+                if (d < res) { res = d; att = s; }
+                else s += 9;  // the reference's skip-ahead (:248)
+            }
+        }
+    }
+    double crit, restr = 0;
+    if (merge) {
+        crit = 0;
+        if (att >= 0) {
+            double dl2 = VV_ADD(VV_MUL(B.dlx[att], B.dlx[att]), VV_MUL(B.dly[att], B.dly[att]));
+            double dx = VV_SUB(px, B.rx[att]), dy = VV_SUB(py, B.ry[att]);
+            double dist = sqrt(VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy)));
+            crit = VV_MUL(VV_MUL(0.16, dl2), VV_ADD(1., dist));  // :33
+        }
+    } else crit = __longlong_as_double(0x7ff8000000000000ll);
+    if (att >= 0) {
+        double dl = sqrt(VV_ADD(VV_MUL(B.dlx[att], B.dlx[att]), VV_MUL(B.dly[att], B.dly[att])));
+        restr = VV_MUL(dl, (1.0 / 3.0));  // :45-47
+    }
+    lcrit[l] = crit; lrestr[l] = restr; latt[l] = att;
+}
+
+// MConvectiveFast::body_list_influence (MConvectiveFast.cpp:172-215) for every particle; only
+// launched when a body has slip segments or a non-zero speed_slae.
+struct BodyFull {
+    int nseg, nbody;
+    const double *rx, *ry, *cx, *cy, *dlx, *dly, *g, *ie;
+    const int* slip;
+    const int* bfirst;
+    const double* bprop;  // per body 16 doubles (vvgpu_body as doubles, see vvgpu.cu)
+};
+__device__ __forceinline__ void cplx_mul(double ar, double ai, double br, double bi, double& cr, double& ci) {
+    cr = ar * br - ai * bi; ci = ar * bi + ai * br;
+}
+__device__ __forceinline__ void cplx_div(double ar, double ai, double br, double bi, double& cr, double& ci) {
+    double d = br * br + bi * bi;
+    cr = (ar * br + ai * bi) / d; ci = (ai * br - ar * bi) / d;
+}
+// SegmentInfluence_linear_source, :440-457
+__device__ __forceinline__ void linear_source(double px, double py, double rx, double ry, double dlx, double dly,
+                                              double q1, double q2, double& ox, double& oy) {
+    double z1r = px - (rx - dlx * 0.5), z1i = py - (ry - dly * 0.5);
+    double z2r = px - (rx + dlx * 0.5), z2i = py - (ry + dly * 0.5);
+    // conj(q2*z1 - q1*z2) / conj(dz)
+    double ar = q2 * z1r - q1 * z2r, ai = -(q2 * z1i - q1 * z2i);
+    double br, bi;
+    cplx_div(ar, ai, dlx, -dly, br, bi);
+    // log(conj(z2)/conj(z1))
+    double cr, ci;
+    cplx_div(z2r, -z2i, z1r, -z1i, cr, ci);
+    double lr = 0.5 * log(cr * cr + ci * ci), li = atan2(ci, cr);
+    double mr, mi;
+    cplx_mul(br, bi, lr, li, mr, mi);
+    cplx_div((q2 - q1) - mr, -mi, dlx, -dly, ox, oy);
+}
+__global__ void k_body_influence(int n, Particles P, BodyFull B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (P.g[i] == 0) return;
+    const double px = P.x[i], py = P.y[i];
+    double rx = 0, ry = 0;
+    for (int ib = 0; ib < B.nbody; ib++) {
+        const double* bp = B.bprop + 16 * ib;
+        const int f = B.bfirst[ib], e = B.bfirst[ib + 1];
+        if (bp[13] != 0) {  // any slip segment (TBody::get_slip)
+            for (int s = f; s < e; s++) {
+                if (!B.slip[s]) continue;
+                double dx = px - B.rx[s], dy = py - B.ry[s];
+                double ee = 1. / B.ie[s];
+                double k = B.g[s] / (dx * dx + dy * dy + ee * ee);
+                rx += -dy * k; ry += dx * k;
+            }
+        }
+        const double sx = bp[9], sy = bp[10], so = bp[11], ax = bp[0], ay = bp[1];
+        if (!(fabs(sx) + fabs(sy) + fabs(so) < 1E-10)) {
+            for (int s = f; s < e; s++) {
+                double dx = px - B.rx[s], dy = py - B.ry[s];
+                double drabs2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+                double dlx = B.dlx[s], dly = B.dly[s];
+                if (drabs2 < VV_ADD(VV_MUL(dlx, dlx), VV_MUL(dly, dly))) {
+                    double ux = B.cx[s] - ax, uy = B.cy[s] - ay;
+                    double v1x = sx - so * uy, v1y = sy + so * ux;
+                    double g1 = -(v1x * dlx + v1y * dly), q1 = -(-v1y * dlx + v1x * dly);
+                    double wx = B.cx[s] + dlx - ax, wy = B.cy[s] + dly - ay;
+                    double v2x = sx - so * wy, v2y = sy + so * wx;
+                    double g2 = -(v2x * dlx + v2y * dly), q2 = -(-v2y * dlx + v2x * dly);
+                    double ix, iy;
+                    linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, g1, g2, ix, iy);
+                    rx += -iy; ry += ix;
+                    linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, q1, q2, ix, iy);
+                    rx += ix; ry += iy;
+                } else {
+                    double ux = B.rx[s] - ax, uy = B.ry[s] - ay;
+                    double vx = sx - so * uy, vy = sy + so * ux;
+                    double gg = -(vx * dlx + vy * dly), q = -(-vy * dlx + vx * dly);
+                    double r = 1. / drabs2;
+                    rx += (dx * q - dy * gg) * r;
+                    ry += (dy * q + dx * gg) * r;
+                }
+            }
+        }
+    }
+    P.vx[i] += rx * k1_2Pi;
+    P.vy[i] += ry * k1_2Pi;
+}
+
+}  // namespace vv

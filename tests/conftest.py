@@ -36,3 +36,14 @@ def ctx():
     c = capi.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(autouse=True)
+def _fresh_tree(request):
+    """a failed GPU test must not leave the shared context with a built tree"""
+    yield
+    if "ctx" in request.fixturenames:
+        try:
+            request.getfixturevalue("ctx").tree_destroy()
+        except Exception:
+            pass

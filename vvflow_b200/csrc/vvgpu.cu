@@ -84,6 +84,10 @@ struct vvgpu_ctx {
     Buf scan_part, scan_out, flags;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
     Buf g_ptr, g_leaf, g_mask, g_count, taylor, farcount, d_err;
+    Buf u_group, u_first, u_sbase, u_tmp, near_scratch;
+    std::vector<int> h_ufirst;
+    int nunits = 0;
+    size_t nslots = 0;
     bool lists_ready = false;
     long long nentries = 0;
     // epsilon
@@ -115,7 +119,10 @@ struct vvgpu_ctx {
     GroupLists Gv() { return GroupLists{g_ptr.as<long long>(), g_leaf.as<int>(), g_mask.as<u32>()}; }
     NearArgs near_args() {
         NearArgs a;
-        a.P = ps[cur].view(); a.L = Lv(); a.G = Gv(); a.nleaves = nleaves; a.g0 = shard_g0;
+        a.P = ps[cur].view(); a.L = Lv(); a.G = Gv(); a.nleaves = nleaves;
+        a.U = Units{u_group.as<int>(), u_first.as<int>(), u_sbase.as<u32>()};
+        a.scratch = near_scratch.p;
+        a.u0 = h_ufirst.empty() ? 0 : h_ufirst[shard_g0];
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
         return a;
@@ -329,27 +336,50 @@ int lists_impl(vvgpu_ctx* c) {
     k_group_ptr<<<cdiv(ng + 1, 256), 256, 0, st>>>(gs, c->g_ptr.as<long long>(), ng); CKLAUNCH();
     k_traverse<true><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr); CKLAUNCH();
     c->lists_ready = true;
-    // shard: contiguous slices of groups balanced by entry count (a proxy for near pairs)
+    // work units (<= kUnitEntries list entries each) and the scratch slots of multi-unit groups
+    u32* nun = c->u_tmp.get<u32>(2 * (size_t)ng + 2, &ok);
+    u32* nsl = nun + ng + 1;
+    int* ufirst = c->u_first.get<int>(ng + 1, &ok);
+    u32* sbase = c->u_sbase.get<u32>(ng + 1, &ok);
+    NEED(ok);
+    k_unit_count<<<cdiv(ng, 128), 128, 0, st>>>(L, c->Gv(), nl, ng, nun, nsl); CKLAUNCH();
+    rc = scan_flags(c, FlagArray{nun}, ng, (u32*)ufirst);
+    if (!rc) rc = scan_flags(c, FlagArray{nsl}, ng, sbase);
+    if (rc) return rc;
+    c->h_ufirst.resize(ng + 1);
+    CK(cudaMemcpyAsync(c->h_ufirst.data(), ufirst, sizeof(int) * (ng + 1), cudaMemcpyDeviceToHost, st));
+    u32 nslots = 0;
+    rc = read_u32(c, sbase + ng, &nslots);
+    if (rc) return rc;
+    c->nunits = c->h_ufirst[ng];
+    c->nslots = nslots;
+    int* ugroup = c->u_group.get<int>(c->nunits, &ok);
+    c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
+    NEED(ok);
+    k_unit_fill<<<cdiv(ng, 128), 128, 0, st>>>(ng, ufirst, ugroup); CKLAUNCH();
+    // shard: contiguous slices of groups balanced by unit count (units bound the work per CTA)
     c->shard_g0 = 0; c->shard_g1 = ng;
     if (c->nranks > 1) {
-        std::vector<long long> ptr(ng + 1);
-        CK(cudaMemcpyAsync(ptr.data(), c->g_ptr.p, sizeof(long long) * (ng + 1), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         auto cut = [&](int r) {
-            long long want = (long long)((double)total * r / c->nranks);
-            return (int)(std::lower_bound(ptr.begin(), ptr.end(), want) - ptr.begin());
+            int want = (int)((double)c->nunits * r / c->nranks);
+            return (int)(std::lower_bound(c->h_ufirst.begin(), c->h_ufirst.end(), want) - c->h_ufirst.begin());
         };
         c->shard_g0 = (c->rank == 0) ? 0 : std::min(cut(c->rank), ng);
-        c->shard_g1 = (c->rank == c->nranks - 1) ? ng : std::min(cut(c->rank + 1), ng);
+        c->shard_g1 = (c->rank == c->nranks - 1) ? ng : std::min(std::max(cut(c->rank + 1), c->shard_g0), ng);
     }
     return 0;
 }
 
 template <class Op>
 int launch_near(vvgpu_ctx* c, Op op) {
-    int ng = c->shard_g1 - c->shard_g0;
-    if (ng <= 0) return 0;
-    k_near<Op><<<ng, kNearThreads, 0, c->stream>>>(c->near_args(), op); CKLAUNCH();
+    static_assert(sizeof(typename Op::Part) <= sizeof(DiffOp::Part), "scratch is sized for the largest Part");
+    const int g0 = c->shard_g0, g1 = c->shard_g1;
+    if (g1 <= g0) return 0;
+    const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
+    k_near<Op><<<nu, kNearThreads, 0, c->stream>>>(c->near_args(), op); CKLAUNCH();
+    if (nu > g1 - g0) {  // some group has more than one unit
+        k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
+    }
     return 0;
 }
 
@@ -403,7 +433,8 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_ptr, &c->g_leaf, &c->g_mask, &c->g_count, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
-                  &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs};
+                  &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
+                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
     c->ps[0].release(); c->ps[1].release();

@@ -96,10 +96,10 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
             double nx = T.x[n], ny = T.y[n];
             double nhw = VV_ADD(T.h[n], T.w[n]);
             c1 = T.ch1[n];
-#pragma unroll 4
-            for (int l = 0; l < nl; l++)
+            for (u32 mm = em; mm; mm &= mm - 1) {  // only the leaves that still see this subtree
+                const int l = __ffs(mm) - 1;
                 if (is_far(nx, ny, nhw, lcx[l], lcy[l], lh[l], lw[l], farc)) farm |= (1u << l);
-            farm &= em;
+            }
             nearm = em & ~farm;
             if (FILL && farm) {
                 cm[lane * 6 + 0] = T.cmp[3ll * n + 0]; cm[lane * 6 + 1] = T.cmp[3ll * n + 1];

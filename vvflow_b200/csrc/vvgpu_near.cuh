@@ -15,20 +15,32 @@
 
 namespace vv {
 
-constexpr int kNearThreads = 256;
-constexpr int kNearEB = 64;     // list entries per batch
-constexpr int kNearTS = 1024;   // source particles per shared-memory tile
+constexpr int kNearThreads = 512;   // >= 32 leaves x 15 particles: one pass over the sources per group
+constexpr int kNearEB = 64;         // list entries per batch
+constexpr int kNearTS = 1024;       // source particles per shared-memory tile
+constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the serial path of one thread)
 
 struct Particles {
     double *x, *y, *g, *vx, *vy, *ie;
+};
+
+// Work units: a group whose list is longer than kUnitEntries is cut into several units (a few
+// fringe leaves see tens of thousands of near leaves). Units of such a group
+// park their partial per-target state in `scratch`; k_near_finalize combines them in unit order.
+struct Units {
+    const int* group;       // unit -> group
+    const int* first;       // group -> first unit (ngroups + 1)
+    const u32* sbase;       // group -> first scratch slot (ngroups + 1)
 };
 
 struct NearArgs {
     Particles P;
     LeafDev L;
     GroupLists G;
+    Units U;
+    void* scratch;
     int nleaves;
-    int g0;  // first group of this launch (shard offset)
+    int u0;  // first unit of this launch (shard offset)
     // segments (diffusive / epsilon wall terms)
     const int* seg_perm;
     const double *srx, *sry, *sdlx, *sdly;
@@ -48,13 +60,18 @@ template <class Op>
 __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
     __shared__ NearShared S;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int g = A.g0 + blockIdx.x;
+    const int u = A.u0 + blockIdx.x;
+    const int g = A.U.group[u];
+    const int chunk = u - A.U.first[g];
+    const bool multi = (A.U.first[g + 1] - A.U.first[g]) > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
-    const long long e0 = A.G.ptr[g], e1 = A.G.ptr[g + 1];
+    const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
+    const long long e1 = min(A.G.ptr[g + 1], e0 + kUnitEntries);
+    typename Op::Part* scratch = (typename Op::Part*)A.scratch;
 
     for (int tb = t0; tb < t1; tb += kNearThreads) {
         const int i = tb + tid;
@@ -150,8 +167,52 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
                 }
             }
         }
-        if (live) op.finish(tg, A, i, l0 + lt);
+        if (multi) {
+            if (live) scratch[(size_t)A.U.sbase[g] + (size_t)chunk * (t1 - t0) + (i - t0)] = op.part(tg);
+        } else if (live) op.finish(tg, A, i, l0 + lt);
     }
+}
+
+// combine the parked partial states of a multi-unit group, in unit order, and finish
+template <class Op>
+__global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, int g0, int g1) {
+    const int g = g0 + blockIdx.x;
+    if (g >= g1) return;
+    const int nu = A.U.first[g + 1] - A.U.first[g];
+    if (nu <= 1) return;
+    const int l0 = g * kGroupLeaves;
+    const int nl = min(kGroupLeaves, A.nleaves - l0);
+    const int t0 = A.L.first[l0], t1 = A.L.last[l0 + nl - 1];
+    const typename Op::Part* scratch = (const typename Op::Part*)A.scratch + A.U.sbase[g];
+    for (int i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+        int lo = 0, hi = nl - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (A.L.first[l0 + mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        typename Op::Tgt tg;
+        if (!op.init(tg, A, i, l0 + lo, true)) continue;
+        for (int c = 0; c < nu; c++) op.combine(tg, scratch[(size_t)c * (t1 - t0) + (i - t0)]);
+        op.finish(tg, A, i, l0 + lo);
+    }
+}
+
+// unit bookkeeping: units per group, scratch slots per group
+__global__ void k_unit_count(LeafDev L, GroupLists G, int nleaves, int ngroups, u32* nunits, u32* nslots) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    long long ne = G.ptr[g + 1] - G.ptr[g];
+    u32 nu = (u32)((ne + kUnitEntries - 1) / kUnitEntries);
+    if (nu == 0) nu = 1;
+    int l0 = g * kGroupLeaves, nl = min(kGroupLeaves, nleaves - l0);
+    u32 T = (u32)(L.last[l0 + nl - 1] - L.first[l0]);
+    nunits[g] = nu;
+    nslots[g] = nu > 1 ? nu * T : 0;
+}
+__global__ void k_unit_fill(int ngroups, const int* first, int* group) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    for (int u = first[g]; u < first[g + 1]; u++) group[u] = g;
 }
 
 // ------------------------------------------------------------------------------------------ K4
@@ -162,6 +223,9 @@ struct ConvOp {
     const double* sinks;   // (x,y,g) triples
     int nsink;
     struct Tgt { double x, y, rx, ry; };
+    struct Part { double rx, ry; };
+    __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.rx, t.ry}; }
+    __device__ __forceinline__ void combine(Tgt& t, const Part& p) const { t.rx += p.rx; t.ry += p.ry; }
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.rx = t.ry = 0; t.x = t.y = 0;
@@ -226,6 +290,11 @@ struct DiffOp {
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
+    struct Part { double S1, S2x, S2y, S0, S3x, S3y; };
+    __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.S1, t.S2x, t.S2y, t.S0, t.S3x, t.S3y}; }
+    __device__ __forceinline__ void combine(Tgt& t, const Part& p) const {
+        t.S1 += p.S1; t.S2x += p.S2x; t.S2y += p.S2y; t.S0 += p.S0; t.S3x += p.S3x; t.S3y += p.S3y;
+    }
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.S1 = t.S2x = t.S2y = t.S0 = t.S3x = t.S3y = 0;
@@ -236,30 +305,35 @@ struct DiffOp {
         t.x = A.P.x[i]; t.y = A.P.y[i]; t.g = g; t.ie = A.P.ie[i]; t.ie2 = t.ie * t.ie; t.pos = g > 0;
         return true;
     }
+    // a g == 0 source is parked at x = +inf: its distance is inf and the pre-test below drops it
     __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
-        xy = make_double2(A.P.x[j], A.P.y[j]);
-        ab = make_double2(A.P.g[j], 0.);
+        double g = A.P.g[j];
+        xy = make_double2(g == 0 ? __longlong_as_double(0x7ff0000000000000ll) : A.P.x[j], A.P.y[j]);
+        ab = make_double2(g, 0.);
     }
-    // vortex_influence, :93-105. The cut-off decision `-|dr|*_1_eps < -8` is replayed exactly;
-    // a squared-distance pre-test with a 1e-6 safety margin rejects the ~95 % of pairs far outside.
+    // vortex_influence, :93-105. The cut-off decision `-|dr|*_1_eps < -8` is replayed exactly in
+    // hit(); a squared-distance pre-test with a 1e-6 safety margin rejects the ~98 % of pairs that
+    // are far outside it, so the common path is 7 FP64 instructions and one rarely-taken branch.
+    __device__ __forceinline__ void hit(Tgt& t, double dx, double dy, double d2, double sg) const {
+        if (sg == 0 || ((sg > 0) != t.pos)) return;        // same sign only (:95)
+        if (VV_ADD(fabs(dx), fabs(dy)) < 1E-10) return;    // TVec::iszero
+        double drabs = sqrt(d2);
+        double exparg = -VV_MUL(drabs, t.ie);
+        if (exparg < -8.) return;
+        double i1tmp = sg * exp(exparg);
+        double q = i1tmp / drabs;
+        t.S2x = fma(dx, q, t.S2x);
+        t.S2y = fma(dy, q, t.S2y);
+        t.S1 += i1tmp;
+    }
     __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
                                         int) const {
+#pragma unroll 4
         for (int k = 0; k < n; k++) {
             double2 p = xy[k];
-            double sg = ab[k].x;
-            if (sg == 0 || ((sg > 0) != t.pos)) continue;  // same sign only (:95); NaN g never matches
             double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
             double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (d2 * t.ie2 > 64.0001) continue;
-            if (VV_ADD(fabs(dx), fabs(dy)) < 1E-10) continue;  // TVec::iszero
-            double drabs = sqrt(d2);
-            double exparg = -VV_MUL(drabs, t.ie);
-            if (exparg < -8.) continue;
-            double i1tmp = sg * exp(exparg);
-            double q = i1tmp / drabs;
-            t.S2x = fma(dx, q, t.S2x);
-            t.S2y = fma(dy, q, t.S2y);
-            t.S1 += i1tmp;
+            if (!(d2 * t.ie2 > 64.0001)) hit(t, dx, dy, d2, ab[k].x);
         }
     }
     // segment_influence, :107-123
@@ -320,6 +394,20 @@ struct EpsOp {
     double* ie_out;
     int* changed;
     struct Tgt { double x, y, r1, r2; int i, i1, i2; };
+    struct Part { double r1, r2; int i1, i2; };
+    __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.r1, t.r2, t.i1, t.i2}; }
+    // two smallest in (distance, index) order == the reference's first-seen-wins scan (:143-151)
+    __device__ __forceinline__ void consider(Tgt& t, double d, int j) const {
+        if (d < t.r1 || (d == t.r1 && j < t.i1)) {
+            t.r2 = t.r1; t.i2 = t.i1; t.r1 = d; t.i1 = j;
+        } else if (d < t.r2 || (d == t.r2 && j < t.i2)) {
+            t.r2 = d; t.i2 = j;
+        }
+    }
+    __device__ __forceinline__ void combine(Tgt& t, const Part& p) const {
+        if (p.i1 >= 0) consider(t, p.r1, p.i1);
+        if (p.i2 >= 0) consider(t, p.r2, p.i2);
+    }
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.r1 = t.r2 = DBL_MAX; t.i1 = t.i2 = -1; t.i = i; t.x = t.y = 0;
@@ -340,9 +428,13 @@ struct EpsOp {
         t.x = A.P.x[i]; t.y = A.P.y[i];
         return true;
     }
+    // A g == 0 source is parked at x = +inf (never a neighbour, :140); a source with a timeline entry
+    // at x = NaN, which fails the `d > r2` test below and is re-read from the timeline in cand().
     __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
-        xy = make_double2(A.P.x[j], A.P.y[j]);
-        ab = make_double2(A.P.g[j], (A_.absby && dyn[j]) ? 1. : 0.);
+        double x = A.P.x[j];
+        if (A.P.g[j] == 0) x = __longlong_as_double(0x7ff0000000000000ll);
+        else if (A_.absby && dyn[j]) x = __longlong_as_double(0x7ff8000000000000ll);
+        xy = make_double2(x, A.P.y[j]);
     }
     // state of source j as target i sees it; false = not a neighbour candidate
     __device__ __forceinline__ bool seen(int j, int i, double& sx, double& sy, double& sg) const {
@@ -351,21 +443,26 @@ struct EpsOp {
         if (A_.init[j] && j < i) { sx = A_.nx[j]; sy = A_.ny[j]; sg = A_.ng[j]; }
         return sg != 0;
     }
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
-                                        int jbase) const {
-        for (int k = 0; k < n; k++) {
-            const int j = jbase + k;
-            double sx = xy[k].x, sy = xy[k].y, sg = ab[k].x;
-            if (sg == 0 || j == t.i) continue;  // :140
-            if (ab[k].y != 0 && !seen(j, t.i, sx, sy, sg)) continue;
+    __device__ __forceinline__ void cand(Tgt& t, const NearArgs& A, double d, int j) const {
+        if (j == t.i) return;  // :140
+        if (isnan(d)) {
+            double sx = A.P.x[j], sy = A.P.y[j], sg = A.P.g[j];
+            if (!A_.absby || !seen(j, t.i, sx, sy, sg)) return;
             double dx = VV_SUB(t.x, sx), dy = VV_SUB(t.y, sy);
+            d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+        }
+        consider(t, d, j);
+    }
+    // common path: 5 FP64 + one compare; only a source at least as close as the current second
+    // neighbour (or a parked NaN) takes the branch
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const double2* xy, const double2*, int n,
+                                        int jbase) const {
+#pragma unroll 4
+        for (int k = 0; k < n; k++) {
+            double2 p = xy[k];
+            double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
             double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            // two smallest in (distance, index) order == the reference's first-seen-wins scan (:143-151)
-            if (d < t.r1 || (d == t.r1 && j < t.i1)) {
-                t.r2 = t.r1; t.i2 = t.i1; t.r1 = d; t.i1 = j;
-            } else if (d < t.r2 || (d == t.r2 && j < t.i2)) {
-                t.r2 = d; t.i2 = j;
-            }
+            if (!(d > t.r2)) cand(t, A, d, jbase + k);
         }
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}

@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json): one full particle step
+(tree build -> epsilon/merge -> convective Biot-Savart -> diffusive -> move/clean,
+utils/vvflow/vvflow.cpp:246-257) on BASELINE config 2: a synthetic Lamb-Oseen vortex cloud, N = 1M.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+
+Under torchrun (N > 1) one rank per GPU: targets are sharded, sources replicated by all-gathers.
+Prints ONE JSON line on rank 0. `value` = steps/s with the particle state resident in HBM;
+`e2e` = the same through the host boundary (48-byte TObj records in pinned host memory copied in
+and out every step); `roofline` = the convective kernel against the measured FP64 pipe peak;
+`cpu_baseline` = the reference's own code on this box's host cores on a bounded sample of leaves.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sim steps/s (full particle hot path; Biot-Savart interactions/s reported beside it)"
+DBL_MAX = float(np.finfo(np.float64).max)
+RE, DT, INF_VX, INF_VY, FAR = 1000.0, 0.005, 1.0, 0.0, 8
+
+
+def lamb_oseen_cloud(n, seed=12345):
+    """BASELINE config 2: x,y ~ N(0,1) (Lamb-Oseen blob, a = sqrt 2), g = 1/N, no bodies"""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros((n, 6))
+    rec[:, :2] = rng.standard_normal((n, 2))
+    rec[:, 2] = 1.0 / n
+    return rec
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def reference_arm(args):
+    """The reference's own CPU implementation (oracle/_ref: libvvhd sources compiled unmodified; else
+    the C restatement) on this box's host cores. One step = tree build on the full cloud + epsilon,
+    convective, diffusive on every `stride`-th leaf, extrapolated to all leaves + move_and_clean."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.n
+    rec = lamb_oseen_cloud(n)
+    from oracle import pyref
+    cores = 1  # README.md:70 / pytest/conftest.py:24: OMP_NUM_THREADS=1 is the reference's own setting
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    kind = "reference" if pyref.available() else "port"
+    stride = max(1, args.ref_stride)
+    times = []
+    pairs_rate = []
+    for it in range(args.warmup + args.steps):
+        ph = it % stride
+        if kind == "reference":
+            r = pyref.Ref(re=RE, dt=DT, inf_vx=INF_VX, inf_vy=INF_VY)
+            r.set_list(rec[:, :3])
+            r.tree_params(FAR, 0.0, DBL_MAX)
+            t0 = time.perf_counter(); r.tree_build(); t_build = time.perf_counter() - t0
+            r.sample_leaves(stride, ph)
+            npairs, _, _ = r.count_interactions()
+            t0 = time.perf_counter(); r.epsilon(True); t_eps = time.perf_counter() - t0
+            t0 = time.perf_counter(); r.convective(); t_conv = time.perf_counter() - t0
+            t0 = time.perf_counter(); r.diffusive(); t_diff = time.perf_counter() - t0
+            t0 = time.perf_counter(); r.tree_destroy(); r.move_and_clean(True); t_move = time.perf_counter() - t0
+            r.close()
+        else:
+            from oracle import pyport
+            p = pyport.Port(rec48=rec)
+            t0 = time.perf_counter(); p.tree_build(FAR, 0.0, DBL_MAX); t_build = time.perf_counter() - t0
+            nl = p.tree.contents.n_leaves
+            npairs = sum(p.count_interactions(l, l + 1)[0] for l in range(ph, nl, stride))
+            p.sample_leaves(stride, ph)
+            t0 = time.perf_counter(); p.epsilon(True); t_eps = time.perf_counter() - t0
+            t0 = time.perf_counter(); p.convective(INF_VX, INF_VY, DT); t_conv = time.perf_counter() - t0
+            t0 = time.perf_counter(); p.diffusive(RE); t_diff = time.perf_counter() - t0
+            p.sample_leaves(1, 0)
+            t0 = time.perf_counter(); p.tree_destroy(); p.move_and_clean(DT); t_move = time.perf_counter() - t0
+        step = t_build + stride * (t_eps + t_conv + t_diff) + t_move
+        if it >= args.warmup:
+            times.append(step)
+            pairs_rate.append(npairs / t_conv)
+    ms = 1e3 * float(np.mean(times))
+    val = 1e3 / ms
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Lamb-Oseen vortex cloud N={n}, one velocity+diffusion step (BASELINE configs[1])",
+                   "n_particles": n, "re": RE, "dt": DT, "far_criteria": FAR},
+        "interactions_per_s": float(np.mean(pairs_rate)),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": kind,
+                         "sample": f"full tree build + every {stride}-th leaf for epsilon/convective/diffusive, "
+                                   f"times x{stride}; OMP_NUM_THREADS=1 as the reference recommends"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def cpu_baseline_sample(n, rec, stride):
+    from oracle import pyref
+    if not pyref.available():
+        return None
+    os.environ["OMP_NUM_THREADS"] = "1"
+    r = pyref.Ref(re=RE, dt=DT, inf_vx=INF_VX, inf_vy=INF_VY)
+    r.set_list(rec[:, :3])
+    r.tree_params(FAR, 0.0, DBL_MAX)
+    t0 = time.perf_counter(); r.tree_build(); t_build = time.perf_counter() - t0
+    r.sample_leaves(stride, 0)
+    npairs, _, _ = r.count_interactions()
+    t0 = time.perf_counter(); r.epsilon(True); t_eps = time.perf_counter() - t0
+    t0 = time.perf_counter(); r.convective(); t_conv = time.perf_counter() - t0
+    t0 = time.perf_counter(); r.diffusive(); t_diff = time.perf_counter() - t0
+    t0 = time.perf_counter(); r.tree_destroy(); r.move_and_clean(True); t_move = time.perf_counter() - t0
+    r.close()
+    step = t_build + stride * (t_eps + t_conv + t_diff) + t_move
+    return {"value": 1.0 / step, "unit": "steps/s", "cores": 1, "kind": "reference",
+            "sample": f"full tree build + every {stride}-th leaf for epsilon/convective/diffusive, times x{stride} "
+                      f"(OMP_NUM_THREADS=1, the reference's recommended setting)",
+            "interactions_per_s": npairs / t_conv,
+            "phase_s": {"build": t_build, "eps": stride * t_eps, "conv": stride * t_conv, "diff": stride * t_diff,
+                        "move": t_move}}
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from vvflow_b200 import capi, multigpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    n = args.n
+    rec = lamb_oseen_cloud(n)
+    ctx = capi.Context(local)
+    stepper = multigpu.ShardedStep(ctx, rank, world, device)
+    host_in = torch.empty((n, 6), dtype=torch.float64).pin_memory()
+    host_out = torch.empty((n, 6), dtype=torch.float64).pin_memory()
+    host_in.numpy()[:] = rec
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        return stepper.step(FAR, 0.0, DBL_MAX, True, INF_VX, INF_VY, DT, RE)
+
+    def flush_l2():
+        flush.zero_()
+
+    # ---- resident: the state stays in HBM from step to step (the simulation loop itself)
+    ctx.set_particles(rec)
+    for _ in range(args.warmup):
+        one_step()
+    ctx.phase_times()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    phase_sum = {k: 0.0 for k in capi.PHASES}
+    launches = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        one_step()
+        ms, la = ctx.phase_times()  # synchronises the library's stream
+        for k in phase_sum:
+            phase_sum[k] += ms[k]
+        launches += la
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([max(dev_ms, 0.0), wall_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[1].item())  # max over ranks; wall bracketed by barrier+synchronize on both sides
+    ms_per_step = total_ms / args.steps
+
+    # interaction counts of the final state's tree (work done per step)
+    ctx.tree_build(FAR, 0.0, DBL_MAX)
+    near_pairs, far_nodes = ctx.count_interactions()
+    nn, nl, depth = ctx.tree_counts()
+    ctx.tree_destroy()
+    ctx.phase_times()
+
+    # ---- e2e: host records in, host records out, every step
+    for _ in range(min(args.warmup, 2)):
+        ctx.set_particles_ptr(host_in.data_ptr(), n)
+        one_step()
+        ctx.get_particles_ptr(host_out.data_ptr(), n)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        ctx.set_particles_ptr(host_in.data_ptr(), n)
+        one_step()
+        nout = ctx.get_particles_ptr(host_out.data_ptr(), n)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(t[0].item()) / args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+    checksum = float(host_out.numpy()[:nout, 2].sum())
+
+    # ---- roofline of the dominant kernel family: K4 convective, FP64 pipe
+    fp64_peak = ctx.fp64_peak()
+    conv_ms = phase_sum["conv"] / args.steps
+    # this rank's share of the pairs (targets are sharded); rank 0 reports its own kernel
+    share = 1.0
+    if world > 1:
+        f, l = ctx_range = stepper.bounds[rank]
+        share = float(l - f) / max(n, 1)
+    flops = 11.0 * near_pairs * share
+    achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(n, rec, args.ref_stride)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Lamb-Oseen vortex cloud N={n}, one velocity+diffusion step (BASELINE configs[1])",
+                       "n_particles": n, "re": RE, "dt": DT, "far_criteria": FAR, "leaves": nl, "tree_depth": depth,
+                       "near_pairs_per_step": near_pairs, "far_nodes_per_step": far_nodes,
+                       "parallelism": f"target-sharded x{world}, sources replicated by all-gather" if world > 1 else "1 GPU",
+                       "l2": "256 MB memset between steps (inside the timed region) flushes the 126 MB L2"},
+            "interactions_per_s": near_pairs * share / (conv_ms * 1e-3) if conv_ms > 0 else None,
+            "phase_ms": {k: v / args.steps for k, v in phase_sum.items()},
+            "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "steps/s", "ms_per_step": e2e_ms_per_step,
+                    "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * int(nout)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "k_near<ConvOp> (K4 convective near field)",
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "note": "achieved = 11 flop x near pairs / CUDA-event time of the kernel on the library's "
+                                 "stream; peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no "
+                                 "fp64 entry; HBM there: %s GB/s). HBM traffic of this kernel is ~0.1 GB: compute-bound."
+                                 % peaks.get("hbm_gbs")},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+            "checksum_sum_g": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--ref-stride", type=int, default=64, help="CPU arms: every stride-th leaf is evaluated")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

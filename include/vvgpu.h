@@ -100,6 +100,11 @@ int vvgpu_count_interactions(vvgpu_ctx* ctx, double* near_pairs, double* far_nod
 
 /* ---- MEpsilonFast::CalcEpsilonFast(merge), MEpsilonFast.cpp:11-63; Merged() -> *merged ---- */
 int vvgpu_epsilon(vvgpu_ctx* ctx, int merge, int* merged);
+/* multi-GPU helper: the first round of CalcEpsilonFast(merge=true) on this rank's slice only;
+ * *ncandidates = particles of the slice that want to merge. If the sum over ranks is 0 no merge can
+ * happen and the slice's _1_eps are final; otherwise every rank calls vvgpu_epsilon(merge=1), which
+ * replays the merges replicated. */
+int vvgpu_epsilon_probe(vvgpu_ctx* ctx, int* ncandidates);
 /* ---- MConvectiveFast::process_all_lists, MConvectiveFast.cpp:36-114. inf_* = S->inf_speed(),
  * dt = S->dt (sink epsilon, :160), sinks = Space::SourceList as (x,y,g) triples -------------- */
 int vvgpu_convective(vvgpu_ctx* ctx, double inf_vx, double inf_vy, double dt, const double* sinks_xyg,

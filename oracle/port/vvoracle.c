@@ -24,6 +24,11 @@ static int sgn(double v) { return (v > 0) ? 1 : ((v < 0) ? -1 : 0); } /* TObj.hp
 static double dmax(double a, double b) { return (a < b) ? b : a; }     /* std::max */
 static double dmin(double a, double b) { return (b < a) ? b : a; }     /* std::min */
 
+/* bench.py's bounded CPU sample: epsilon / convective / diffusive visit every stride-th leaf only */
+static int64_t g_stride = 1, g_phase = 0;
+void vvo_set_leaf_sample(int64_t stride, int64_t phase) { g_stride = stride > 0 ? stride : 1; g_phase = phase; }
+#define LEAF_LOOP(l, t) for (int64_t l = g_phase % g_stride; l < (t)->n_leaves; l += g_stride)
+
 /* ------------------------------------------------------------------ tree */
 
 typedef struct {
@@ -304,7 +309,7 @@ int64_t vvo_epsilon(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, int me
     static const vvo_bodies nobody;
     if (!b) b = &nobody;
     int64_t merged = 0;
-    for (int64_t l = 0; l < t->n_leaves; l++) {
+    LEAF_LOOP(l, t) {
         int64_t node = t->leaf_node[l];
         double cx = t->x[node], cy = t->y[node];
         int64_t att = nearest_body_segment(t, b, l, cx, cy);
@@ -396,7 +401,7 @@ void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double
                     const double* sinks, int64_t nsink) {
     static const vvo_bodies nobody;
     if (!b) b = &nobody;
-    for (int64_t l = 0; l < t->n_leaves; l++) {
+    LEAF_LOOP(l, t) {
         int64_t node = t->leaf_node[l];
         double cx = t->x[node], cy = t->y[node];
         double T1 = 0, T2 = 0, T3 = 0, T4 = 0;
@@ -454,7 +459,7 @@ void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)
  * and segment_influence (:107-123) */
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re) {
-    for (int64_t l = 0; l < t->n_leaves; l++) {
+    LEAF_LOOP(l, t) {
         int64_t node = t->leaf_node[l];
         for (int64_t i = t->vfirst[node]; i < t->vlast[node]; i++) {
             if (!p->g[i]) continue;

@@ -79,6 +79,8 @@ int64_t vvo_move_and_clean(vvo_plist* p, vvo_bodies* b, double dt, double remove
 /* TBody::isPointInvalid for body `ib`: nearest segment id (global) or -1 */
 int64_t vvo_point_invalid(const vvo_bodies* b, int64_t ib, double px, double py);
 
+/* bench helper: restrict epsilon/convective/diffusive to every stride-th leaf (default: all) */
+void vvo_set_leaf_sample(int64_t stride, int64_t phase);
 /* bench helper: near pairs / far nodes of leaves [l0, l1) */
 void vvo_count_interactions(const vvo_tree* t, const vvo_plist* p, int64_t l0, int64_t l1, double* near_pairs,
                             double* far_nodes);

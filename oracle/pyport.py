@@ -61,6 +61,7 @@ def lib():
                                          C.POINTER(C.c_int64)]
         L.vvo_point_invalid.restype = C.c_int64
         L.vvo_point_invalid.argtypes = [C.POINTER(_Bodies), C.c_int64, C.c_double, C.c_double]
+        L.vvo_set_leaf_sample.argtypes = [C.c_int64, C.c_int64]
         L.vvo_count_interactions.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.c_int64, C.c_int64,
                                              C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib = L
@@ -213,6 +214,9 @@ class Port:
         cl = C.c_int64(0)
         n = self.L.vvo_move_and_clean(C.byref(self.p), self._b(), dt, remove_eps, int(remove), C.byref(cl))
         return n, cl.value
+
+    def sample_leaves(self, stride, phase=0):
+        self.L.vvo_set_leaf_sample(stride, phase)
 
     def count_interactions(self, l0=0, l1=None):
         a, b = C.c_double(), C.c_double()

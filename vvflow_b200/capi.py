@@ -18,7 +18,7 @@ SYMBOLS = [
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
-    "vvgpu_epsilon", "vvgpu_convective", "vvgpu_diffusive", "vvgpu_move_and_clean",
+    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_diffusive", "vvgpu_move_and_clean",
     "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
 ]
@@ -68,6 +68,7 @@ def load():
         "vvgpu_tree_leaf_segments": [vp, ip, ip, sz],
         "vvgpu_count_interactions": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "vvgpu_epsilon": [vp, C.c_int, C.POINTER(C.c_int)],
+        "vvgpu_epsilon_probe": [vp, C.POINTER(C.c_int)],
         "vvgpu_convective": [vp, C.c_double, C.c_double, C.c_double, dp, sz],
         "vvgpu_diffusive": [vp, C.c_double, dp],
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
@@ -212,6 +213,11 @@ class Context:
     def epsilon(self, merge):
         m = C.c_int()
         self._ck(self.L.vvgpu_epsilon(self.h, int(merge), C.byref(m)))
+        return m.value
+
+    def epsilon_probe(self):
+        m = C.c_int()
+        self._ck(self.L.vvgpu_epsilon_probe(self.h, C.byref(m)))
         return m.value
 
     def convective(self, inf_vx=0.0, inf_vy=0.0, dt=0.0, sinks=None):

@@ -765,6 +765,48 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     return 0;
 }
 
+// First round of the merge iteration only, on this rank's slice: writes _1_eps of the slice's
+// particles if NO particle of the slice wants to merge and reports the number that do. The
+// multi-GPU host layer sums that over ranks: zero everywhere means no merge can happen at all
+// (every particle saw the unmodified state), otherwise every rank runs the replicated replay.
+int vvgpu_epsilon_probe(vvgpu_ctx* c, int* ncandidates) {
+    if (!c || !ncandidates) return VVGPU_EINVAL;
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    CK(cudaSetDevice(c->device));
+    PhaseTimer t(c, VVGPU_T_EPS);
+    cudaStream_t st = c->stream;
+    *ncandidates = 0;
+    const int n = c->tn, nl = c->nleaves;
+    if (n == 0) return 0;
+    bool ok = true;
+    PSet& P = c->ps[c->cur];
+    double* lcrit = c->lcrit.get<double>(nl, &ok);
+    double* lrestr = c->lrestr.get<double>(nl, &ok);
+    int* latt = c->latt.get<int>(nl, &ok);
+    int* dchg = c->d_changed.get<int>(2, &ok);
+    double* ietmp = c->ie_tmp.get<double>(n, &ok);
+    for (int k = 0; k < 3; k++) c->mB[k].get<int>(n, &ok);
+    for (int k = 3; k < 6; k++) c->mB[k].get<double>(n, &ok);
+    NEED(ok);
+    const bool walls = c->tnseg > 0;
+    BodySegs B{c->tnseg, walls ? c->nbody : 0, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_dlx.as<double>(),
+               c->s_dly.as<double>(), c->b_first.as<int>()};
+    k_leaf_wall<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->Gv(), c->t_segperm[c->segcur].as<int>(), B, 1, lcrit, lrestr, latt); CKLAUNCH();
+    CK(cudaMemcpyAsync(ietmp, P.ie.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    MergeState Bm = mstate(c->mB);
+    k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, Bm); CKLAUNCH();
+    CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
+    EpsOp<false> op{MergeState{}, Bm, lcrit, lrestr, nullptr, ietmp, dchg};
+    int rc = launch_near(c, op);
+    if (rc) return rc;
+    u32 changed = 0;
+    rc = read_u32(c, (u32*)dchg, &changed);
+    if (rc) return rc;
+    *ncandidates = (int)changed;
+    if (!changed) std::swap(c->ie_tmp, P.ie);
+    return 0;
+}
+
 int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, const double* sinks_xyg, size_t nsink) {
     if (!c || (nsink && !sinks_xyg)) return fail(c, VVGPU_EINVAL, "convective: bad argument");
     if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");

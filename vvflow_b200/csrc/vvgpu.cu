@@ -84,7 +84,7 @@ struct vvgpu_ctx {
     Buf scan_part, scan_out, flags;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
     Buf g_ptr, g_leaf, g_mask, g_count, taylor, farcount, d_err;
-    Buf u_group, u_first, u_sbase, u_tmp, near_scratch;
+    Buf u_group, u_first, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list, hv_flag, hv_stack;
     std::vector<int> h_ufirst;
     int nunits = 0;
     size_t nslots = 0;
@@ -122,6 +122,8 @@ struct vvgpu_ctx {
         a.P = ps[cur].view(); a.L = Lv(); a.G = Gv(); a.nleaves = nleaves;
         a.U = Units{u_group.as<int>(), u_first.as<int>(), u_sbase.as<u32>()};
         a.scratch = near_scratch.p;
+        a.src4 = src4.as<double4>();
+        a.lbox = lbox.as<double>();
         a.u0 = h_ufirst.empty() ? 0 : h_ufirst[shard_g0];
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
@@ -308,7 +310,7 @@ int lists_impl(vvgpu_ctx* c) {
     c->g_ptr.get<long long>(ng + 1, &ok);
     double* taylor = c->taylor.get<double>(4 * (size_t)nl, &ok);
     double* farcount = c->farcount.get<double>(nl, &ok);
-    int* derr = c->d_err.get<int>(1, &ok);
+    int* derr = c->d_err.get<int>(2, &ok);
     c->scan_out.get<u32>(ng + 2, &ok);
     NEED(ok);
     TreeDev T = c->T();
@@ -317,11 +319,32 @@ int lists_impl(vvgpu_ctx* c) {
     size_t smem = trav_smem(cap);
     CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
     CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
-    CK(cudaMemsetAsync(derr, 0, sizeof(int), st));
+    int* hvlist = c->hv_list.get<int>(ng + 1, &ok);
+    unsigned char* hvflag = c->hv_flag.get<unsigned char>(ng + 1, &ok);
+    NEED(ok);
+    int* nheavy_d = derr + 1;
+    CK(cudaMemsetAsync(derr, 0, 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(hvflag, 0, ng + 1, st));
     const int grid = cdiv(ng, kTravWarps);
-    k_traverse<false><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr); CKLAUNCH();
+    k_traverse<false><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr, hvlist, nheavy_d, hvflag); CKLAUNCH();
+    u32 nheavy = 0;
+    int rc = read_u32(c, (u32*)nheavy_d, &nheavy);
+    if (rc) return rc;
+    int2* stacks = nullptr;
+    const long long stride = (long long)c->nnodes + 2;
+    // heavy groups run in batches so that their stacks (one slot per tree node each) stay within 512 MB
+    const int hbatch = (int)std::max<long long>(1, std::min<long long>(nheavy, (512ll << 20) / (stride * (long long)sizeof(int2))));
+    if (nheavy) {
+        stacks = c->hv_stack.get<int2>((size_t)stride * hbatch, &ok);
+        NEED(ok);
+        k_mark_heavy<<<cdiv(nheavy, 256), 256, 0, st>>>(hvlist, (int)nheavy, hvflag); CKLAUNCH();
+        for (int b = 0; b < (int)nheavy; b += hbatch) {
+            int nb = std::min(hbatch, (int)nheavy - b);
+            k_traverse_heavy<false><<<nb, kHeavyThreads, 0, st>>>(T, L, nl, hvlist + b, c->farc, c->Gv(), gcount, taylor, farcount, stacks, stride, derr); CKLAUNCH();
+        }
+    }
     u32* gs = c->scan_out.as<u32>();
-    int rc = scan_flags(c, FlagArray{gcount}, ng, gs);
+    rc = scan_flags(c, FlagArray{gcount}, ng, gs);
     if (rc) return rc;
     u32 total = 0;
     rc = read_u32(c, gs + ng, &total);
@@ -334,7 +357,11 @@ int lists_impl(vvgpu_ctx* c) {
     c->g_leaf.get<int>(total, &ok); c->g_mask.get<u32>(total, &ok);
     NEED(ok);
     k_group_ptr<<<cdiv(ng + 1, 256), 256, 0, st>>>(gs, c->g_ptr.as<long long>(), ng); CKLAUNCH();
-    k_traverse<true><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr); CKLAUNCH();
+    k_traverse<true><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr, hvlist, nheavy_d, hvflag); CKLAUNCH();
+    for (int b = 0; b < (int)nheavy; b += hbatch) {
+        int nb = std::min(hbatch, (int)nheavy - b);
+        k_traverse_heavy<true><<<nb, kHeavyThreads, 0, st>>>(T, L, nl, hvlist + b, c->farc, c->Gv(), gcount, taylor, farcount, stacks, stride, derr); CKLAUNCH();
+    }
     c->lists_ready = true;
     // work units (<= kUnitEntries list entries each) and the scratch slots of multi-unit groups
     u32* nun = c->u_tmp.get<u32>(2 * (size_t)ng + 2, &ok);
@@ -357,6 +384,7 @@ int lists_impl(vvgpu_ctx* c) {
     c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
     NEED(ok);
     k_unit_fill<<<cdiv(ng, 128), 128, 0, st>>>(ng, ufirst, ugroup); CKLAUNCH();
+    k_sort_units<<<c->nunits, 256, 0, st>>>(c->Gv(), Units{ugroup, ufirst, sbase}, c->nunits); CKLAUNCH();
     // shard: contiguous slices of groups balanced by unit count (units bound the work per CTA)
     c->shard_g0 = 0; c->shard_g1 = ng;
     if (c->nranks > 1) {
@@ -371,15 +399,42 @@ int lists_impl(vvgpu_ctx* c) {
 }
 
 template <class Op>
-int launch_near(vvgpu_ctx* c, Op op) {
+int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
     static_assert(sizeof(typename Op::Part) <= sizeof(DiffOp::Part), "scratch is sized for the largest Part");
     const int g0 = c->shard_g0, g1 = c->shard_g1;
     if (g1 <= g0) return 0;
+    {
+        bool ok = true;
+        double4* s4 = c->src4.get<double4>(c->tn, &ok);
+        NEED(ok);
+        k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
+    }
     const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
     k_near<Op><<<nu, kNearThreads, 0, c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (nu > g1 - g0) {  // some group has more than one unit
         k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
     }
+    return 0;
+}
+
+// per-leaf merge criterion / epsilon restriction / nearest segment (MEpsilonFast.cpp:26-47)
+int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* latt) {
+    cudaStream_t st = c->stream;
+    const int nl = c->nleaves;
+    BodySegs B{c->tnseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_dlx.as<double>(),
+               c->s_dly.as<double>(), c->b_first.as<int>()};
+    u64 *bd = nullptr, *bk = nullptr;
+    if (c->tnseg > 0) {
+        bool ok = true;
+        bd = c->wall_d.get<u64>(nl, &ok); bk = c->wall_key.get<u64>(nl, &ok);
+        NEED(ok);
+        const int* sp = c->t_segperm[c->segcur].as<int>();
+        Units U{c->u_group.as<int>(), c->u_first.as<int>(), c->u_sbase.as<u32>()};
+        k_wall_init<<<cdiv(nl, 256), 256, 0, st>>>(nl, bd, bk); CKLAUNCH();
+        k_wall_pass<1><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
+        k_wall_pass<2><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
+    }
+    k_wall_finish<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->t_segperm[c->segcur].as<int>(), B, merge, bd, bk, lcrit, lrestr, latt); CKLAUNCH();
     return 0;
 }
 
@@ -434,7 +489,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_ptr, &c->g_leaf, &c->g_mask, &c->g_count, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
-                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch};
+                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list, &c->hv_flag, &c->hv_stack};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
     c->ps[0].release(); c->ps[1].release();
@@ -700,13 +755,12 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     PSet& P = c->ps[c->cur];
     const bool walls = c->tnseg > 0;
     double *lcrit = nullptr, *lrestr = nullptr;
-    if (walls || merge) {
+    if (walls || c->nbody > 0 || merge) {
         lcrit = c->lcrit.get<double>(nl, &ok); lrestr = c->lrestr.get<double>(nl, &ok);
         int* latt = c->latt.get<int>(nl, &ok);
         NEED(ok);
-        BodySegs B{c->tnseg, walls ? c->nbody : 0, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_dlx.as<double>(),
-                   c->s_dly.as<double>(), c->b_first.as<int>()};
-        k_leaf_wall<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->Gv(), c->t_segperm[c->segcur].as<int>(), B, merge, lcrit, lrestr, latt); CKLAUNCH();
+        int rcw = wall_params(c, merge, lcrit, lrestr, latt);
+        if (rcw) return rcw;
     }
     int* dchg = c->d_changed.get<int>(2, &ok);
     NEED(ok);
@@ -736,7 +790,7 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH();
         CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
         EpsOp<false> op{A, B, lcrit, lrestr, dyn, ietmp, dchg};
-        int rc = launch_near(c, op);
+        int rc = launch_near(c, op, haveA ? dyn : nullptr);
         if (rc) return rc;
         u32 changed = 0;
         rc = read_u32(c, (u32*)dchg, &changed);
@@ -753,7 +807,7 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     // epsilon of the initiators at their merged position (the recursive epsv call, :169), then commit
     MergeState A = mstate(c->mA);
     EpsOp<true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
-    int rc = launch_near(c, opf);
+    int rc = launch_near(c, opf, dyn);
     if (rc) return rc;
     std::swap(c->ie_tmp, P.ie);  // absorbed-before-turn particles kept their old value in ie_tmp (never written)
     CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
@@ -788,10 +842,10 @@ int vvgpu_epsilon_probe(vvgpu_ctx* c, int* ncandidates) {
     for (int k = 0; k < 3; k++) c->mB[k].get<int>(n, &ok);
     for (int k = 3; k < 6; k++) c->mB[k].get<double>(n, &ok);
     NEED(ok);
-    const bool walls = c->tnseg > 0;
-    BodySegs B{c->tnseg, walls ? c->nbody : 0, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_dlx.as<double>(),
-               c->s_dly.as<double>(), c->b_first.as<int>()};
-    k_leaf_wall<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->Gv(), c->t_segperm[c->segcur].as<int>(), B, 1, lcrit, lrestr, latt); CKLAUNCH();
+    {
+        int rcw = wall_params(c, 1, lcrit, lrestr, latt);
+        if (rcw) return rcw;
+    }
     CK(cudaMemcpyAsync(ietmp, P.ie.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     MergeState Bm = mstate(c->mB);
     k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, Bm); CKLAUNCH();
@@ -838,6 +892,10 @@ int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
         PhaseTimer t(c, VVGPU_T_DIFF);
         if (c->nseg) CK(cudaMemsetAsync(c->d_fric.p, 0, sizeof(double) * c->nseg, c->stream));
         if (c->tn) {
+            bool ok = true;
+            double* lb = c->lbox.get<double>(5 * (size_t)c->nleaves, &ok);
+            NEED(ok);
+            k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), lb); CKLAUNCH();
             DiffOp op{re, c->d_fric.as<double>()};
             int rc = launch_near(c, op);
             if (rc) return rc;

@@ -18,6 +18,8 @@ namespace vv {
 
 constexpr int kGroupLeaves = 32;
 constexpr int kTravWarps = 4;  // warps per CTA in k_traverse
+constexpr int kTravBudget = 512;  // warp iterations before a group is declared heavy
+constexpr int kHeavyThreads = 1024;
 
 struct GroupLists {
     long long* ptr;  // ngroups + 1
@@ -53,7 +55,7 @@ __device__ __forceinline__ void taylor_add(double cx, double cy, double mx, doub
 template <bool FILL>
 __global__ void __launch_bounds__(kTravWarps * 32)
 k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLists G, u32* gcount, double* taylor,
-           double* farcount, int stack_cap, int* err) {
+           double* farcount, int stack_cap, int* err, int* heavy, int* nheavy, const unsigned char* is_heavy) {
     extern __shared__ unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x * kTravWarps + warp;
@@ -67,6 +69,7 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
     double* lw = lh + 32;
     double* cm = lw + 32;
     if (g >= ngroups) return;  // warps are independent: no block-level barrier below
+    if (FILL && is_heavy[g]) return;  // handled by k_traverse_heavy
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, nleaves - l0);
     double mycx = 0, mycy = 0;
@@ -82,7 +85,14 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
     u32 cnt = 0;
     double nfar = 0;
     const long long gbase = FILL ? G.ptr[g] : 0;
+    int iters = 0;
     while (size > 0) {
+        if (!FILL && ++iters > kTravBudget) {
+            // a fringe group that sees most of the tree: a single warp would serialise the whole
+            // step behind it, so it is handed to k_traverse_heavy (one 1024-thread CTA per group)
+            if (lane == 0) { heavy[atomicAdd(nheavy, 1)] = g; gcount[g] = 0; }
+            return;
+        }
         // near the capacity fall back to plain depth-first order (growth <= 1 per pop)
         int take = (size > stack_cap - 80) ? 1 : min(size, 32);
         int n = -1;
@@ -160,6 +170,126 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
         double* t = taylor + 4ll * (l0 + lane);
         t[0] = T1 * k1_2Pi; t[1] = T2 * k1_2Pi; t[2] = T3 * k1_Pi; t[3] = T4 * k1_2Pi;  // :66-69
     }
+}
+
+// Cooperative traversal of one HEAVY group by a 1024-thread CTA: the same walk as k_traverse with a
+// 1024-wide frontier and the stack in global memory (at most one entry per tree node). Entry order
+// and the Taylor sums are deterministic (block-wide prefix sums, warp partials combined in order).
+template <bool FILL>
+__global__ void __launch_bounds__(kHeavyThreads)
+k_traverse_heavy(TreeDev T, LeafDev L, int nleaves, const int* heavy, double farc, GroupLists G, u32* gcount,
+                 double* taylor, double* farcount, int2* stacks, long long stack_stride, int* err) {
+    __shared__ double lcx[32], lcy[32], lh[32], lw[32];
+    __shared__ int wn[32][32];
+    __shared__ int wpush[33], wemit[33];
+    __shared__ double acc[4][32];
+    __shared__ double accn[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = heavy[blockIdx.x];
+    int2* stack = stacks + stack_stride * blockIdx.x;
+    const int l0 = g * kGroupLeaves;
+    const int nl = min(kGroupLeaves, nleaves - l0);
+    if (tid < 32) {
+        bool in = tid < nl;
+        lcx[tid] = in ? L.cx[l0 + tid] : 0; lcy[tid] = in ? L.cy[l0 + tid] : 0;
+        lh[tid] = in ? L.h[l0 + tid] : 0; lw[tid] = in ? L.w[l0 + tid] : 0;
+        acc[0][tid] = acc[1][tid] = acc[2][tid] = acc[3][tid] = 0; accn[tid] = 0;
+    }
+    const u32 full = (nl == 32) ? 0xffffffffu : ((1u << nl) - 1u);
+    if (tid == 0) stack[0] = make_int2(0, (int)full);
+    __syncthreads();
+    const double mycx = lcx[lane], mycy = lcy[lane];
+    int size = 1;
+    double T1 = 0, T2 = 0, T3 = 0, T4 = 0, nfar = 0;
+    u32 cnt = 0;
+    const long long gbase = FILL ? G.ptr[g] : 0;
+    while (size > 0) {
+        const int take = min(size, kHeavyThreads);
+        int n = -1;
+        u32 em = 0;
+        if (tid < take) { int2 e = stack[size - 1 - tid]; n = e.x; em = (u32)e.y; }
+        size -= take;
+        u32 farm = 0, nearm = 0;
+        int c1 = -1;
+        if (n >= 0) {
+            double nx = T.x[n], ny = T.y[n];
+            double nhw = VV_ADD(T.h[n], T.w[n]);
+            c1 = T.ch1[n];
+            for (u32 mm = em; mm; mm &= mm - 1) {
+                const int l = __ffs(mm) - 1;
+                if (is_far(nx, ny, nhw, lcx[l], lcy[l], lh[l], lw[l], farc)) farm |= (1u << l);
+            }
+            nearm = em & ~farm;
+        }
+        wn[warp][lane] = n;
+        const bool push = (n >= 0) && nearm && (c1 >= 0);
+        const bool emit = (n >= 0) && nearm && (c1 < 0);
+        const u32 pb = __ballot_sync(0xffffffffu, push), eb = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) { wpush[warp] = __popc(pb); wemit[warp] = __popc(eb); }
+        __syncthreads();  // also orders the stack reads above before the pushes below
+        if (warp == 0) {
+            int a = wpush[lane], b = wemit[lane], ia = a, ib = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) { ia += ta; ib += tb; }
+            }
+            wpush[lane] = ia - a; wemit[lane] = ib - b;
+            if (lane == 31) { wpush[32] = ia; wemit[32] = ib; }
+        }
+        __syncthreads();
+        if (size + 2 * wpush[32] > stack_stride) {  // cannot happen: every node is pushed at most once
+            if (tid == 0) atomicExch(err, 1);
+            return;
+        }
+        if (push) {
+            int off = size + 2 * (wpush[warp] + __popc(pb & lanemask_lt()));
+            stack[off] = make_int2(c1 + 1, (int)nearm);
+            stack[off + 1] = make_int2(c1, (int)nearm);
+        }
+        if (FILL && emit) {
+            long long k = gbase + cnt + wemit[warp] + __popc(eb & lanemask_lt());
+            G.leaf[k] = T.lstart[n];
+            G.mask[k] = nearm;
+        }
+        size += 2 * wpush[32];
+        cnt += wemit[32];
+        // far nodes of this warp's 32 frontier nodes -> lane = leaf
+        if (__ballot_sync(0xffffffffu, farm != 0)) {
+            u32 mine = 0;
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                u32 tm = __ballot_sync(0xffffffffu, (farm >> l) & 1u);
+                if (lane == l) mine = tm;
+            }
+            nfar += (double)__popc(mine);
+            if (FILL) {
+                while (mine) {
+                    int j = __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    const int nj = wn[warp][j];
+                    taylor_add(mycx, mycy, T.cmp[3ll * nj], T.cmp[3ll * nj + 1], T.cmp[3ll * nj + 2], T1, T2, T3, T4);
+                    taylor_add(mycx, mycy, T.cmm[3ll * nj], T.cmm[3ll * nj + 1], T.cmm[3ll * nj + 2], T1, T2, T3, T4);
+                }
+            }
+        }
+        __syncthreads();  // pushes visible, wn / wpush / wemit free for the next round
+    }
+    for (int w = 0; w < kHeavyThreads / 32; w++) {  // warp partials, in warp order
+        if (warp == w) { acc[0][lane] += T1; acc[1][lane] += T2; acc[2][lane] += T3; acc[3][lane] += T4; accn[lane] += nfar; }
+        __syncthreads();
+    }
+    if (!FILL) {
+        if (tid == 0) gcount[g] = cnt;
+        if (tid < nl && farcount) farcount[l0 + tid] = accn[tid];
+    } else if (tid < nl) {
+        double* t = taylor + 4ll * (l0 + tid);
+        t[0] = acc[0][tid] * k1_2Pi; t[1] = acc[1][tid] * k1_2Pi; t[2] = acc[2][tid] * k1_Pi; t[3] = acc[3][tid] * k1_2Pi;
+    }
+}
+__global__ void k_mark_heavy(const int* heavy, int nheavy, unsigned char* is_heavy) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nheavy) is_heavy[heavy[i]] = 1;
 }
 
 __global__ void k_group_ptr(const u32* gscan, long long* ptr, int ngroups) {

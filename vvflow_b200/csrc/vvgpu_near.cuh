@@ -15,7 +15,7 @@
 
 namespace vv {
 
-constexpr int kNearThreads = 512;   // >= 32 leaves x 15 particles: one pass over the sources per group
+constexpr int kNearThreads = 384;   // one target per thread: 32 leaves x ~10.4 particles fit in one pass
 constexpr int kNearEB = 64;         // list entries per batch
 constexpr int kNearTS = 1024;       // source particles per shared-memory tile
 constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the serial path of one thread)
@@ -39,6 +39,8 @@ struct NearArgs {
     GroupLists G;
     Units U;
     void* scratch;
+    const double4* src4;  // per particle, packed by k_pack_src for the running phase
+    const double* lbox;   // per leaf 5 doubles: min x, max x, min y, max y of its particles NOW, max eps (k_leaf_box)
     int nleaves;
     int u0;  // first unit of this launch (shard offset)
     // segments (diffusive / epsilon wall terms)
@@ -49,10 +51,15 @@ struct NearArgs {
 struct NearShared {
     double2 sxy[kNearTS];
     double2 sab[kNearTS];
-    int epre[kNearEB + 1];
+    int sj[kNearTS];          // particle index of each staged source
+    int epre[kNearEB + 1];    // source prefix per entry
     int epf[kNearEB];
     u32 emk[kNearEB];
     int esf[kNearEB], esl[kNearEB];
+    int rstart[kNearEB + 1];  // runs of consecutive entries with the same mask (units are sorted by mask)
+    u32 rmask[kNearEB];
+    int nruns;
+    double gbox[5];           // group's target box + cut-off radius (ops with kFilter)
     int bounds[kGroupLeaves + 1];
 };
 
@@ -69,6 +76,20 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
+    if (Op::kFilter && tid < 32) {  // box of the group's targets and the largest cut-off radius among them
+        double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
+        if (tid < nl) {
+            const double* b = A.lbox + 5ll * (l0 + tid);
+            x0 = b[0]; x1 = b[1]; y0 = b[2]; y1 = b[3]; em = b[4];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+            em = fmax(em, __shfl_xor_sync(0xffffffffu, em, o));
+        }
+        if (tid == 0) { S.gbox[0] = x0; S.gbox[1] = x1; S.gbox[2] = y0; S.gbox[3] = y1; S.gbox[4] = op.reach(em); }
+    }
     const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
     const long long e1 = min(A.G.ptr[g + 1], e0 + kUnitEntries);
     typename Op::Part* scratch = (typename Op::Part*)A.scratch;
@@ -87,6 +108,7 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
         }
         typename Op::Tgt tg;
         const bool live = op.init(tg, A, i, l0 + lt, inrange);
+        if (live) op.seed(tg, A, l0 + lt);
         // leaves covered by this warp's live targets
         int ltmin = live ? lt : 64, ltmax = live ? lt : -1;
 #pragma unroll
@@ -106,16 +128,24 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
             __syncthreads();  // everyone is done with the previous batch / tile
             if (tid < 32) {
                 int c[2];
+                u32 mk[2];
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     int e = 2 * tid + k;
-                    c[k] = 0;
+                    c[k] = 0; mk[k] = 0;
                     if (e < ne) {
                         int sl = A.G.leaf[eb + e];
                         int f = A.L.first[sl];
                         c[k] = A.L.last[sl] - f;
+                        if (Op::kFilter) {  // gap between the source leaf's box and the group's box
+                            const double* b = A.lbox + 5ll * sl;
+                            double gx = fmax(0., fmax(b[0] - S.gbox[1], S.gbox[0] - b[1]));
+                            double gy = fmax(0., fmax(b[2] - S.gbox[3], S.gbox[2] - b[3]));
+                            if (gx * gx + gy * gy > S.gbox[4] * S.gbox[4]) c[k] = 0;
+                        }
+                        mk[k] = A.G.mask[eb + e];
                         S.epf[e] = f;
-                        S.emk[e] = A.G.mask[eb + e];
+                        S.emk[e] = mk[k];
                         S.esf[e] = A.L.sfirst[sl];
                         S.esl[e] = A.L.slast[sl];
                     }
@@ -130,6 +160,20 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
                 S.epre[2 * tid] = ex;
                 S.epre[2 * tid + 1] = ex + c[0];
                 if (tid == 31) S.epre[kNearEB] = inc;
+                // runs: an entry opens a run when its mask differs from its predecessor's
+                u32 mprev = __shfl_up_sync(0xffffffffu, mk[1], 1);
+                int f0 = (2 * tid < ne) && (tid == 0 || mk[0] != mprev);
+                int f1 = (2 * tid + 1 < ne) && (mk[1] != mk[0]);
+                int fs = f0 + f1, finc = fs;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, finc, o);
+                    if (lane >= o) finc += t;
+                }
+                int r = finc - fs;
+                if (f0) { S.rstart[r] = ex; S.rmask[r] = mk[0]; r++; }
+                if (f1) { S.rstart[r] = ex + c[0]; S.rmask[r] = mk[1]; }
+                if (tid == 31) { S.nruns = finc; S.rstart[finc] = inc; }
             }
             __syncthreads();
             const int total = S.epre[ne];
@@ -144,19 +188,20 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
                         if (S.epre[mid] <= F) lo = mid; else hi = mid - 1;
                     }
                     int j = S.epf[lo] + (F - S.epre[lo]);
-                    op.stage(A, j, S.sxy[k], S.sab[k]);
+                    double4 v = A.src4[j];
+                    S.sxy[k] = make_double2(v.x, v.y);
+                    S.sab[k] = make_double2(v.z, v.w);
+                    S.sj[k] = j;
                 }
                 __syncthreads();
                 if (wmask) {
-                    for (int e = 0; e < ne; e++) {
-                        const u32 m = S.emk[e];
+                    const int nr = S.nruns;
+                    for (int r = 0; r < nr; r++) {
+                        const u32 m = S.rmask[r];
                         if (!(m & wmask)) continue;
-                        int k0 = max(S.epre[e], s0) - s0, k1 = min(S.epre[e + 1], s0 + kNearTS) - s0;
+                        int k0 = max(S.rstart[r], s0) - s0, k1 = min(S.rstart[r + 1], s0 + kNearTS) - s0;
                         if (k0 >= k1) continue;
-                        if (live && (m & mybit)) {
-                            const int jbase = S.epf[e] + (s0 + k0 - S.epre[e]);
-                            op.run(tg, A, &S.sxy[k0], &S.sab[k0], k1 - k0, jbase);
-                        }
+                        if (live && (m & mybit)) op.run(tg, A, &S.sxy[k0], &S.sab[k0], &S.sj[k0], k1 - k0);
                     }
                 }
             }
@@ -192,6 +237,7 @@ __global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, int g0
         }
         typename Op::Tgt tg;
         if (!op.init(tg, A, i, l0 + lo, true)) continue;
+        op.seed(tg, A, l0 + lo);
         for (int c = 0; c < nu; c++) op.combine(tg, scratch[(size_t)c * (t1 - t0) + (i - t0)]);
         op.finish(tg, A, i, l0 + lo);
     }
@@ -215,9 +261,50 @@ __global__ void k_unit_fill(int ngroups, const int* first, int* group) {
     for (int u = first[g]; u < first[g + 1]; u++) group[u] = g;
 }
 
+// per-phase packed source records (one 32-byte load per staged source instead of four scattered ones)
+template <class Op>
+__global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4* out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = Op::pack(P, j, dyn);
+}
+
+// Sort the entries of every unit by (mask, leaf): entries that are seen by the same target leaves
+// become one long run, so the per-entry bookkeeping of k_near is paid per run. One CTA per unit,
+// bitonic sort of <= kUnitEntries 64-bit keys in shared memory. Deterministic.
+__global__ void __launch_bounds__(256) k_sort_units(GroupLists G, Units U, int nunits) {
+    __shared__ u64 key[kUnitEntries];
+    const int u = blockIdx.x;
+    if (u >= nunits) return;
+    const int g = U.group[u];
+    const int chunk = u - U.first[g];
+    const long long e0 = G.ptr[g] + (long long)chunk * kUnitEntries;
+    const int ne = (int)min((long long)kUnitEntries, G.ptr[g + 1] - e0);
+    for (int k = threadIdx.x; k < kUnitEntries; k += blockDim.x)
+        key[k] = (k < ne) ? (((u64)G.mask[e0 + k] << 32) | (u32)G.leaf[e0 + k]) : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= kUnitEntries; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < kUnitEntries / 2; t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = ((lo & size) == 0);
+                u64 a = key[lo], b = key[hi];
+                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+        G.leaf[e0 + k] = (int)(u32)(key[k] & 0xffffffffull);
+        G.mask[e0 + k] = (u32)(key[k] >> 32);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K4
 struct ConvOp {
     static constexpr bool kSegments = false;
+    static constexpr bool kFilter = false;
+    __device__ __forceinline__ double reach(double) const { return 0; }
     double inf_vx, inf_vy, eps2_div_srcg;
     const double* taylor;  // 4 per leaf
     const double* sinks;   // (x,y,g) triples
@@ -226,6 +313,7 @@ struct ConvOp {
     struct Part { double rx, ry; };
     __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.rx, t.ry}; }
     __device__ __forceinline__ void combine(Tgt& t, const Part& p) const { t.rx += p.rx; t.ry += p.ry; }
+    __device__ __forceinline__ void seed(Tgt&, const NearArgs&, int) const {}
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.rx = t.ry = 0; t.x = t.y = 0;
@@ -234,17 +322,17 @@ struct ConvOp {
         t.x = A.P.x[i]; t.y = A.P.y[i];
         return true;
     }
-    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
-        double g = A.P.g[j];
-        xy = make_double2(A.P.x[j], A.P.y[j]);
-        // eps^2 = sqr(1./_1_eps) of the SOURCE (:119); a g==0 source is skipped by the reference (:130)
-        double e = 1. / A.P.ie[j];
-        ab = (g == 0) ? make_double2(0., 1.) : make_double2(g, e * e);
+    // packed source record: eps^2 = sqr(1./_1_eps) of the SOURCE (:119); a g==0 source is skipped by
+    // the reference (:130) and is packed as g = 0, eps^2 = 1 so that it adds exactly nothing
+    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*) {
+        double g = P.g[j];
+        double e = 1. / P.ie[j];
+        return (g == 0) ? make_double4(P.x[j], P.y[j], 0., 1.) : make_double4(P.x[j], P.y[j], g, e * e);
     }
     // rotl(dr) * g / (|dr|^2 + eps^2): reciprocal by rcp.approx + one third-order correction
     // (relative error ~ e0^3, e0 <= 2^-20: below 1 ulp; exactness is not required of velocities)
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
-                                        int) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, const int*,
+                                        int n) const {
         double rx = t.rx, ry = t.ry;
         const double tx = t.x, ty = t.y;
 #pragma unroll 4
@@ -287,6 +375,10 @@ struct ConvOp {
 // ------------------------------------------------------------------------------------------ K5
 struct DiffOp {
     static constexpr bool kSegments = true;
+    // only sources within 8 eps of a target contribute (:101): leaves farther than that from the whole
+    // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
+    static constexpr bool kFilter = true;
+    __device__ __forceinline__ double reach(double epsmax) const { return 8.000008 * epsmax; }
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
@@ -295,6 +387,7 @@ struct DiffOp {
     __device__ __forceinline__ void combine(Tgt& t, const Part& p) const {
         t.S1 += p.S1; t.S2x += p.S2x; t.S2y += p.S2y; t.S0 += p.S0; t.S3x += p.S3x; t.S3y += p.S3y;
     }
+    __device__ __forceinline__ void seed(Tgt&, const NearArgs&, int) const {}
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.S1 = t.S2x = t.S2y = t.S0 = t.S3x = t.S3y = 0;
@@ -306,10 +399,9 @@ struct DiffOp {
         return true;
     }
     // a g == 0 source is parked at x = +inf: its distance is inf and the pre-test below drops it
-    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
-        double g = A.P.g[j];
-        xy = make_double2(g == 0 ? __longlong_as_double(0x7ff0000000000000ll) : A.P.x[j], A.P.y[j]);
-        ab = make_double2(g, 0.);
+    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*) {
+        double g = P.g[j];
+        return make_double4(g == 0 ? __longlong_as_double(0x7ff0000000000000ll) : P.x[j], P.y[j], g, 0.);
     }
     // vortex_influence, :93-105. The cut-off decision `-|dr|*_1_eps < -8` is replayed exactly in
     // hit(); a squared-distance pre-test with a 1e-6 safety margin rejects the ~98 % of pairs that
@@ -317,17 +409,25 @@ struct DiffOp {
     __device__ __forceinline__ void hit(Tgt& t, double dx, double dy, double d2, double sg) const {
         if (sg == 0 || ((sg > 0) != t.pos)) return;        // same sign only (:95)
         if (VV_ADD(fabs(dx), fabs(dy)) < 1E-10) return;    // TVec::iszero
-        double drabs = sqrt(d2);
+        // |dr| and 1/|dr| from one rsqrt; the exact sqrt of the reference decides only when the
+        // cut-off test is within 1e-9 of the boundary
+        double rinv = rsqrt(d2);
+        double drabs = d2 * rinv;
         double exparg = -VV_MUL(drabs, t.ie);
+        if (fabs(exparg + 8.) < 1e-9) {
+            drabs = sqrt(d2);
+            exparg = -VV_MUL(drabs, t.ie);
+            rinv = 1. / drabs;
+        }
         if (exparg < -8.) return;
         double i1tmp = sg * exp(exparg);
-        double q = i1tmp / drabs;
+        double q = i1tmp * rinv;
         t.S2x = fma(dx, q, t.S2x);
         t.S2y = fma(dy, q, t.S2y);
         t.S1 += i1tmp;
     }
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, int n,
-                                        int) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, const int*,
+                                        int n) const {
 #pragma unroll 4
         for (int k = 0; k < n; k++) {
             double2 p = xy[k];
@@ -386,6 +486,8 @@ constexpr int kNoAbs = 0x7fffffff;
 template <bool FINAL>
 struct EpsOp {
     static constexpr bool kSegments = false;
+    static constexpr bool kFilter = false;
+    __device__ __forceinline__ double reach(double) const { return 0; }
     MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
     MergeState B_;      // recomputed solution (decision mode only)
     const double* lcrit;   // per leaf merge_criteria_sq (NaN: never merge)
@@ -398,6 +500,7 @@ struct EpsOp {
     __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.r1, t.r2, t.i1, t.i2}; }
     // two smallest in (distance, index) order == the reference's first-seen-wins scan (:143-151)
     __device__ __forceinline__ void consider(Tgt& t, double d, int j) const {
+        if (j == t.i1 || j == t.i2) return;  // already recorded (own-leaf seed, or a parked partial)
         if (d < t.r1 || (d == t.r1 && j < t.i1)) {
             t.r2 = t.r1; t.i2 = t.i1; t.r1 = d; t.i1 = j;
         } else if (d < t.r2 || (d == t.r2 && j < t.i2)) {
@@ -428,13 +531,29 @@ struct EpsOp {
         t.x = A.P.x[i]; t.y = A.P.y[i];
         return true;
     }
+    // Seed the two-nearest search with a few neighbours from the target's own leaf, so that r2 is
+    // already small when the stream starts and almost no source takes the cand() branch. Sources
+    // met again in the stream are recognised by index in consider().
+    __device__ __forceinline__ void seed(Tgt& t, const NearArgs& A, int leaf) const {
+        const int f = max(A.L.first[leaf], t.i - 8), l = min(A.L.last[leaf], t.i + 9);
+        for (int j = f; j < l; j++) {
+            if (j == t.i || A.P.g[j] == 0) continue;
+            double d;
+            if (A_.absby && dyn[j]) d = __longlong_as_double(0x7ff8000000000000ll);
+            else {
+                double dx = VV_SUB(t.x, A.P.x[j]), dy = VV_SUB(t.y, A.P.y[j]);
+                d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+            }
+            cand(t, A, d, j);
+        }
+    }
     // A g == 0 source is parked at x = +inf (never a neighbour, :140); a source with a timeline entry
     // at x = NaN, which fails the `d > r2` test below and is re-read from the timeline in cand().
-    __device__ __forceinline__ void stage(const NearArgs& A, int j, double2& xy, double2& ab) const {
-        double x = A.P.x[j];
-        if (A.P.g[j] == 0) x = __longlong_as_double(0x7ff0000000000000ll);
-        else if (A_.absby && dyn[j]) x = __longlong_as_double(0x7ff8000000000000ll);
-        xy = make_double2(x, A.P.y[j]);
+    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char* dyn) {
+        double x = P.x[j];
+        if (P.g[j] == 0) x = __longlong_as_double(0x7ff0000000000000ll);
+        else if (dyn && dyn[j]) x = __longlong_as_double(0x7ff8000000000000ll);
+        return make_double4(x, P.y[j], 0., 0.);
     }
     // state of source j as target i sees it; false = not a neighbour candidate
     __device__ __forceinline__ bool seen(int j, int i, double& sx, double& sy, double& sg) const {
@@ -455,14 +574,14 @@ struct EpsOp {
     }
     // common path: 5 FP64 + one compare; only a source at least as close as the current second
     // neighbour (or a parked NaN) takes the branch
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const double2* xy, const double2*, int n,
-                                        int jbase) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const double2* xy, const double2*, const int* sj,
+                                        int n) const {
 #pragma unroll 4
         for (int k = 0; k < n; k++) {
             double2 p = xy[k];
             double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
             double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (!(d > t.r2)) cand(t, A, d, jbase + k);
+            if (!(d > t.r2)) cand(t, A, d, sj[k]);
         }
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
@@ -527,37 +646,71 @@ __global__ void k_merge_dyn(int n, MergeState M, unsigned char* dyn) {
     dyn[i] = (M.init[i] != 0 || M.absby[i] != kNoAbs) ? 1 : 0;
 }
 
+// current bounding box and largest epsilon of every leaf's particles (after epsilon / merging)
+__global__ void k_leaf_box(LeafDev L, int nleaves, Particles P, double* lbox) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
+    for (int i = L.first[l]; i < L.last[l]; i++) {
+        double x = P.x[i], y = P.y[i];
+        x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+        if (P.g[i] != 0) em = fmax(em, 1. / P.ie[i]);
+    }
+    double* b = lbox + 5ll * l;
+    b[0] = x0; b[1] = x1; b[2] = y0; b[3] = y1; b[4] = em;
+}
+
 // Per-leaf wall parameters of CalcEpsilonFast (MEpsilonFast.cpp:26-47) with nearestBodySegment
-// (:214-253). One thread per leaf; the 32 leaves of a group read the same list entries.
+// (:214-253). Only the few list entries whose leaf holds body segments do any work: pass 1 finds
+// each target leaf's smallest squared distance to a segment of its near leaves, pass 2 resolves ties
+// to the first segment in the reference's scan order (leaf order, then list order; strict `<`, :229),
+// k_wall_finish falls back to the global scan with its skip-ahead (:237-251) and derives the criteria.
 struct BodySegs {
     int nseg, nbody;
     const double *rx, *ry, *dlx, *dly;
     const int* bfirst;  // nbody + 1
 };
-__global__ void k_leaf_wall(LeafDev L, int nleaves, GroupLists G, const int* __restrict__ seg_perm, BodySegs B,
-                            int merge, double* lcrit, double* lrestr, int* latt) {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nleaves) return;
-    const int g = l / kGroupLeaves;
-    const u32 bit = 1u << (l % kGroupLeaves);
-    const double px = L.cx[l], py = L.cy[l];
-    double res = DBL_MAX;
-    int att = -1, aleaf = 0x7fffffff, apos = 0x7fffffff;
-    // nearest among the segments of the near leaves; ties resolve to the first in (leaf, list) order,
-    // which is the order the reference scans them in (strict `<`, :229)
-    for (long long e = G.ptr[g]; e < G.ptr[g + 1]; e++) {
-        if (!(G.mask[e] & bit)) continue;
-        int sl = G.leaf[e];
-        for (int k = L.sfirst[sl]; k < L.slast[sl]; k++) {
-            int s = seg_perm[k];
-            double dx = VV_SUB(px, B.rx[s]), dy = VV_SUB(py, B.ry[s]);
-            double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (d < res || (d == res && att >= 0 && (sl < aleaf || (sl == aleaf && k < apos)))) {
-                res = d; att = s; aleaf = sl; apos = k;
+template <int PASS>
+__global__ void __launch_bounds__(256) k_wall_pass(LeafDev L, GroupLists G, Units U, int nunits,
+                                                   const int* __restrict__ seg_perm, BodySegs B, u64* best_d,
+                                                   u64* best_key) {
+    const int u = blockIdx.x;
+    if (u >= nunits) return;
+    const int g = U.group[u];
+    const int chunk = u - U.first[g];
+    const long long e0 = G.ptr[g] + (long long)chunk * kUnitEntries;
+    const long long e1 = min(G.ptr[g + 1], e0 + kUnitEntries);
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const int sl = G.leaf[e];
+        const int sf = L.sfirst[sl], se = L.slast[sl];
+        if (se <= sf) continue;
+        for (u32 m = G.mask[e]; m; m &= m - 1) {
+            const int l = g * kGroupLeaves + (__ffs(m) - 1);
+            const double px = L.cx[l], py = L.cy[l];
+            for (int k = sf; k < se; k++) {
+                const int s = seg_perm[k];
+                double dx = VV_SUB(px, B.rx[s]), dy = VV_SUB(py, B.ry[s]);
+                u64 d = (u64)__double_as_longlong(VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy)));  // >= 0: bits are ordered
+                if (PASS == 1) atomicMin(&best_d[l], d);
+                else if (d == best_d[l]) atomicMin(&best_key[l], ((u64)(u32)sl << 32) | (u32)k);
             }
         }
     }
+}
+__global__ void k_wall_init(int nleaves, u64* best_d, u64* best_key) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < nleaves) { best_d[l] = 0x7fefffffffffffffull /* DBL_MAX */; best_key[l] = ~0ull; }
+}
+__global__ void k_wall_finish(LeafDev L, int nleaves, const int* __restrict__ seg_perm, BodySegs B, int merge,
+                              const u64* best_d, const u64* best_key, double* lcrit, double* lrestr, int* latt) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    const double px = L.cx[l], py = L.cy[l];
+    int att = -1;
+    // `drabs2 < res` with res starting at DBL_MAX (:229): a segment at distance DBL_MAX never wins
+    if (best_key && best_key[l] != ~0ull && best_d[l] < 0x7fefffffffffffffull) att = seg_perm[(int)(best_key[l] & 0xffffffffull)];
     if (att < 0) {
+        double res = DBL_MAX;
         for (int ib = 0; ib < B.nbody; ib++) {
             for (int s = B.bfirst[ib]; s < B.bfirst[ib + 1]; s++) {
                 double dx = VV_SUB(px, B.rx[s]), dy = VV_SUB(py, B.ry[s]);

@@ -124,6 +124,7 @@ struct vvgpu_ctx {
         a.scratch = near_scratch.p;
         a.src4 = src4.as<double4>();
         a.lbox = lbox.as<double>();
+        a.nseg = tnseg;
         a.u0 = h_ufirst.empty() ? 0 : h_ufirst[shard_g0];
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
@@ -410,7 +411,8 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
     const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
-    k_near<Op><<<nu, kNearThreads, 0, c->stream>>>(c->near_args(), op); CKLAUNCH();
+    CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NearShared)));
+    k_near<Op><<<nu, kNearThreads, sizeof(NearShared), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (nu > g1 - g0) {  // some group has more than one unit
         k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
     }

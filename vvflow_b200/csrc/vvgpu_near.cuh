@@ -42,6 +42,7 @@ struct NearArgs {
     const double4* src4;  // per particle, packed by k_pack_src for the running phase
     const double* lbox;   // per leaf 5 doubles: min x, max x, min y, max y of its particles NOW, max eps (k_leaf_box)
     int nleaves;
+    int nseg;
     int u0;  // first unit of this launch (shard offset)
     // segments (diffusive / epsilon wall terms)
     const int* seg_perm;
@@ -51,22 +52,52 @@ struct NearArgs {
 struct NearShared {
     double2 sxy[kNearTS];
     double2 sab[kNearTS];
-    int sj[kNearTS];          // particle index of each staged source
-    int epre[kNearEB + 1];    // source prefix per entry
-    int epf[kNearEB];
-    u32 emk[kNearEB];
-    int esf[kNearEB], esl[kNearEB];
-    int rstart[kNearEB + 1];  // runs of consecutive entries with the same mask (units are sorted by mask)
-    u32 rmask[kNearEB];
+    int sj[kNearTS];                 // particle index of each staged source
+    int epre[kUnitEntries + 1];      // source prefix per entry of the unit (0 sources once filtered out)
+    int epf[kUnitEntries];           // first particle of the entry's leaf
+    u32 emk[kUnitEntries];           // target-leaf mask
+    int eleaf[kUnitEntries];
+    int rstart[kUnitEntries + 1];    // runs of consecutive entries with the same mask (units are mask-sorted)
+    u32 rmask[kUnitEntries];
+    int wsum[8];
     int nruns;
-    double gbox[5];           // group's target box + cut-off radius (ops with kFilter)
+    double gbox[5];                  // group's target box + cut-off radius (ops with kFilter)
     int bounds[kGroupLeaves + 1];
 };
 
+// exclusive prefix sum of v[0..kUnitEntries) in place, by threads 0..127 (4 entries each); returns the
+// total in *total. Every thread of the CTA must call it (it contains barriers).
+__device__ __forceinline__ void unit_scan(int* v, int* wsum, int* total_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0, inc = 0;
+    if (tid < kUnitEntries / 4) {
+        a0 = v[4 * tid]; a1 = v[4 * tid + 1]; a2 = v[4 * tid + 2]; a3 = v[4 * tid + 3];
+        inc = a0 + a1 + a2 + a3;
+        const int s = inc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        inc -= s;  // exclusive within the warp
+    }
+    __syncthreads();
+    if (tid < kUnitEntries / 4) {
+        int off = 0;
+        for (int w = 0; w < warp; w++) off += wsum[w];
+        int ex = off + inc;
+        v[4 * tid] = ex; v[4 * tid + 1] = ex + a0; v[4 * tid + 2] = ex + a0 + a1; v[4 * tid + 3] = ex + a0 + a1 + a2;
+        if (tid == kUnitEntries / 4 - 1) *total_out = ex + a0 + a1 + a2 + a3;
+    }
+    __syncthreads();
+}
+
 template <class Op>
 __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
-    __shared__ NearShared S;
-    const int tid = threadIdx.x, lane = tid & 31;
+    extern __shared__ __align__(16) unsigned char near_smem[];
+    NearShared& S = *reinterpret_cast<NearShared*>(near_smem);
+    const int tid = threadIdx.x;
     const int u = A.u0 + blockIdx.x;
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
@@ -74,8 +105,6 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    __syncthreads();
-    const int t0 = S.bounds[0], t1 = S.bounds[nl];
     if (Op::kFilter && tid < 32) {  // box of the group's targets and the largest cut-off radius among them
         double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
         if (tid < nl) {
@@ -90,9 +119,60 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
         }
         if (tid == 0) { S.gbox[0] = x0; S.gbox[1] = x1; S.gbox[2] = y0; S.gbox[3] = y1; S.gbox[4] = op.reach(em); }
     }
+    __syncthreads();
+    const int t0 = S.bounds[0], t1 = S.bounds[nl];
     const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
-    const long long e1 = min(A.G.ptr[g + 1], e0 + kUnitEntries);
+    const int ne = (int)(min(A.G.ptr[g + 1], e0 + kUnitEntries) - e0);
     typename Op::Part* scratch = (typename Op::Part*)A.scratch;
+
+    // ---- prologue: the unit's whole entry table, in parallel (one entry per thread)
+    for (int e = tid; e < kUnitEntries; e += kNearThreads) {
+        int cnt = 0, f = 0, sl = 0;
+        u32 mk = 0;
+        if (e < ne) {
+            sl = A.G.leaf[e0 + e];
+            mk = A.G.mask[e0 + e];
+            f = A.L.first[sl];
+            cnt = A.L.last[sl] - f;
+            if (Op::kFilter) {  // gap between the source leaf's box and the group's box
+                const double* b = A.lbox + 5ll * sl;
+                double gx = fmax(0., fmax(b[0] - S.gbox[1], S.gbox[0] - b[1]));
+                double gy = fmax(0., fmax(b[2] - S.gbox[3], S.gbox[2] - b[3]));
+                if (gx * gx + gy * gy > S.gbox[4] * S.gbox[4]) cnt = 0;
+            }
+        }
+        S.epre[e] = cnt; S.epf[e] = f; S.emk[e] = mk; S.eleaf[e] = sl;
+    }
+    __syncthreads();
+    // a run opens where the mask changes (only among entries that still have sources)
+    for (int e = tid; e < kUnitEntries; e += kNearThreads) {
+        int flag = 0;
+        if (e < ne && S.epre[e] > 0) {
+            int p = e - 1;
+            while (p >= 0 && S.epre[p] == 0) p--;   // previous surviving entry
+            flag = (p < 0) || (S.emk[p] != S.emk[e]);
+        }
+        S.rstart[e] = flag;
+    }
+    __syncthreads();
+    int total, nruns;
+    unit_scan(S.epre, S.wsum, &S.rstart[kUnitEntries]);   // total sources parked in rstart[kUnitEntries]
+    total = S.rstart[kUnitEntries];
+    __syncthreads();
+    if (tid == 0) S.epre[kUnitEntries] = total;
+    // run ids: scan the flags, then every opening entry records its run
+    int myflag[2] = {0, 0};
+    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++) myflag[q] = S.rstart[e];
+    __syncthreads();
+    unit_scan(S.rstart, S.wsum, &S.nruns);
+    nruns = S.nruns;
+    int myrid[2];
+    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++) myrid[q] = S.rstart[e];
+    __syncthreads();
+    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++)
+        if (myflag[q]) { S.rstart[myrid[q]] = S.epre[e]; S.rmask[myrid[q]] = S.emk[e]; }
+    if (tid == 0) S.rstart[nruns] = total;
+    __syncthreads();
 
     for (int tb = t0; tb < t1; tb += kNearThreads) {
         const int i = tb + tid;
@@ -123,93 +203,47 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
         }
         const u32 mybit = 1u << lt;
 
-        for (long long eb = e0; eb < e1; eb += kNearEB) {
-            const int ne = (int)min((long long)kNearEB, e1 - eb);
-            __syncthreads();  // everyone is done with the previous batch / tile
-            if (tid < 32) {
-                int c[2];
-                u32 mk[2];
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    int e = 2 * tid + k;
-                    c[k] = 0; mk[k] = 0;
-                    if (e < ne) {
-                        int sl = A.G.leaf[eb + e];
-                        int f = A.L.first[sl];
-                        c[k] = A.L.last[sl] - f;
-                        if (Op::kFilter) {  // gap between the source leaf's box and the group's box
-                            const double* b = A.lbox + 5ll * sl;
-                            double gx = fmax(0., fmax(b[0] - S.gbox[1], S.gbox[0] - b[1]));
-                            double gy = fmax(0., fmax(b[2] - S.gbox[3], S.gbox[2] - b[3]));
-                            if (gx * gx + gy * gy > S.gbox[4] * S.gbox[4]) c[k] = 0;
-                        }
-                        mk[k] = A.G.mask[eb + e];
-                        S.epf[e] = f;
-                        S.emk[e] = mk[k];
-                        S.esf[e] = A.L.sfirst[sl];
-                        S.esl[e] = A.L.slast[sl];
-                    }
+        for (int s0 = 0; s0 < total; s0 += kNearTS) {
+            if (s0 > 0 || tb > t0) __syncthreads();  // the previous tile has been consumed
+            const int nsrc = min(kNearTS, total - s0);
+            for (int k = tid; k < nsrc; k += kNearThreads) {
+                const int F = s0 + k;
+                int lo = 0, hi = ne - 1;  // largest e with epre[e] <= F (entries without sources never match)
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (S.epre[mid] <= F) lo = mid; else hi = mid - 1;
                 }
-                int s = c[0] + c[1], inc = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                int ex = inc - s;
-                S.epre[2 * tid] = ex;
-                S.epre[2 * tid + 1] = ex + c[0];
-                if (tid == 31) S.epre[kNearEB] = inc;
-                // runs: an entry opens a run when its mask differs from its predecessor's
-                u32 mprev = __shfl_up_sync(0xffffffffu, mk[1], 1);
-                int f0 = (2 * tid < ne) && (tid == 0 || mk[0] != mprev);
-                int f1 = (2 * tid + 1 < ne) && (mk[1] != mk[0]);
-                int fs = f0 + f1, finc = fs;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, finc, o);
-                    if (lane >= o) finc += t;
-                }
-                int r = finc - fs;
-                if (f0) { S.rstart[r] = ex; S.rmask[r] = mk[0]; r++; }
-                if (f1) { S.rstart[r] = ex + c[0]; S.rmask[r] = mk[1]; }
-                if (tid == 31) { S.nruns = finc; S.rstart[finc] = inc; }
+                const int j = S.epf[lo] + (F - S.epre[lo]);
+                const double4 v = A.src4[j];
+                S.sxy[k] = make_double2(v.x, v.y);
+                S.sab[k] = make_double2(v.z, v.w);
+                S.sj[k] = j;
             }
             __syncthreads();
-            const int total = S.epre[ne];
-            for (int s0 = 0; s0 < total; s0 += kNearTS) {
-                if (s0 > 0) __syncthreads();
-                const int nsrc = min(kNearTS, total - s0);
-                for (int k = tid; k < nsrc; k += kNearThreads) {
-                    int F = s0 + k;
-                    int lo = 0, hi = ne - 1;  // largest e with epre[e] <= F
+            if (wmask) {
+                int r = 0;
+                {   // first run that reaches into this tile
+                    int lo = 0, hi = nruns - 1;
                     while (lo < hi) {
-                        int mid = (lo + hi + 1) >> 1;
-                        if (S.epre[mid] <= F) lo = mid; else hi = mid - 1;
+                        int mid = (lo + hi) >> 1;
+                        if (S.rstart[mid + 1] > s0) hi = mid; else lo = mid + 1;
                     }
-                    int j = S.epf[lo] + (F - S.epre[lo]);
-                    double4 v = A.src4[j];
-                    S.sxy[k] = make_double2(v.x, v.y);
-                    S.sab[k] = make_double2(v.z, v.w);
-                    S.sj[k] = j;
+                    r = lo;
                 }
-                __syncthreads();
-                if (wmask) {
-                    const int nr = S.nruns;
-                    for (int r = 0; r < nr; r++) {
-                        const u32 m = S.rmask[r];
-                        if (!(m & wmask)) continue;
-                        int k0 = max(S.rstart[r], s0) - s0, k1 = min(S.rstart[r + 1], s0 + kNearTS) - s0;
-                        if (k0 >= k1) continue;
-                        if (live && (m & mybit)) op.run(tg, A, &S.sxy[k0], &S.sab[k0], &S.sj[k0], k1 - k0);
-                    }
+                for (; r < nruns && S.rstart[r] < s0 + kNearTS; r++) {
+                    const u32 m = S.rmask[r];
+                    if (!(m & wmask)) continue;
+                    const int k0 = max(S.rstart[r], s0) - s0, k1 = min(S.rstart[r + 1], s0 + kNearTS) - s0;
+                    if (live && (m & mybit) && k1 > k0) op.run(tg, A, S, k0, k1 - k0);
                 }
             }
-            if (Op::kSegments && wmask) {
-                for (int e = 0; e < ne; e++) {
-                    const u32 m = S.emk[e];
-                    if (S.esl[e] > S.esf[e] && live && (m & mybit)) op.segments(tg, A, S.esf[e], S.esl[e]);
-                }
+        }
+        if (Op::kSegments && A.nseg > 0 && live) {
+            for (int e = 0; e < ne; e++) {
+                if (!(S.emk[e] & mybit)) continue;
+                const int sl = S.eleaf[e];
+                const int sf = A.L.sfirst[sl], se = A.L.slast[sl];
+                if (se > sf) op.segments(tg, A, sf, se);
             }
         }
         if (multi) {
@@ -331,13 +365,12 @@ struct ConvOp {
     }
     // rotl(dr) * g / (|dr|^2 + eps^2): reciprocal by rcp.approx + one third-order correction
     // (relative error ~ e0^3, e0 <= 2^-20: below 1 ulp; exactness is not required of velocities)
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, const int*,
-                                        int n) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const NearShared& S, int k0, int n) const {
         double rx = t.rx, ry = t.ry;
         const double tx = t.x, ty = t.y;
 #pragma unroll 4
-        for (int k = 0; k < n; k++) {
-            double2 p = xy[k], q = ab[k];
+        for (int k = k0; k < k0 + n; k++) {
+            double2 p = S.sxy[k], q = S.sab[k];
             double dx = tx - p.x, dy = ty - p.y;
             double den = fma(dx, dx, fma(dy, dy, q.y));
             double r0;
@@ -381,7 +414,7 @@ struct DiffOp {
     __device__ __forceinline__ double reach(double epsmax) const { return 8.000008 * epsmax; }
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
-    struct Tgt { double x, y, ie, ie2, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
+    struct Tgt { double x, y, ie, ie2, lim, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
     struct Part { double S1, S2x, S2y, S0, S3x, S3y; };
     __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.S1, t.S2x, t.S2y, t.S0, t.S3x, t.S3y}; }
     __device__ __forceinline__ void combine(Tgt& t, const Part& p) const {
@@ -391,7 +424,7 @@ struct DiffOp {
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.S1 = t.S2x = t.S2y = t.S0 = t.S3x = t.S3y = 0;
-        t.x = t.y = t.ie = t.ie2 = t.g = 0; t.pos = false;
+        t.x = t.y = t.ie = t.ie2 = t.g = 0; t.pos = false; t.lim = 64.0001;
         if (!inrange) return false;
         double g = A.P.g[i];
         if (g == 0) return false;
@@ -426,14 +459,13 @@ struct DiffOp {
         t.S2y = fma(dy, q, t.S2y);
         t.S1 += i1tmp;
     }
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const double2* xy, const double2* ab, const int*,
-                                        int n) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const NearShared& S, int k0, int n) const {
 #pragma unroll 4
-        for (int k = 0; k < n; k++) {
-            double2 p = xy[k];
+        for (int k = k0; k < k0 + n; k++) {
+            double2 p = S.sxy[k];
             double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
             double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (!(d2 * t.ie2 > 64.0001)) hit(t, dx, dy, d2, ab[k].x);
+            if (!(d2 * t.ie2 > t.lim)) hit(t, dx, dy, d2, S.sab[k].x);
         }
     }
     // segment_influence, :107-123
@@ -574,14 +606,13 @@ struct EpsOp {
     }
     // common path: 5 FP64 + one compare; only a source at least as close as the current second
     // neighbour (or a parked NaN) takes the branch
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const double2* xy, const double2*, const int* sj,
-                                        int n) const {
+    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const NearShared& S, int k0, int n) const {
 #pragma unroll 4
-        for (int k = 0; k < n; k++) {
-            double2 p = xy[k];
+        for (int k = k0; k < k0 + n; k++) {
+            double2 p = S.sxy[k];
             double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
             double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (!(d > t.r2)) cand(t, A, d, sj[k]);
+            if (!(d > t.r2)) cand(t, A, d, S.sj[k]);
         }
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}

@@ -1,0 +1,62 @@
+"""The C++ adapter (vvflow_b200/host/vvgpu_adapter.hpp) as a drop-in inside the reference's own step loop.
+
+oracle/_ref/dropin_step is tests/host/dropin_step.cpp compiled against the reference's headers and
+linked with the reference's objects (oracle/_ref/libvvref.so) and libvvgpu.so: the loop of
+utils/vvflow/vvflow.cpp:198-266 for example/cyl_re600.lua where only the hot-path block (:246-257)
+names vvgpu:: classes. It needs /root/reference to BUILD (done by `make -C oracle`), not to run.
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_step")
+
+# README.md:117-120 of the reference: time, force_hydro x / y / o (the only published known answers)
+README_ROWS = [
+    (0.00, "+3.140723e+01", None, None),
+    (0.05, "+4.766549e-01", "+2.608255e-06", None),
+    (0.10, "+8.190494e-01", "-1.868534e-03", "-5.548347e-05"),
+    (0.15, "+7.309763e-01", "-1.069637e-04", "+5.027510e-05"),
+]
+
+
+def _need_bin():
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/dropin_step not built (needs the reference headers; `make -C oracle`)")
+
+
+def test_adapter_fails_loudly_without_gpu():
+    """no CPU fallback: without a CUDA device the first hot-path call raises"""
+    _need_bin()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = subprocess.run([BIN, "free", "1"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 2 and "no CPU fallback" in p.stdout, p.stdout + p.stderr
+
+
+@pytest.mark.gpu
+def test_free_run_reproduces_readme_rows():
+    """cyl_re600 with the GPU hot path reproduces the reference's published force_hydro rows"""
+    _need_bin()
+    p = subprocess.run([BIN, "free", "4"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    rows = [l.split() for l in p.stdout.strip().splitlines()]
+    assert len(rows) == 4
+    for got, want in zip(rows, README_ROWS):
+        assert abs(float(got[0]) - want[0]) < 1e-12
+        for k in (1, 2, 3):
+            if want[k] is not None:
+                assert got[k] == want[k], (got, want)   # all 7 printed digits
+
+
+@pytest.mark.gpu
+def test_lockstep_against_reference_classes():
+    """40 steps from identical state each step: order, g, _1_eps, merge and removal decisions
+    bit-exact; positions, fric, gsum and dead-vortex sums within 1e-10 (checked inside the binary)"""
+    _need_bin()
+    p = subprocess.run([BIN, "lockstep", "40"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert p.stdout.strip().splitlines()[-1].startswith("OK"), p.stdout[-500:]

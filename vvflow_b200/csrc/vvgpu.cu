@@ -385,7 +385,6 @@ int lists_impl(vvgpu_ctx* c) {
     c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
     NEED(ok);
     k_unit_fill<<<cdiv(ng, 128), 128, 0, st>>>(ng, ufirst, ugroup); CKLAUNCH();
-    k_sort_units<<<c->nunits, 256, 0, st>>>(c->Gv(), Units{ugroup, ufirst, sbase}, c->nunits); CKLAUNCH();
     // shard: contiguous slices of groups balanced by unit count (units bound the work per CTA)
     c->shard_g0 = 0; c->shard_g1 = ng;
     if (c->nranks > 1) {
@@ -411,8 +410,8 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
     const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
-    CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NearShared)));
-    k_near<Op><<<nu, kNearThreads, sizeof(NearShared), c->stream>>>(c->near_args(), op); CKLAUNCH();
+    CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwShared)));
+    k_near<Op><<<nu, kLwThreads, sizeof(LwShared), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (nu > g1 - g0) {  // some group has more than one unit
         k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
     }
@@ -437,6 +436,15 @@ int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* lat
         k_wall_pass<2><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
     }
     k_wall_finish<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->t_segperm[c->segcur].as<int>(), B, merge, bd, bk, lcrit, lrestr, latt); CKLAUNCH();
+    return 0;
+}
+
+// source-leaf boxes for the exact pruning of EpsOp (covering the tentative merged positions of M)
+int eps_boxes(vvgpu_ctx* c, MergeState M) {
+    bool ok = true;
+    double* lb = c->lbox.get<double>(5 * (size_t)c->nleaves, &ok);
+    NEED(ok);
+    k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), M, lb); CKLAUNCH();
     return 0;
 }
 
@@ -767,6 +775,8 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     int* dchg = c->d_changed.get<int>(2, &ok);
     NEED(ok);
     if (!merge) {
+        int rcb = eps_boxes(c, MergeState{});
+        if (rcb) return rcb;
         EpsOp<false> op{MergeState{}, MergeState{}, nullptr, lrestr, nullptr, P.ie.as<double>(), dchg};
         return launch_near(c, op);
     }
@@ -792,7 +802,8 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH();
         CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
         EpsOp<false> op{A, B, lcrit, lrestr, dyn, ietmp, dchg};
-        int rc = launch_near(c, op, haveA ? dyn : nullptr);
+        int rc = eps_boxes(c, A);
+        if (!rc) rc = launch_near(c, op, haveA ? dyn : nullptr);
         if (rc) return rc;
         u32 changed = 0;
         rc = read_u32(c, (u32*)dchg, &changed);
@@ -809,7 +820,8 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     // epsilon of the initiators at their merged position (the recursive epsv call, :169), then commit
     MergeState A = mstate(c->mA);
     EpsOp<true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
-    int rc = launch_near(c, opf, dyn);
+    int rc = eps_boxes(c, A);
+    if (!rc) rc = launch_near(c, opf, dyn);
     if (rc) return rc;
     std::swap(c->ie_tmp, P.ie);  // absorbed-before-turn particles kept their old value in ie_tmp (never written)
     CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
@@ -853,7 +865,8 @@ int vvgpu_epsilon_probe(vvgpu_ctx* c, int* ncandidates) {
     k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, Bm); CKLAUNCH();
     CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
     EpsOp<false> op{MergeState{}, Bm, lcrit, lrestr, nullptr, ietmp, dchg};
-    int rc = launch_near(c, op);
+    int rc = eps_boxes(c, MergeState{});
+    if (!rc) rc = launch_near(c, op);
     if (rc) return rc;
     u32 changed = 0;
     rc = read_u32(c, (u32*)dchg, &changed);
@@ -897,7 +910,7 @@ int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
             bool ok = true;
             double* lb = c->lbox.get<double>(5 * (size_t)c->nleaves, &ok);
             NEED(ok);
-            k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), lb); CKLAUNCH();
+            k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), MergeState{}, lb); CKLAUNCH();
             DiffOp op{re, c->d_fric.as<double>()};
             int rc = launch_near(c, op);
             if (rc) return rc;

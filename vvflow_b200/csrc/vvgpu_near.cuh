@@ -1,24 +1,35 @@
-// K3 / K4 / K5 — the three near-field passes over the same pair set:
+// K3 / K4 / K5 — the three near-field passes over the reference's (leaf, near leaf) pair set:
 //   EpsOp   MEpsilonFast::epsv + merge decision        (libvvhd/src/MEpsilonFast.cpp:128-173)
 //   ConvOp  MConvectiveFast::near_nodes_influence      (libvvhd/src/MConvectiveFast.cpp:116-137)
 //           + the per-particle assembly of process_all_lists (:76-86)
 //   DiffOp  MDiffusiveFast::process_vort_list          (libvvhd/src/MDiffusiveFast.cpp:8-48,93-123)
 //
-// One CTA owns one group of 32 consecutive leaves. Its targets are a contiguous slice of the
-// permuted particle array (one target per thread, in chunks of kNearThreads); the group's near
-// source leaves are streamed through shared memory in tiles and every thread walks the tile with
-// broadcast loads. A source leaf is applied to a target only if the leaf's bit is set in the
-// entry's mask, i.e. exactly the (leaf, near leaf) pairs of the reference; a warp skips entries
-// none of its leaves see.
+// Layout ("leaf-warp"): a CTA owns one work unit = one group of 32 consecutive leaves x <= 512
+// entries of the group's near list. Its warps pull TARGET LEAVES from a shared counter; a warp
+// scans the unit's entry table, keeps the source leaves whose mask bit names its leaf (and, for
+// epsilon / diffusive, whose box is within the leaf's exact reach), expands them into a flat
+// list of source particle indices in shared memory and streams that list:
+//   * ConvOp — lanes hold SOURCES (one 32-byte packed record per lane, prefetched), the leaf's
+//     <= 15 targets are broadcast from shared memory, 2 x 15 accumulators stay in registers and
+//     are reduced across lanes once per leaf. Every lane does useful FP64 work on every pair.
+//   * EpsOp / DiffOp — the pruned lists are short; the warp is split into nt x m sub-lanes
+//     (m = 32 / nt), each target's sources are dealt round-robin to its m sub-lanes and the
+//     partial states are merged with a segmented shuffle reduction.
+// A leaf normally holds < 16 particles (Tree_MaxListSize); leaves made by the min-node-size rule
+// can hold more and are processed in chunks of 15 targets.
 #pragma once
 #include "vvgpu_lists.cuh"
 
 namespace vv {
 
-constexpr int kNearThreads = 384;   // one target per thread: 32 leaves x ~10.4 particles fit in one pass
-constexpr int kNearEB = 64;         // list entries per batch
-constexpr int kNearTS = 1024;       // source particles per shared-memory tile
-constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the serial path of one thread)
+constexpr int kLwWarps = 4;
+constexpr int kLwThreads = kLwWarps * 32;
+constexpr int kMaxT = 15;           // targets per pass of a warp
+constexpr int kIdxCap = 1024;       // flat source indices buffered per warp
+constexpr int kIdxFlush = 512;      // the buffer is drained whenever it holds at least this many
+constexpr int kPiece = 16;          // sources appended per entry per round (a normal leaf has < 16)
+constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the work of one CTA)
+constexpr u32 kFullMask = 0xffffffffu;
 
 struct Particles {
     double *x, *y, *g, *vx, *vy, *ie;
@@ -49,55 +60,76 @@ struct NearArgs {
     const double *srx, *sry, *sdlx, *sdly;
 };
 
-struct NearShared {
-    double2 sxy[kNearTS];
-    double2 sab[kNearTS];
-    int sj[kNearTS];                 // particle index of each staged source
-    int epre[kUnitEntries + 1];      // source prefix per entry of the unit (0 sources once filtered out)
-    int epf[kUnitEntries];           // first particle of the entry's leaf
-    u32 emk[kUnitEntries];           // target-leaf mask
-    int eleaf[kUnitEntries];
-    int rstart[kUnitEntries + 1];    // runs of consecutive entries with the same mask (units are mask-sorted)
-    u32 rmask[kUnitEntries];
-    int wsum[8];
-    int nruns;
-    double gbox[5];                  // group's target box + cut-off radius (ops with kFilter)
+struct LwWarp {
+    int idx[kIdxCap];            // flat list of source particle indices
+    double2 txy[kMaxT + 1];      // ConvOp: target positions, broadcast to all lanes
+    double tsave[kMaxT][16];     // sub-lane ops: the target states handed from the init lane to its sub-lanes
+    int tpart[kMaxT + 1];        // particle index of each target slot
+};
+struct LwShared {
+    int4 ent[kUnitEntries];      // first particle, count, first segment, segment count of the entry's leaf
+    u32 emk[kUnitEntries];       // target-leaf mask
+    double ebox[kUnitEntries][4];  // source-leaf box (ops with kFilter)
     int bounds[kGroupLeaves + 1];
+    int next;                    // next target leaf of the group to hand out
+    int anyseg;
+    LwWarp w[kLwWarps];
 };
 
-// exclusive prefix sum of v[0..kUnitEntries) in place, by threads 0..127 (4 entries each); returns the
-// total in *total. Every thread of the CTA must call it (it contains barriers).
-__device__ __forceinline__ void unit_scan(int* v, int* wsum, int* total_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int a0 = 0, a1 = 0, a2 = 0, a3 = 0, inc = 0;
-    if (tid < kUnitEntries / 4) {
-        a0 = v[4 * tid]; a1 = v[4 * tid + 1]; a2 = v[4 * tid + 2]; a3 = v[4 * tid + 3];
-        inc = a0 + a1 + a2 + a3;
-        const int s = inc;
+template <class T>
+__device__ __forceinline__ T shfl_down_struct(const T& v, int o) {
+    static_assert(sizeof(T) % 4 == 0, "word-sized parts only");
+    T r;
+    const u32* a = reinterpret_cast<const u32*>(&v);
+    u32* b = reinterpret_cast<u32*>(&r);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        inc -= s;  // exclusive within the warp
+    for (int k = 0; k < (int)(sizeof(T) / 4); k++) b[k] = __shfl_down_sync(kFullMask, a[k], o);
+    return r;
+}
+
+// ---- ConvOp streaming: lanes = sources, NT targets from shared memory, accumulators in registers
+template <class Op, int NT>
+__device__ __forceinline__ void lw_stream(const Op& op, const NearArgs& A, const LwWarp& W, double* ax, double* ay,
+                                          int nit, int fill, int lane) {
+    double4 s = (lane < fill) ? A.src4[W.idx[lane]] : Op::dummy();
+    for (int it = 0; it < nit; it++) {
+        double4 nx = Op::dummy();
+        const int k = (it + 1) * 32 + lane;
+        if (k < fill) nx = A.src4[W.idx[k]];   // prefetch the next record behind this iteration's math
+#pragma unroll
+        for (int t = 0; t < NT; t++) op.pair(W.txy[t], s, ax[t], ay[t]);
+        s = nx;
     }
-    __syncthreads();
-    if (tid < kUnitEntries / 4) {
-        int off = 0;
-        for (int w = 0; w < warp; w++) off += wsum[w];
-        int ex = off + inc;
-        v[4 * tid] = ex; v[4 * tid + 1] = ex + a0; v[4 * tid + 2] = ex + a0 + a1; v[4 * tid + 3] = ex + a0 + a1 + a2;
-        if (tid == kUnitEntries / 4 - 1) *total_out = ex + a0 + a1 + a2 + a3;
-    }
-    __syncthreads();
 }
 
 template <class Op>
-__global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
+__device__ __forceinline__ void lw_drain_src(const Op& op, const NearArgs& A, LwWarp& W, double* ax, double* ay,
+                                             int& fill, int nt, bool final, int lane) {
+    const int nit = final ? ((fill + 31) >> 5) : (fill >> 5);
+    const int upto = final ? fill : (nit << 5);
+    if (nit > 0) {
+        switch (nt) {
+#define VV_CASE(N) case N: lw_stream<Op, N>(op, A, W, ax, ay, nit, upto, lane); break;
+            VV_CASE(1) VV_CASE(2) VV_CASE(3) VV_CASE(4) VV_CASE(5) VV_CASE(6) VV_CASE(7) VV_CASE(8)
+            VV_CASE(9) VV_CASE(10) VV_CASE(11) VV_CASE(12) VV_CASE(13) VV_CASE(14) VV_CASE(15)
+#undef VV_CASE
+        }
+    }
+    // carry the incomplete last iteration over to the next drain
+    const int r = final ? 0 : (fill & 31);
+    int v = 0;
+    if (lane < r) v = W.idx[upto + lane];
+    __syncwarp();
+    if (lane < r) W.idx[lane] = v;
+    __syncwarp();
+    fill = r;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A, Op op) {
     extern __shared__ __align__(16) unsigned char near_smem[];
-    NearShared& S = *reinterpret_cast<NearShared*>(near_smem);
-    const int tid = threadIdx.x;
+    LwShared& S = *reinterpret_cast<LwShared*>(near_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u = A.u0 + blockIdx.x;
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
@@ -105,150 +137,163 @@ __global__ void __launch_bounds__(kNearThreads) k_near(NearArgs A, Op op) {
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    if (Op::kFilter && tid < 32) {  // box of the group's targets and the largest cut-off radius among them
-        double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
-        if (tid < nl) {
-            const double* b = A.lbox + 5ll * (l0 + tid);
-            x0 = b[0]; x1 = b[1]; y0 = b[2]; y1 = b[3]; em = b[4];
+    if (tid == 0) { S.next = 0; S.anyseg = 0; }
+    const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
+    const int ne = (int)(min(A.G.ptr[g + 1], e0 + kUnitEntries) - e0);
+    __syncthreads();
+    // ---- the unit's entry table, once per CTA
+    for (int e = tid; e < ne; e += kLwThreads) {
+        const int sl = A.G.leaf[e0 + e];
+        const int f = A.L.first[sl];
+        int4 en = make_int4(f, A.L.last[sl] - f, 0, 0);
+        if (Op::kSegments && A.nseg > 0) {
+            en.z = A.L.sfirst[sl]; en.w = A.L.slast[sl] - en.z;
+            if (en.w > 0) S.anyseg = 1;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-            em = fmax(em, __shfl_xor_sync(0xffffffffu, em, o));
+        S.ent[e] = en;
+        S.emk[e] = A.G.mask[e0 + e];
+        if constexpr (Op::kFilter) {
+            const double* b = A.lbox + 5ll * sl;
+            S.ebox[e][0] = b[0]; S.ebox[e][1] = b[1]; S.ebox[e][2] = b[2]; S.ebox[e][3] = b[3];
         }
-        if (tid == 0) { S.gbox[0] = x0; S.gbox[1] = x1; S.gbox[2] = y0; S.gbox[3] = y1; S.gbox[4] = op.reach(em); }
     }
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
-    const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
-    const int ne = (int)(min(A.G.ptr[g + 1], e0 + kUnitEntries) - e0);
+    LwWarp& W = S.w[warp];
     typename Op::Part* scratch = (typename Op::Part*)A.scratch;
+    const size_t sbase = multi ? ((size_t)A.U.sbase[g] + (size_t)chunk * (t1 - t0)) : 0;
 
-    // ---- prologue: the unit's whole entry table, in parallel (one entry per thread)
-    for (int e = tid; e < kUnitEntries; e += kNearThreads) {
-        int cnt = 0, f = 0, sl = 0;
-        u32 mk = 0;
-        if (e < ne) {
-            sl = A.G.leaf[e0 + e];
-            mk = A.G.mask[e0 + e];
-            f = A.L.first[sl];
-            cnt = A.L.last[sl] - f;
-            if (Op::kFilter) {  // gap between the source leaf's box and the group's box
-                const double* b = A.lbox + 5ll * sl;
-                double gx = fmax(0., fmax(b[0] - S.gbox[1], S.gbox[0] - b[1]));
-                double gy = fmax(0., fmax(b[2] - S.gbox[3], S.gbox[2] - b[3]));
-                if (gx * gx + gy * gy > S.gbox[4] * S.gbox[4]) cnt = 0;
-            }
-        }
-        S.epre[e] = cnt; S.epf[e] = f; S.emk[e] = mk; S.eleaf[e] = sl;
-    }
-    __syncthreads();
-    // a run opens where the mask changes (only among entries that still have sources)
-    for (int e = tid; e < kUnitEntries; e += kNearThreads) {
-        int flag = 0;
-        if (e < ne && S.epre[e] > 0) {
-            int p = e - 1;
-            while (p >= 0 && S.epre[p] == 0) p--;   // previous surviving entry
-            flag = (p < 0) || (S.emk[p] != S.emk[e]);
-        }
-        S.rstart[e] = flag;
-    }
-    __syncthreads();
-    int total, nruns;
-    unit_scan(S.epre, S.wsum, &S.rstart[kUnitEntries]);   // total sources parked in rstart[kUnitEntries]
-    total = S.rstart[kUnitEntries];
-    __syncthreads();
-    if (tid == 0) S.epre[kUnitEntries] = total;
-    // run ids: scan the flags, then every opening entry records its run
-    int myflag[2] = {0, 0};
-    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++) myflag[q] = S.rstart[e];
-    __syncthreads();
-    unit_scan(S.rstart, S.wsum, &S.nruns);
-    nruns = S.nruns;
-    int myrid[2];
-    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++) myrid[q] = S.rstart[e];
-    __syncthreads();
-    for (int q = 0, e = tid; e < kUnitEntries; e += kNearThreads, q++)
-        if (myflag[q]) { S.rstart[myrid[q]] = S.epre[e]; S.rmask[myrid[q]] = S.emk[e]; }
-    if (tid == 0) S.rstart[nruns] = total;
-    __syncthreads();
-
-    for (int tb = t0; tb < t1; tb += kNearThreads) {
-        const int i = tb + tid;
-        const bool inrange = i < t1;
+    for (;;) {
         int lt = 0;
-        if (inrange) {  // largest k with bounds[k] <= i
-            int lo = 0, hi = nl - 1;
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (S.bounds[mid] <= i) lo = mid; else hi = mid - 1;
-            }
-            lt = lo;
-        }
-        typename Op::Tgt tg;
-        const bool live = op.init(tg, A, i, l0 + lt, inrange);
-        if (live) op.seed(tg, A, l0 + lt);
-        // leaves covered by this warp's live targets
-        int ltmin = live ? lt : 64, ltmax = live ? lt : -1;
+        if (lane == 0) lt = atomicAdd(&S.next, 1);
+        lt = __shfl_sync(kFullMask, lt, 0);
+        if (lt >= nl) break;
+        const int leaf = l0 + lt;
+        const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
+        for (int tb = pf; tb < pl; tb += kMaxT) {
+            const int np = min(kMaxT, pl - tb);
+            typename Op::Tgt tg;
+            const int i = tb + lane;
+            const bool live = op.init(tg, A, i, leaf, lane < np);
+            if (live) op.seed(tg, A, leaf);
+            const u32 lm = __ballot_sync(kFullMask, live);
+            const int nt = __popc(lm);
+            if (nt == 0) continue;
+            const int slot = __popc(lm & lanemask_lt());
+            // box of the live targets and their largest squared reach (exact pruning of source leaves)
+            double bx0 = DBL_MAX, bx1 = -DBL_MAX, by0 = DBL_MAX, by1 = -DBL_MAX, R2 = 0;
+            if constexpr (Op::kFilter) {
+                if (live) { bx0 = bx1 = tg.x; by0 = by1 = tg.y; R2 = op.reach2(tg); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ltmin = min(ltmin, __shfl_xor_sync(0xffffffffu, ltmin, o));
-            ltmax = max(ltmax, __shfl_xor_sync(0xffffffffu, ltmax, o));
-        }
-        u32 wmask = 0;
-        if (ltmax >= 0) {
-            u32 hi = (ltmax == 31) ? 0xffffffffu : ((1u << (ltmax + 1)) - 1u);
-            wmask = hi & ~((1u << ltmin) - 1u);
-        }
-        const u32 mybit = 1u << lt;
-
-        for (int s0 = 0; s0 < total; s0 += kNearTS) {
-            if (s0 > 0 || tb > t0) __syncthreads();  // the previous tile has been consumed
-            const int nsrc = min(kNearTS, total - s0);
-            for (int k = tid; k < nsrc; k += kNearThreads) {
-                const int F = s0 + k;
-                int lo = 0, hi = ne - 1;  // largest e with epre[e] <= F (entries without sources never match)
-                while (lo < hi) {
-                    int mid = (lo + hi + 1) >> 1;
-                    if (S.epre[mid] <= F) lo = mid; else hi = mid - 1;
+                for (int o = 16; o > 0; o >>= 1) {
+                    bx0 = fmin(bx0, __shfl_xor_sync(kFullMask, bx0, o)); bx1 = fmax(bx1, __shfl_xor_sync(kFullMask, bx1, o));
+                    by0 = fmin(by0, __shfl_xor_sync(kFullMask, by0, o)); by1 = fmax(by1, __shfl_xor_sync(kFullMask, by1, o));
+                    R2 = fmax(R2, __shfl_xor_sync(kFullMask, R2, o));
                 }
-                const int j = S.epf[lo] + (F - S.epre[lo]);
-                const double4 v = A.src4[j];
-                S.sxy[k] = make_double2(v.x, v.y);
-                S.sab[k] = make_double2(v.z, v.w);
-                S.sj[k] = j;
+                R2 *= 1.000000001;  // the skip stays strictly conservative against rounding in the gap
             }
-            __syncthreads();
-            if (wmask) {
-                int r = 0;
-                {   // first run that reaches into this tile
-                    int lo = 0, hi = nruns - 1;
-                    while (lo < hi) {
-                        int mid = (lo + hi) >> 1;
-                        if (S.rstart[mid + 1] > s0) hi = mid; else lo = mid + 1;
+            // sub-lane layout of EpsOp / DiffOp
+            int m = 1, myslot = 0, sub = 0;
+            bool active = false;
+            typename Op::Tgt my;
+            double ax[kMaxT], ay[kMaxT];
+            if constexpr (Op::kLanesAreSources) {
+                if (live) W.txy[slot] = make_double2(tg.x, tg.y);
+#pragma unroll
+                for (int t = 0; t < kMaxT; t++) { ax[t] = 0; ay[t] = 0; }
+            } else {
+                static_assert(sizeof(typename Op::Tgt) <= sizeof(W.tsave[0]), "tsave slot too small");
+                if (live) { *reinterpret_cast<typename Op::Tgt*>(W.tsave[slot]) = tg; W.tpart[slot] = i; }
+                m = 32 / nt;
+                myslot = lane / m;
+                sub = lane - myslot * m;
+                active = myslot < nt;
+            }
+            __syncwarp();
+            if constexpr (!Op::kLanesAreSources) {
+                my = *reinterpret_cast<const typename Op::Tgt*>(W.tsave[active ? myslot : 0]);
+                // wall segments of the near leaves (MDiffusiveFast.cpp:26-34): one sub-lane per target
+                if (Op::kSegments && S.anyseg && active && sub == 0) {
+                    for (int e = 0; e < ne; e++) {
+                        if (!((S.emk[e] >> lt) & 1u)) continue;
+                        const int4 en = S.ent[e];
+                        if (en.w > 0) op.segments(my, A, en.z, en.z + en.w);
                     }
-                    r = lo;
-                }
-                for (; r < nruns && S.rstart[r] < s0 + kNearTS; r++) {
-                    const u32 m = S.rmask[r];
-                    if (!(m & wmask)) continue;
-                    const int k0 = max(S.rstart[r], s0) - s0, k1 = min(S.rstart[r + 1], s0 + kNearTS) - s0;
-                    if (live && (m & mybit) && k1 > k0) op.run(tg, A, S, k0, k1 - k0);
                 }
             }
-        }
-        if (Op::kSegments && A.nseg > 0 && live) {
-            for (int e = 0; e < ne; e++) {
-                if (!(S.emk[e] & mybit)) continue;
-                const int sl = S.eleaf[e];
-                const int sf = A.L.sfirst[sl], se = A.L.slast[sl];
-                if (se > sf) op.segments(tg, A, sf, se);
+            // ---- scan the entry table, expand the kept leaves into source indices, stream them
+            int fill = 0;
+            for (int eb = 0; eb < ne; eb += 32) {
+                const int e = eb + lane;
+                int cnt = 0, f = 0;
+                if (e < ne && ((S.emk[e] >> lt) & 1u)) {
+                    const int4 en = S.ent[e];
+                    f = en.x; cnt = en.y;
+                    if constexpr (Op::kFilter) if (cnt) {
+                        const double* b = S.ebox[e];
+                        const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
+                        const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
+                        if (gx * gx + gy * gy > R2) cnt = 0;
+                    }
+                }
+                while (__any_sync(kFullMask, cnt > 0)) {
+                    const int c = min(cnt, kPiece);
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFullMask, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    const int tot = __shfl_sync(kFullMask, inc, 31);
+                    int* dst = W.idx + fill + inc - c;
+                    for (int k = 0; k < c; k++) dst[k] = f + k;
+                    fill += tot; cnt -= c; f += c;
+                    __syncwarp();
+                    if (fill >= kIdxFlush) {
+                        if constexpr (Op::kLanesAreSources) lw_drain_src(op, A, W, ax, ay, fill, nt, false, lane);
+                        else {
+                            if (active) for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
+                            __syncwarp();
+                            fill = 0;
+                        }
+                    }
+                }
+            }
+            if constexpr (Op::kLanesAreSources) {
+                lw_drain_src(op, A, W, ax, ay, fill, nt, true, lane);
+                // lane sums -> the lane that owns the target
+#pragma unroll
+                for (int t = 0; t < kMaxT; t++) {
+                    if (t < nt) {
+                        double vx = ax[t], vy = ay[t];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            vx += __shfl_xor_sync(kFullMask, vx, o);
+                            vy += __shfl_xor_sync(kFullMask, vy, o);
+                        }
+                        if (live && slot == t) op.take(tg, vx, vy);
+                    }
+                }
+                if (live) {
+                    if (multi) scratch[sbase + (i - t0)] = op.part(tg);
+                    else op.finish(tg, A, i, leaf);
+                }
+            } else {
+                if (active) for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
+                __syncwarp();
+                // merge the m sub-lane states of every target into its first sub-lane
+                for (int o = 1; o < m; o <<= 1) {
+                    const typename Op::Part q = shfl_down_struct(op.part(my), o);
+                    if (active && sub + o < m) op.combine(my, q);
+                }
+                if (active && sub == 0) {
+                    const int ip = W.tpart[myslot];
+                    if (multi) scratch[sbase + (ip - t0)] = op.part(my);
+                    else op.finish(my, A, ip, leaf);
+                }
+                __syncwarp();
             }
         }
-        if (multi) {
-            if (live) scratch[(size_t)A.U.sbase[g] + (size_t)chunk * (t1 - t0) + (i - t0)] = op.part(tg);
-        } else if (live) op.finish(tg, A, i, l0 + lt);
     }
 }
 
@@ -302,43 +347,12 @@ __global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4
     if (j < n) out[j] = Op::pack(P, j, dyn);
 }
 
-// Sort the entries of every unit by (mask, leaf): entries that are seen by the same target leaves
-// become one long run, so the per-entry bookkeeping of k_near is paid per run. One CTA per unit,
-// bitonic sort of <= kUnitEntries 64-bit keys in shared memory. Deterministic.
-__global__ void __launch_bounds__(256) k_sort_units(GroupLists G, Units U, int nunits) {
-    __shared__ u64 key[kUnitEntries];
-    const int u = blockIdx.x;
-    if (u >= nunits) return;
-    const int g = U.group[u];
-    const int chunk = u - U.first[g];
-    const long long e0 = G.ptr[g] + (long long)chunk * kUnitEntries;
-    const int ne = (int)min((long long)kUnitEntries, G.ptr[g + 1] - e0);
-    for (int k = threadIdx.x; k < kUnitEntries; k += blockDim.x)
-        key[k] = (k < ne) ? (((u64)G.mask[e0 + k] << 32) | (u32)G.leaf[e0 + k]) : ~0ull;
-    __syncthreads();
-    for (int size = 2; size <= kUnitEntries; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < kUnitEntries / 2; t += blockDim.x) {
-                int lo = 2 * t - (t & (stride - 1));
-                int hi = lo + stride;
-                bool up = ((lo & size) == 0);
-                u64 a = key[lo], b = key[hi];
-                if ((a > b) == up) { key[lo] = b; key[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-        G.leaf[e0 + k] = (int)(u32)(key[k] & 0xffffffffull);
-        G.mask[e0 + k] = (u32)(key[k] >> 32);
-    }
-}
-
 // ------------------------------------------------------------------------------------------ K4
 struct ConvOp {
     static constexpr bool kSegments = false;
     static constexpr bool kFilter = false;
-    __device__ __forceinline__ double reach(double) const { return 0; }
+    static constexpr bool kLanesAreSources = true;
+    static constexpr int kMinBlocks = 3;   // 128 threads x 3: up to 170 registers for the 30 accumulators
     double inf_vx, inf_vy, eps2_div_srcg;
     const double* taylor;  // 4 per leaf
     const double* sinks;   // (x,y,g) triples
@@ -363,27 +377,22 @@ struct ConvOp {
         double e = 1. / P.ie[j];
         return (g == 0) ? make_double4(P.x[j], P.y[j], 0., 1.) : make_double4(P.x[j], P.y[j], g, e * e);
     }
-    // rotl(dr) * g / (|dr|^2 + eps^2): reciprocal by rcp.approx + one third-order correction
-    // (relative error ~ e0^3, e0 <= 2^-20: below 1 ulp; exactness is not required of velocities)
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const NearShared& S, int k0, int n) const {
-        double rx = t.rx, ry = t.ry;
-        const double tx = t.x, ty = t.y;
-#pragma unroll 4
-        for (int k = k0; k < k0 + n; k++) {
-            double2 p = S.sxy[k], q = S.sab[k];
-            double dx = tx - p.x, dy = ty - p.y;
-            double den = fma(dx, dx, fma(dy, dy, q.y));
-            double r0;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
-            double e = fma(-den, r0, 1.0);
-            double e2 = fma(e, e, e);
-            double gr = q.x * r0;
-            double w = fma(gr, e2, gr);
-            rx = fma(-dy, w, rx);
-            ry = fma(dx, w, ry);
-        }
-        t.rx = rx; t.ry = ry;
+    // rotl(dr) * g / (|dr|^2 + eps^2). Reciprocal = rcp.approx.ftz.f64 (MUFU.RCP64H, relative error
+    // e0 <= 2^-19.9 measured on B200, tools/microbench2.cu) + one Newton step: 1/den = r0 (1 + e) up to
+    // e0^2 <= 2^-39.8 ~ 1e-12 per pair, two orders below the 1e-10 bar on velocities. 9 FP64 ops / pair.
+    static __device__ __forceinline__ double4 dummy() { return make_double4(0., 0., 0., 1.); }
+    __device__ __forceinline__ void pair(const double2 p, const double4 s, double& ax, double& ay) const {
+        const double dx = p.x - s.x, dy = p.y - s.y;
+        const double den = fma(dx, dx, fma(dy, dy, s.w));
+        double r0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
+        const double e = fma(-den, r0, 1.0);
+        const double gr = s.z * r0;
+        const double w = fma(gr, e, gr);
+        ax = fma(-dy, w, ax);
+        ay = fma(dx, w, ay);
     }
+    __device__ __forceinline__ void take(Tgt& t, double vx, double vy) const { t.rx = vx; t.ry = vy; }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
         double vx = inf_vx + t.rx * k1_2Pi, vy = inf_vy + t.ry * k1_2Pi;
@@ -411,7 +420,8 @@ struct DiffOp {
     // only sources within 8 eps of a target contribute (:101): leaves farther than that from the whole
     // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
     static constexpr bool kFilter = true;
-    __device__ __forceinline__ double reach(double epsmax) const { return 8.000008 * epsmax; }
+    static constexpr bool kLanesAreSources = false;
+    static constexpr int kMinBlocks = 4;
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, lim, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
@@ -459,14 +469,13 @@ struct DiffOp {
         t.S2y = fma(dy, q, t.S2y);
         t.S1 += i1tmp;
     }
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs&, const NearShared& S, int k0, int n) const {
-#pragma unroll 4
-        for (int k = k0; k < k0 + n; k++) {
-            double2 p = S.sxy[k];
-            double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
-            double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (!(d2 * t.ie2 > t.lim)) hit(t, dx, dy, d2, S.sab[k].x);
-        }
+    // squared reach of a target: sources farther than 8 eps never contribute (:101)
+    __device__ __forceinline__ double reach2(const Tgt& t) const { double r = 8.000008 / t.ie; return r * r; }
+    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
+        const double4 v = A.src4[j];
+        double dx = VV_SUB(t.x, v.x), dy = VV_SUB(t.y, v.y);
+        double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+        if (!(d2 * t.ie2 > t.lim)) hit(t, dx, dy, d2, v.z);
     }
     // segment_influence, :107-123
     __device__ __forceinline__ void segments(Tgt& t, const NearArgs& A, int sf, int sl) const {
@@ -518,8 +527,11 @@ constexpr int kNoAbs = 0x7fffffff;
 template <bool FINAL>
 struct EpsOp {
     static constexpr bool kSegments = false;
-    static constexpr bool kFilter = false;
-    __device__ __forceinline__ double reach(double) const { return 0; }
+    // a source leaf whose box is farther from the leaf's targets than the largest seeded second-neighbour
+    // distance cannot hold a closer neighbour of any of them: exact pruning
+    static constexpr bool kFilter = true;
+    static constexpr bool kLanesAreSources = false;
+    static constexpr int kMinBlocks = 6;
     MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
     MergeState B_;      // recomputed solution (decision mode only)
     const double* lcrit;   // per leaf merge_criteria_sq (NaN: never merge)
@@ -527,7 +539,8 @@ struct EpsOp {
     const unsigned char* dyn;  // per particle: has a timeline entry in A_
     double* ie_out;
     int* changed;
-    struct Tgt { double x, y, r1, r2; int i, i1, i2; };
+    struct Tgt { double x, y, r1, r2; int i, i1, i2, pad_; };
+    __device__ __forceinline__ double reach2(const Tgt& t) const { return t.r2; }
     struct Part { double r1, r2; int i1, i2; };
     __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.r1, t.r2, t.i1, t.i2}; }
     // two smallest in (distance, index) order == the reference's first-seen-wins scan (:143-151)
@@ -606,14 +619,11 @@ struct EpsOp {
     }
     // common path: 5 FP64 + one compare; only a source at least as close as the current second
     // neighbour (or a parked NaN) takes the branch
-    __device__ __forceinline__ void run(Tgt& t, const NearArgs& A, const NearShared& S, int k0, int n) const {
-#pragma unroll 4
-        for (int k = k0; k < k0 + n; k++) {
-            double2 p = S.sxy[k];
-            double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
-            double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-            if (!(d > t.r2)) cand(t, A, d, S.sj[k]);
-        }
+    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
+        const double2 p = *reinterpret_cast<const double2*>(A.src4 + j);
+        double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
+        double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+        if (!(d > t.r2)) cand(t, A, d, j);
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
@@ -677,15 +687,21 @@ __global__ void k_merge_dyn(int n, MergeState M, unsigned char* dyn) {
     dyn[i] = (M.init[i] != 0 || M.absby[i] != kNoAbs) ? 1 : 0;
 }
 
-// current bounding box and largest epsilon of every leaf's particles (after epsilon / merging)
-__global__ void k_leaf_box(LeafDev L, int nleaves, Particles P, double* lbox) {
+// current bounding box and largest epsilon of every leaf's particles (after epsilon / merging). With a
+// tentative merge solution M (epsilon rounds), the box also covers the post-merge position of every
+// initiator, so that it bounds every state a source of the leaf can be seen in.
+__global__ void k_leaf_box(LeafDev L, int nleaves, Particles P, MergeState M, double* lbox) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaves) return;
     double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
     for (int i = L.first[l]; i < L.last[l]; i++) {
         double x = P.x[i], y = P.y[i];
         x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
-        if (P.g[i] != 0) em = fmax(em, 1. / P.ie[i]);
+        if (M.absby && M.init[i]) {
+            x = M.nx[i]; y = M.ny[i];
+            x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+        }
+        if (P.g[i] != 0 && P.ie[i] != 0) em = fmax(em, 1. / P.ie[i]);
     }
     double* b = lbox + 5ll * l;
     b[0] = x0; b[1] = x1; b[2] = y0; b[3] = y1; b[4] = em;

@@ -410,8 +410,8 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
     const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
-    CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwShared)));
-    k_near<Op><<<nu, kLwThreads, sizeof(LwShared), c->stream>>>(c->near_args(), op); CKLAUNCH();
+    CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
+    k_near<Op><<<nu, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (nu > g1 - g0) {  // some group has more than one unit
         k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
     }

@@ -20,14 +20,19 @@
 #pragma once
 #include "vvgpu_lists.cuh"
 
+#ifndef VV_CONV_MINB
+#define VV_CONV_MINB 3
+#endif
+#ifndef VV_CONV_LANES_SRC
+#define VV_CONV_LANES_SRC 1
+#endif
+
 namespace vv {
 
 constexpr int kLwWarps = 4;
 constexpr int kLwThreads = kLwWarps * 32;
 constexpr int kMaxT = 15;           // targets per pass of a warp
 constexpr int kIdxCap = 1024;       // flat source indices buffered per warp
-constexpr int kIdxFlush = 512;      // the buffer is drained whenever it holds at least this many
-constexpr int kPiece = 16;          // sources appended per entry per round (a normal leaf has < 16)
 constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the work of one CTA)
 constexpr u32 kFullMask = 0xffffffffu;
 
@@ -60,20 +65,24 @@ struct NearArgs {
     const double *srx, *sry, *sdlx, *sdly;
 };
 
-struct LwWarp {
-    int idx[kIdxCap];            // flat list of source particle indices
-    double2 txy[kMaxT + 1];      // ConvOp: target positions, broadcast to all lanes
-    double tsave[kMaxT][16];     // sub-lane ops: the target states handed from the init lane to its sub-lanes
-    int tpart[kMaxT + 1];        // particle index of each target slot
+template <class Op>
+struct LwWarpT {
+    static constexpr int kCap = Op::kLanesAreSources ? kIdxCap : kIdxCap / 2;
+    static constexpr int kFlush = kCap / 2;
+    int idx[kCap];                                             // flat list of source particle indices
+    double2 txy[Op::kLanesAreSources ? kMaxT + 1 : 1];         // ConvOp: target positions, broadcast to all lanes
+    double tsave[Op::kLanesAreSources ? 1 : kMaxT][16];        // sub-lane ops: target states handed to the sub-lanes
+    int tpart[kMaxT + 1];                                      // particle index of each target slot
 };
-struct LwShared {
+template <class Op>
+struct LwSharedT {
     int4 ent[kUnitEntries];      // first particle, count, first segment, segment count of the entry's leaf
     u32 emk[kUnitEntries];       // target-leaf mask
-    double ebox[kUnitEntries][4];  // source-leaf box (ops with kFilter)
+    double ebox[Op::kFilter ? kUnitEntries : 1][4];   // source-leaf box (ops with kFilter)
     int bounds[kGroupLeaves + 1];
     int next;                    // next target leaf of the group to hand out
     int anyseg;
-    LwWarp w[kLwWarps];
+    LwWarpT<Op> w[kLwWarps];
 };
 
 template <class T>
@@ -87,48 +96,74 @@ __device__ __forceinline__ T shfl_down_struct(const T& v, int o) {
     return r;
 }
 
-// ---- ConvOp streaming: lanes = sources, NT targets from shared memory, accumulators in registers
-template <class Op, int NT>
-__device__ __forceinline__ void lw_stream(const Op& op, const NearArgs& A, const LwWarp& W, double* ax, double* ay,
-                                          int nit, int fill, int lane) {
-    double4 s = (lane < fill) ? A.src4[W.idx[lane]] : Op::dummy();
-    for (int it = 0; it < nit; it++) {
-        double4 nx = Op::dummy();
-        const int k = (it + 1) * 32 + lane;
-        if (k < fill) nx = A.src4[W.idx[k]];   // prefetch the next record behind this iteration's math
+// ---- ConvOp streaming: lanes = sources, targets from shared memory, accumulators in registers.
+// The nt <= 15 targets of a pass sit in up to three groups of at most five slots (bases 0, 5, 10)
+// of as equal size as possible, so that every group offers 3-5 independent dependency chains
+// (tools/microbench3.cu: 9+ chains per SM sub-partition fill the FP64 pipe). One copy of the code
+// serves every target count: per-count variants overflow the instruction cache (ncu:
+// stall_no_instruction dominated a 15-variant build).
+struct LwGroups {
+    int s[3];   // slots used in each group
+    __device__ __forceinline__ void set(int nt) {
+        const int ng = (nt + 4) / 5, q = nt / ng, r = nt - q * ng;
+        s[0] = q + (0 < r ? 1 : 0);
+        s[1] = (ng > 1) ? q + (1 < r ? 1 : 0) : 0;
+        s[2] = (ng > 2) ? q : 0;
+    }
+    __device__ __forceinline__ int slot(int k) const {   // k-th live target -> slot
+        if (k < s[0]) return k;
+        k -= s[0];
+        if (k < s[1]) return 5 + k;
+        return 10 + (k - s[1]);
+    }
+    __device__ __forceinline__ bool used(int t) const { return (t % 5) < s[t / 5]; }
+};
+
+template <class Op, int BASE, int N>
+__device__ __forceinline__ void lw_group(const Op& op, const LwWarpT<Op>& W, const double4& s, const double4& s2,
+                                         double (&ax)[kMaxT], double (&ay)[kMaxT]) {
 #pragma unroll
-        for (int t = 0; t < NT; t++) op.pair(W.txy[t], s, ax[t], ay[t]);
-        s = nx;
+    for (int t = 0; t < N; t++) {
+        const double2 p = W.txy[BASE + t];   // one broadcast load serves both sources of the lane
+        op.pair(p, s, ax[BASE + t], ay[BASE + t]);
+        op.pair(p, s2, ax[BASE + t], ay[BASE + t]);
     }
 }
 
+// Two sources per lane and iteration (64 per warp): halves the shared-memory loads, branches and
+// loop overhead per pair and doubles the independent chains in flight.
 template <class Op>
-__device__ __forceinline__ void lw_drain_src(const Op& op, const NearArgs& A, LwWarp& W, double* ax, double* ay,
-                                             int& fill, int nt, bool final, int lane) {
-    const int nit = final ? ((fill + 31) >> 5) : (fill >> 5);
-    const int upto = final ? fill : (nit << 5);
-    if (nit > 0) {
-        switch (nt) {
-#define VV_CASE(N) case N: lw_stream<Op, N>(op, A, W, ax, ay, nit, upto, lane); break;
-            VV_CASE(1) VV_CASE(2) VV_CASE(3) VV_CASE(4) VV_CASE(5) VV_CASE(6) VV_CASE(7) VV_CASE(8)
-            VV_CASE(9) VV_CASE(10) VV_CASE(11) VV_CASE(12) VV_CASE(13) VV_CASE(14) VV_CASE(15)
-#undef VV_CASE
+__device__ __forceinline__ void lw_stream(const Op& op, const NearArgs& A, const LwWarpT<Op>& W, const int* idx,
+                                          double (&ax)[kMaxT], double (&ay)[kMaxT], int nit, int fill, const LwGroups& G,
+                                          int lane) {
+    double4 s = (lane < fill) ? A.src4[idx[lane]] : Op::dummy();
+    double4 s2 = (lane + 32 < fill) ? A.src4[idx[lane + 32]] : Op::dummy();
+    for (int it = 0; it < nit; it++) {
+        double4 nx = Op::dummy(), nx2 = Op::dummy();
+        const int k = (it + 1) * 64 + lane;
+        if (k < fill) nx = A.src4[idx[k]];   // prefetch the next records behind this iteration's math
+        if (k + 32 < fill) nx2 = A.src4[idx[k + 32]];
+#define VV_GROUP(BASE, SZ)                                                     \
+        if (SZ >= 4) {                                                         \
+            if (SZ == 5) lw_group<Op, BASE, 5>(op, W, s, s2, ax, ay);          \
+            else lw_group<Op, BASE, 4>(op, W, s, s2, ax, ay);                  \
+        } else if (SZ == 3) lw_group<Op, BASE, 3>(op, W, s, s2, ax, ay);       \
+        else if (SZ == 2) lw_group<Op, BASE, 2>(op, W, s, s2, ax, ay);         \
+        else lw_group<Op, BASE, 1>(op, W, s, s2, ax, ay);
+        VV_GROUP(0, G.s[0])
+        if (G.s[1]) {
+            VV_GROUP(5, G.s[1])
+            if (G.s[2]) { VV_GROUP(10, G.s[2]) }
         }
+#undef VV_GROUP
+        s = nx; s2 = nx2;
     }
-    // carry the incomplete last iteration over to the next drain
-    const int r = final ? 0 : (fill & 31);
-    int v = 0;
-    if (lane < r) v = W.idx[upto + lane];
-    __syncwarp();
-    if (lane < r) W.idx[lane] = v;
-    __syncwarp();
-    fill = r;
 }
 
 template <class Op>
 __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A, Op op) {
     extern __shared__ __align__(16) unsigned char near_smem[];
-    LwShared& S = *reinterpret_cast<LwShared*>(near_smem);
+    LwSharedT<Op>& S = *reinterpret_cast<LwSharedT<Op>*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u = A.u0 + blockIdx.x;
     const int g = A.U.group[u];
@@ -159,7 +194,9 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     }
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
-    LwWarp& W = S.w[warp];
+    LwWarpT<Op>& W = S.w[warp];
+    constexpr int kFlush = LwWarpT<Op>::kFlush;
+    constexpr int kPiece = kFlush / 32;   // sources appended per entry per round: 32 x kPiece fills half a buffer
     typename Op::Part* scratch = (typename Op::Part*)A.scratch;
     const size_t sbase = multi ? ((size_t)A.U.sbase[g] + (size_t)chunk * (t1 - t0)) : 0;
 
@@ -197,8 +234,10 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
             bool active = false;
             typename Op::Tgt my;
             double ax[kMaxT], ay[kMaxT];
+            LwGroups GR;
             if constexpr (Op::kLanesAreSources) {
-                if (live) W.txy[slot] = make_double2(tg.x, tg.y);
+                GR.set(nt);
+                if (live) W.txy[GR.slot(slot)] = make_double2(tg.x, tg.y);
 #pragma unroll
                 for (int t = 0; t < kMaxT; t++) { ax[t] = 0; ay[t] = 0; }
             } else {
@@ -222,56 +261,87 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
                 }
             }
             // ---- scan the entry table, expand the kept leaves into source indices, stream them
-            int fill = 0;
-            for (int eb = 0; eb < ne; eb += 32) {
-                const int e = eb + lane;
-                int cnt = 0, f = 0;
-                if (e < ne && ((S.emk[e] >> lt) & 1u)) {
-                    const int4 en = S.ent[e];
-                    f = en.x; cnt = en.y;
-                    if constexpr (Op::kFilter) if (cnt) {
-                        const double* b = S.ebox[e];
-                        const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
-                        const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
-                        if (gx * gx + gy * gy > R2) cnt = 0;
-                    }
-                }
-                while (__any_sync(kFullMask, cnt > 0)) {
-                    const int c = min(cnt, kPiece);
-                    int inc = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(kFullMask, inc, o);
-                        if (lane >= o) inc += t;
-                    }
-                    const int tot = __shfl_sync(kFullMask, inc, 31);
-                    int* dst = W.idx + fill + inc - c;
-                    for (int k = 0; k < c; k++) dst[k] = f + k;
-                    fill += tot; cnt -= c; f += c;
-                    __syncwarp();
-                    if (fill >= kIdxFlush) {
-                        if constexpr (Op::kLanesAreSources) lw_drain_src(op, A, W, ax, ay, fill, nt, false, lane);
-                        else {
-                            if (active) for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
-                            __syncwarp();
-                            fill = 0;
+            int fill = 0, eb = 0, cnt = 0, f = 0;
+            for (;;) {
+                const int* ip = W.idx;
+                int nit = 0, upto = 0, carry = 0;
+                bool final = false;
+                {
+                    // refill: until the buffer is worth draining or the table is exhausted
+                    bool pending = __any_sync(kFullMask, cnt > 0);
+                    while (fill < kFlush && (pending || eb < ne)) {
+                        if (!pending) {
+                            const int e = eb + lane;
+                            eb += 32;
+                            if (e < ne && ((S.emk[e] >> lt) & 1u)) {
+                                const int4 en = S.ent[e];
+                                f = en.x; cnt = en.y;
+                                if constexpr (Op::kFilter) if (cnt) {
+                                    const double* b = S.ebox[e];
+                                    const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
+                                    const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
+                                    if (gx * gx + gy * gy > R2) cnt = 0;
+                                }
+                            }
+                            pending = __any_sync(kFullMask, cnt > 0);
+                            continue;
                         }
+                        const int c = min(cnt, kPiece);
+                        int inc = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(kFullMask, inc, o);
+                            if (lane >= o) inc += t;
+                        }
+                        const int tot = __shfl_sync(kFullMask, inc, 31);
+                        int* dst = W.idx + fill + inc - c;
+                        for (int k = 0; k < c; k++) dst[k] = f + k;
+                        fill += tot; cnt -= c; f += c;
+                        pending = __any_sync(kFullMask, cnt > 0);
                     }
+                    __syncwarp();
+                    final = !pending && eb >= ne;
+                    constexpr int kStep = Op::kLanesAreSources ? 64 : 32;   // sources per streaming iteration
+                    nit = final ? ((fill + kStep - 1) / kStep) : (fill / kStep);
+                    upto = final ? fill : (nit * kStep);
+                    carry = final ? 0 : (fill - upto);
                 }
+                if constexpr (Op::kLanesAreSources) {
+                    if (nit > 0) lw_stream(op, A, W, ip, ax, ay, nit, upto, GR, lane);
+                    if (ip == W.idx) {   // the incomplete last iteration goes to the front of the next drain
+                        int v = 0, v2 = 0;
+                        if (lane < carry) v = W.idx[upto + lane];
+                        if (lane + 32 < carry) v2 = W.idx[upto + lane + 32];
+                        __syncwarp();
+                        if (lane < carry) W.idx[lane] = v;
+                        if (lane + 32 < carry) W.idx[lane + 32] = v2;
+                        __syncwarp();
+                        fill = carry;
+                    }
+                } else {
+                    if (active) {
+#pragma unroll 4
+                        for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
+                    }
+                    __syncwarp();
+                    fill = 0;
+                }
+                if (final) break;
             }
             if constexpr (Op::kLanesAreSources) {
-                lw_drain_src(op, A, W, ax, ay, fill, nt, true, lane);
                 // lane sums -> the lane that owns the target
 #pragma unroll
+                const int myt = live ? GR.slot(slot) : -1;
+#pragma unroll
                 for (int t = 0; t < kMaxT; t++) {
-                    if (t < nt) {
+                    if (GR.used(t)) {
                         double vx = ax[t], vy = ay[t];
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
                             vx += __shfl_xor_sync(kFullMask, vx, o);
                             vy += __shfl_xor_sync(kFullMask, vy, o);
                         }
-                        if (live && slot == t) op.take(tg, vx, vy);
+                        if (myt == t) op.take(tg, vx, vy);
                     }
                 }
                 if (live) {
@@ -279,8 +349,6 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
                     else op.finish(tg, A, i, leaf);
                 }
             } else {
-                if (active) for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
-                __syncwarp();
                 // merge the m sub-lane states of every target into its first sub-lane
                 for (int o = 1; o < m; o <<= 1) {
                     const typename Op::Part q = shfl_down_struct(op.part(my), o);
@@ -351,8 +419,8 @@ __global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4
 struct ConvOp {
     static constexpr bool kSegments = false;
     static constexpr bool kFilter = false;
-    static constexpr bool kLanesAreSources = true;
-    static constexpr int kMinBlocks = 3;   // 128 threads x 3: up to 170 registers for the 30 accumulators
+    static constexpr bool kLanesAreSources = VV_CONV_LANES_SRC;
+    static constexpr int kMinBlocks = VV_CONV_LANES_SRC ? VV_CONV_MINB : 10;   // 128 threads x 3: up to 170 registers for the 30 accumulators
     double inf_vx, inf_vy, eps2_div_srcg;
     const double* taylor;  // 4 per leaf
     const double* sinks;   // (x,y,g) triples
@@ -393,6 +461,9 @@ struct ConvOp {
         ay = fma(dx, w, ay);
     }
     __device__ __forceinline__ void take(Tgt& t, double vx, double vy) const { t.rx = vx; t.ry = vy; }
+    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
+        pair(make_double2(t.x, t.y), A.src4[j], t.rx, t.ry);
+    }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
         double vx = inf_vx + t.rx * k1_2Pi, vy = inf_vy + t.ry * k1_2Pi;
@@ -421,7 +492,7 @@ struct DiffOp {
     // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
     static constexpr bool kFilter = true;
     static constexpr bool kLanesAreSources = false;
-    static constexpr int kMinBlocks = 4;
+    static constexpr int kMinBlocks = 5;
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, lim, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };

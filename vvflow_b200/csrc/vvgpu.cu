@@ -3,6 +3,7 @@
 // every entry point either runs the CUDA kernels or returns an error.
 #include "../../include/vvgpu.h"
 #include "vvgpu_move.cuh"
+#include "vvgpu_tree_coop.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -77,11 +78,11 @@ struct vvgpu_ctx {
     int tn = 0, tnseg = 0;  // objects included in the built tree
     int nnodes = 0, nleaves = 0, depth = 0, ngroups = 0;
     double farc = 8;
-    std::vector<int> lvl;
     Buf t_x, t_y, t_h, t_w, t_bb, t_first, t_last, t_sfirst, t_slast, t_ch1, t_parent, t_depth, t_status, t_axis,
         t_nl, t_nn, t_lstart, t_pre, t_cmp, t_cmm, t_leafnode, t_pnode, t_snode[2], t_segperm[2], t_perm, t_tmpR;
     int segcur = 0;
-    Buf scan_part, scan_out, flags;
+    Buf scan_part, scan_out, flags, scan_seg, part_n, part_p, part_s, build_state;
+    int coop_grid = 0;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
     Buf g_ptr, g_leaf, g_mask, g_count, taylor, farcount, d_err;
     Buf u_group, u_first, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list, hv_flag, hv_stack;
@@ -209,81 +210,55 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     const size_t cap = 2 * ((size_t)n + nseg) + 2;
     int rc = alloc_tree(c, cap, n, nseg);
     if (rc) return rc;
+    bool ok = true;
+    c->t_nl.get<int>(cap, &ok); c->t_nn.get<int>(cap, &ok); c->t_lstart.get<int>(cap, &ok); c->t_pre.get<int>(cap, &ok);
+    c->t_cmp.get<double>(3 * cap, &ok); c->t_cmm.get<double>(3 * cap, &ok);
+    c->t_leafnode.get<int>(cap, &ok);
+    u32* Gs = c->scan_seg.get<u32>((size_t)nseg + 2, &ok);
+    u32* partN = c->part_n.get<u32>(cap / kCoopTile + 2, &ok);
+    u32* partP = c->part_p.get<u32>((size_t)n / kCoopTile + 2, &ok);
+    u32* partS = c->part_s.get<u32>((size_t)nseg / kCoopTile + 2, &ok);
+    BuildState* bs = c->build_state.get<BuildState>(1, &ok);
+    NEED(ok);
     c->segcur = 0;
     c->tn = n; c->tnseg = nseg; c->farc = (double)far_criteria;
-    TreeDev T = c->T();
-    BuildParams bp{min_node, max_node};
-    double *px = P.x.as<double>(), *py = P.y.as<double>(), *pg = P.g.as<double>();
-    const double *sx = c->s_rx.as<double>(), *sy = c->s_ry.as<double>();
-    int* perm = c->t_perm.as<int>();
-    u32* G = c->scan_out.as<u32>();
-    u32* splitflag = c->flags.as<u32>();
-
-    k_tree_init_root<<<1, 1, 0, st>>>(T, n, nseg); CKLAUNCH();
-    if (n) { CK(cudaMemsetAsync(T.pnode, 0, sizeof(int) * n, st)); k_iota<<<cdiv(n, 256), 256, 0, st>>>(perm, n); CKLAUNCH(); }
-    if (nseg) { CK(cudaMemsetAsync(T.snode, 0, sizeof(int) * nseg, st)); k_iota<<<cdiv(nseg, 256), 256, 0, st>>>(c->t_segperm[0].as<int>(), nseg); CKLAUNCH(); }
-    if (n + nseg) { k_tree_bbox<<<cdiv(n + nseg, 256), 256, 0, st>>>(T, px, py, n, sx, sy, c->t_segperm[0].as<int>(), nseg); CKLAUNCH(); }
-
-    c->lvl.clear();
-    c->lvl.push_back(0); c->lvl.push_back(1);
-    for (int d = 0;; d++) {
-        if (d > kMaxDepth) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels (degenerate input)");
-        const int a0 = c->lvl[d], a1 = c->lvl[d + 1], na = a1 - a0;
-        k_tree_decide<<<cdiv(na, 128), 128, 0, st>>>(T, a0, a1, bp, splitflag); CKLAUNCH();
-        rc = scan_flags(c, FlagArray{splitflag}, na, G);
-        if (rc) return rc;
-        k_tree_assign<<<cdiv(na, 128), 128, 0, st>>>(T, a0, a1, G); CKLAUNCH();
-        u32 nsplit = 0;
-        rc = read_u32(c, G + na, &nsplit);
-        if (rc) return rc;
-        if (nsplit == 0) break;
-        if ((size_t)a1 + 2 * (size_t)nsplit > cap) return fail(c, VVGPU_ELIMIT, "node capacity exceeded");
-        if (n) {
-            rc = scan_flags(c, PartFlag{T, px, py}, n, G);
-            if (rc) return rc;
-            k_tree_partition<<<cdiv(n, 256), 256, 0, st>>>(T, n, G, c->t_tmpR.as<int>()); CKLAUNCH();
-            k_tree_swap<<<cdiv(n, 256), 256, 0, st>>>(T, n, G, c->t_tmpR.as<int>(), px, py, pg, perm); CKLAUNCH();
-            k_tree_relabel<<<cdiv(n, 256), 256, 0, st>>>(T, n, G); CKLAUNCH();
-        }
-        if (nseg) {
-            const int* pin = c->t_segperm[c->segcur].as<int>();
-            rc = scan_flags(c, SegFlag{T, sx, sy, pin}, nseg, G);
-            if (rc) return rc;
-            k_tree_seg_scatter<<<cdiv(nseg, 256), 256, 0, st>>>(T, nseg, G, pin, c->t_segperm[c->segcur ^ 1].as<int>(),
-                                                               c->t_snode[c->segcur ^ 1].as<int>()); CKLAUNCH();
-            c->segcur ^= 1;
-            T = c->T();
-        }
-        k_tree_bbox<<<cdiv(n + nseg, 256), 256, 0, st>>>(T, px, py, n, sx, sy, c->t_segperm[c->segcur].as<int>(), nseg); CKLAUNCH();
-        c->lvl.push_back(a1 + 2 * (int)nsplit);
+    if (c->coop_grid == 0) {
+        int sms = 0, occ = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tree_build_coop, kCoopThreads, 0));
+        if (occ < 1) return fail(c, VVGPU_ECUDA, "k_tree_build_coop does not fit on an SM");
+        c->coop_grid = sms;
     }
-    c->nnodes = c->lvl.back();
-    c->depth = (int)c->lvl.size() - 2;
-    const int nn = c->nnodes;
-    bool ok = true;
-    c->t_nl.get<int>(nn, &ok); c->t_nn.get<int>(nn, &ok); c->t_lstart.get<int>(nn, &ok); c->t_pre.get<int>(nn, &ok);
-    c->t_cmp.get<double>(3 * (size_t)nn, &ok); c->t_cmm.get<double>(3 * (size_t)nn, &ok);
-    c->t_leafnode.get<int>(nn, &ok);
-    NEED(ok);
-    T = c->T();
-    for (int d = c->depth; d >= 0; d--) {
-        int a0 = c->lvl[d], a1 = c->lvl[d + 1];
-        k_tree_up<<<cdiv(a1 - a0, 128), 128, 0, st>>>(T, a0, a1, px, py, pg); CKLAUNCH();
-    }
-    for (int d = 0; d <= c->depth; d++) {
-        int a0 = c->lvl[d], a1 = c->lvl[d + 1];
-        k_tree_down<<<cdiv(a1 - a0, 128), 128, 0, st>>>(T, a0, a1); CKLAUNCH();
-    }
-    u32 nl = 0;
-    rc = read_u32(c, (const u32*)T.nl, &nl);
-    if (rc) return rc;
+    CoopArgs A;
+    A.T = c->T();
+    A.bp = BuildParams{min_node, max_node};
+    A.px = P.x.as<double>(); A.py = P.y.as<double>(); A.pg = P.g.as<double>();
+    A.sx = c->s_rx.as<double>(); A.sy = c->s_ry.as<double>();
+    A.n = n; A.nseg = nseg;
+    A.perm = c->t_perm.as<int>(); A.tmpR = c->t_tmpR.as<int>();
+    for (int k = 0; k < 2; k++) { A.segperm[k] = c->t_segperm[k].as<int>(); A.snode[k] = c->t_snode[k].as<int>(); }
+    A.G = c->scan_out.as<u32>(); A.Gs = Gs; A.splitflag = c->flags.as<u32>();
+    A.partN = partN; A.partP = partP; A.partS = partS;
+    A.st = bs; A.cap = (long long)cap;
+    void* args[] = {&A};
+    CK(cudaLaunchCooperativeKernel((void*)k_tree_build_coop, dim3(c->coop_grid), dim3(kCoopThreads), args, 0, st));
+    c->launches++;
+    CK(cudaMemcpyAsync(c->h_pinned + 32, bs, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int* hb = c->h_pinned + 32;
+    if (hb[3]) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
+    c->nnodes = hb[0]; c->depth = hb[1];
+    const u32 nl = (u32)hb[2];
+    // the stable segment split ping-pongs between two buffers: one flip per level that split
+    c->segcur = (nseg > 0) ? (c->depth & 1) : 0;
     c->nleaves = (int)nl;
     c->ngroups = cdiv(c->nleaves, kGroupLeaves);
+    TreeDev T = c->T();
     // the rest of each TObj follows the permutation
     if (n) {
         PSet& Q = c->ps[c->cur ^ 1];
         if (!Q.ensure(c->n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
-        k_tree_gather_rest<<<cdiv(n, 256), 256, 0, st>>>(n, perm, P.vx.as<double>(), P.vy.as<double>(), P.ie.as<double>(),
+        k_tree_gather_rest<<<cdiv(n, 256), 256, 0, st>>>(n, c->t_perm.as<int>(), P.vx.as<double>(), P.vy.as<double>(), P.ie.as<double>(),
                                                         P.orig.as<int>(), Q.vx.as<double>(), Q.vy.as<double>(),
                                                         Q.ie.as<double>(), Q.orig.as<int>()); CKLAUNCH();
         std::swap(P.vx, Q.vx); std::swap(P.vy, Q.vy); std::swap(P.ie, Q.ie); std::swap(P.orig, Q.orig);
@@ -481,7 +456,7 @@ int vvgpu_create(int device, vvgpu_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
     for (int k = 0; k < VVGPU_T_COUNT; k++) { cudaEventCreate(&c->ev0[k]); cudaEventCreate(&c->ev1[k]); }
-    if (cudaMallocHost((void**)&c->h_pinned, 256) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
+    if (cudaMallocHost((void**)&c->h_pinned, 1024) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
     *out = c;
     return VVGPU_OK;
 }
@@ -495,7 +470,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_x, &c->t_y, &c->t_h, &c->t_w, &c->t_bb, &c->t_first, &c->t_last, &c->t_sfirst, &c->t_slast,
                   &c->t_ch1, &c->t_parent, &c->t_depth, &c->t_status, &c->t_axis, &c->t_nl, &c->t_nn, &c->t_lstart,
                   &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode, &c->t_pnode, &c->t_snode[0], &c->t_snode[1],
-                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags,
+                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->scan_seg, &c->part_n, &c->part_p, &c->part_s, &c->build_state,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_ptr, &c->g_leaf, &c->g_mask, &c->g_count, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,

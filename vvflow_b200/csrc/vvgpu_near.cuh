@@ -319,9 +319,20 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
                         fill = carry;
                     }
                 } else {
-                    if (active) {
-#pragma unroll 4
-                        for (int k = sub; k < fill; k += m) op.source(my, A, W.idx[k]);
+                    if (active) {   // four loads in flight per lane before the first is used
+                        for (int k = sub; k < fill; k += 4 * m) {
+                            int j[4];
+                            typename Op::Src v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int kk = k + q * m;
+                                j[q] = (kk < fill) ? W.idx[kk] : -1;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) v[q] = (j[q] >= 0) ? Op::fetch(A, j[q]) : Op::none();
+#pragma unroll
+                            for (int q = 0; q < 4; q++) op.use(my, A, v[q], j[q]);
+                        }
                     }
                     __syncwarp();
                     fill = 0;
@@ -461,8 +472,11 @@ struct ConvOp {
         ay = fma(dx, w, ay);
     }
     __device__ __forceinline__ void take(Tgt& t, double vx, double vy) const { t.rx = vx; t.ry = vy; }
-    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
-        pair(make_double2(t.x, t.y), A.src4[j], t.rx, t.ry);
+    typedef double4 Src;
+    static __device__ __forceinline__ Src none() { return dummy(); }
+    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return A.src4[j]; }
+    __device__ __forceinline__ void use(Tgt& t, const NearArgs&, const Src& v, int) const {
+        pair(make_double2(t.x, t.y), v, t.rx, t.ry);
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
@@ -542,8 +556,10 @@ struct DiffOp {
     }
     // squared reach of a target: sources farther than 8 eps never contribute (:101)
     __device__ __forceinline__ double reach2(const Tgt& t) const { double r = 8.000008 / t.ie; return r * r; }
-    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
-        const double4 v = A.src4[j];
+    typedef double4 Src;
+    static __device__ __forceinline__ Src none() { return make_double4(__longlong_as_double(0x7ff0000000000000ll), 0., 0., 0.); }
+    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return A.src4[j]; }
+    __device__ __forceinline__ void use(Tgt& t, const NearArgs&, const Src& v, int) const {
         double dx = VV_SUB(t.x, v.x), dy = VV_SUB(t.y, v.y);
         double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
         if (!(d2 * t.ie2 > t.lim)) hit(t, dx, dy, d2, v.z);
@@ -690,8 +706,10 @@ struct EpsOp {
     }
     // common path: 5 FP64 + one compare; only a source at least as close as the current second
     // neighbour (or a parked NaN) takes the branch
-    __device__ __forceinline__ void source(Tgt& t, const NearArgs& A, int j) const {
-        const double2 p = *reinterpret_cast<const double2*>(A.src4 + j);
+    typedef double2 Src;
+    static __device__ __forceinline__ Src none() { return make_double2(__longlong_as_double(0x7ff0000000000000ll), 0.); }
+    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return *reinterpret_cast<const double2*>(A.src4 + j); }
+    __device__ __forceinline__ void use(Tgt& t, const NearArgs& A, const Src& p, int j) const {
         double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
         double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
         if (!(d > t.r2)) cand(t, A, d, j);

@@ -296,11 +296,13 @@ def ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "k_near<ConvOp> (K4 convective near field)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                         "note": "achieved = 11 flop x near pairs / CUDA-event time of the kernel on the library's "
-                                 "stream; peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no "
-                                 "fp64 entry; HBM there: %s GB/s). HBM traffic of this kernel is ~0.1 GB: compute-bound."
-                                 % peaks.get("hbm_gbs")},
+                         "frac": achieved / fp64_peak if fp64_peak else None,
+                         # ncu dram__bytes_read+write of this kernel at N=1M (profiles/r1_ncu_near_leafwarp.txt)
+                         "traffic": 9.3e7 if n == 1_000_000 and world == 1 else None,
+                         "note": "FP64-pipe bound (no tensor cores: N-body gather). achieved = 11 flop x near pairs / "
+                                 "CUDA-event time of the phase on the library's stream; peak = DFMA micro-benchmark "
+                                 "measured in this run (MEASURED_PEAKS.json holds HBM %s GB/s and bf16 only). "
+                                 "HBM traffic of the kernel is ~0.09 GB vs 39.7 GFLOP: compute-bound." % peaks.get("hbm_gbs")},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "checksum_sum_g": checksum,

@@ -33,6 +33,18 @@ struct Buf {
         }
         return (T*)p;
     }
+    // grow, keeping the current contents (device-to-device copy on the given stream)
+    template <class T>
+    T* get_keep(size_t n, bool* ok, cudaStream_t st) {
+        size_t need = n * sizeof(T);
+        if (need <= bytes) return (T*)p;
+        void* old = p; size_t oldb = bytes;
+        p = nullptr; bytes = 0;
+        T* q = get<T>(n, ok);
+        if (q && old) cudaMemcpyAsync(q, old, oldb, cudaMemcpyDeviceToDevice, st);
+        if (old) { cudaStreamSynchronize(st); cudaFree(old); }
+        return q;
+    }
     template <class T>
     T* as() const { return (T*)p; }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
@@ -84,13 +96,15 @@ struct vvgpu_ctx {
     Buf scan_part, scan_out, flags, scan_seg, part_n, part_p, part_s, build_state;
     int coop_grid = 0;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
-    Buf g_ptr, g_leaf, g_mask, g_count, taylor, farcount, d_err;
-    Buf u_group, u_first, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list, hv_flag, hv_stack;
-    std::vector<int> h_ufirst;
+    Buf g_leaf, g_mask, g_cursor, slot_base, slot_count, taylor, farcount, d_err;
+    long long pool_cap = 0;
+    std::vector<int> h_lvl;
+    int lists_g0 = 0, lists_g1 = 0;
+    Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list,
+        hv_inode, hv_imask, hv_icount, hv_tpart;
     int nunits = 0;
     size_t nslots = 0;
     bool lists_ready = false;
-    long long nentries = 0;
     // epsilon
     Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged;
     Buf mA[6], mB[6];
@@ -117,16 +131,17 @@ struct vvgpu_ctx {
         return LeafDev{l_first.as<int>(), l_last.as<int>(), l_sfirst.as<int>(), l_slast.as<int>(), l_cx.as<double>(),
                        l_cy.as<double>(), l_h.as<double>(), l_w.as<double>(), l_node.as<int>()};
     }
-    GroupLists Gv() { return GroupLists{g_ptr.as<long long>(), g_leaf.as<int>(), g_mask.as<u32>()}; }
+    GroupLists Gv() { return GroupLists{g_leaf.as<int>(), g_mask.as<u32>()}; }
+    Units Uv() { return Units{u_group.as<int>(), u_base.as<long long>(), u_count.as<int>(), u_first.as<int>(), u_num.as<int>(), u_sbase.as<u32>()}; }
     NearArgs near_args() {
         NearArgs a;
         a.P = ps[cur].view(); a.L = Lv(); a.G = Gv(); a.nleaves = nleaves;
-        a.U = Units{u_group.as<int>(), u_first.as<int>(), u_sbase.as<u32>()};
+        a.U = Uv();
         a.scratch = near_scratch.p;
         a.src4 = src4.as<double4>();
         a.lbox = lbox.as<double>();
         a.nseg = tnseg;
-        a.u0 = h_ufirst.empty() ? 0 : h_ufirst[shard_g0];
+        a.u0 = 0;
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
         return a;
@@ -249,6 +264,9 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     if (hb[3]) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
     c->nnodes = hb[0]; c->depth = hb[1];
     const u32 nl = (u32)hb[2];
+    c->h_lvl.resize(c->depth + 2);
+    CK(cudaMemcpyAsync(c->h_lvl.data(), (const int*)bs + 4, sizeof(int) * (c->depth + 2), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     // the stable segment split ping-pongs between two buffers: one flip per level that split
     c->segcur = (nseg > 0) ? (c->depth & 1) : 0;
     c->nleaves = (int)nl;
@@ -274,121 +292,139 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     return 0;
 }
 
-constexpr int kStackCap = 1024;
-size_t trav_smem(int cap) { return (size_t)kTravWarps * ((size_t)cap * sizeof(int2) + (4 * 32 + 32 * 6) * sizeof(double)); }
+size_t trav_smem() { return (size_t)kTravWarps * ((size_t)kTravStack * sizeof(int2) + (4 * 32 + 32 * 6) * sizeof(double)); }
 
-int lists_impl(vvgpu_ctx* c) {
-    if (c->lists_ready) return 0;
+// Interaction lists + Taylor coefficients for the groups [g0, g1) in ONE tree walk per group, then the
+// work-unit table (vvgpu_lists.cuh). `all` = every group (single GPU, or the replicated merge replay);
+// otherwise only this rank's slice.
+int lists_impl(vvgpu_ctx* c, bool all) {
+    const int ng = c->ngroups, nl = c->nleaves;
+    int g0 = 0, g1 = ng;
+    if (!all && c->nranks > 1) {   // contiguous slices of groups: uniform clouds balance by themselves
+        g0 = (int)((long long)ng * c->rank / c->nranks);
+        g1 = (int)((long long)ng * (c->rank + 1) / c->nranks);
+    }
+    if (c->lists_ready && c->lists_g0 == g0 && c->lists_g1 == g1) return 0;
     cudaStream_t st = c->stream;
     bool ok = true;
-    const int ng = c->ngroups, nl = c->nleaves;
-    u32* gcount = c->g_count.get<u32>(ng + 1, &ok);
-    c->g_ptr.get<long long>(ng + 1, &ok);
     double* taylor = c->taylor.get<double>(4 * (size_t)nl, &ok);
     double* farcount = c->farcount.get<double>(nl, &ok);
-    int* derr = c->d_err.get<int>(2, &ok);
-    c->scan_out.get<u32>(ng + 2, &ok);
+    int* derr = c->d_err.get<int>(4, &ok);   // [0] error bits, [1] heavy groups
+    int* hvlist = c->hv_list.get<int>(ng + 1, &ok);
     NEED(ok);
     TreeDev T = c->T();
     LeafDev L = c->Lv();
-    int cap = kStackCap;
-    size_t smem = trav_smem(cap);
-    CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
-    CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem(kStackCap)));
-    int* hvlist = c->hv_list.get<int>(ng + 1, &ok);
-    unsigned char* hvflag = c->hv_flag.get<unsigned char>(ng + 1, &ok);
-    NEED(ok);
-    int* nheavy_d = derr + 1;
-    CK(cudaMemsetAsync(derr, 0, 2 * sizeof(int), st));
-    CK(cudaMemsetAsync(hvflag, 0, ng + 1, st));
-    const int grid = cdiv(ng, kTravWarps);
-    k_traverse<false><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr, hvlist, nheavy_d, hvflag); CKLAUNCH();
-    u32 nheavy = 0;
-    int rc = read_u32(c, (u32*)nheavy_d, &nheavy);
-    if (rc) return rc;
-    int2* stacks = nullptr;
-    const long long stride = (long long)c->nnodes + 2;
-    // heavy groups run in batches so that their stacks (one slot per tree node each) stay within 512 MB
-    const int hbatch = (int)std::max<long long>(1, std::min<long long>(nheavy, (512ll << 20) / (stride * (long long)sizeof(int2))));
-    if (nheavy) {
-        stacks = c->hv_stack.get<int2>((size_t)stride * hbatch, &ok);
+    CK(cudaFuncSetAttribute(k_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
+    CK(cudaFuncSetAttribute(k_traverse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
+    CK(cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
+    // heavy groups are cut at the first tree level that is at least 256 nodes wide
+    int cut = c->depth;
+    for (int d = 0; d <= c->depth; d++)
+        if (c->h_lvl[d + 1] - c->h_lvl[d] >= 256) { cut = d; break; }
+    const int item_cap = std::max(2, c->h_lvl[cut + 1] - c->h_lvl[cut]);
+    const long long nreg_slots = (long long)ng * kGroupSlots;
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 6) return fail(c, VVGPU_ELIMIT, "interaction lists do not fit the entry pool");
+        if (c->pool_cap == 0) c->pool_cap = 48ll * nl + (4ll << 20);
+        int* pleaf = c->g_leaf.get<int>((size_t)c->pool_cap, &ok);
+        u32* pmask = c->g_mask.get<u32>((size_t)c->pool_cap, &ok);
+        unsigned long long* cursor = c->g_cursor.get<unsigned long long>(1, &ok);
+        long long* sbase = c->slot_base.get<long long>((size_t)nreg_slots + 1, &ok);
+        int* scount = c->slot_count.get<int>((size_t)nreg_slots + 1, &ok);
         NEED(ok);
-        k_mark_heavy<<<cdiv(nheavy, 256), 256, 0, st>>>(hvlist, (int)nheavy, hvflag); CKLAUNCH();
-        for (int b = 0; b < (int)nheavy; b += hbatch) {
-            int nb = std::min(hbatch, (int)nheavy - b);
-            k_traverse_heavy<false><<<nb, kHeavyThreads, 0, st>>>(T, L, nl, hvlist + b, c->farc, c->Gv(), gcount, taylor, farcount, stacks, stride, derr); CKLAUNCH();
+        CK(cudaMemsetAsync(derr, 0, 4 * sizeof(int), st));
+        CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(scount, 0, sizeof(int) * (nreg_slots + 1), st));
+        TravOut O{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase, scount, derr};
+        TravItems I0{nullptr, nullptr, nullptr, item_cap, cut};
+        if (g1 > g0) {
+            k_traverse<0><<<cdiv(g1 - g0, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
+                T, L, nl, g0, g1, c->farc, O, taylor, farcount, nullptr, nullptr, 0, hvlist, derr + 1, I0); CKLAUNCH();
         }
-    }
-    u32* gs = c->scan_out.as<u32>();
-    rc = scan_flags(c, FlagArray{gcount}, ng, gs);
-    if (rc) return rc;
-    u32 total = 0;
-    rc = read_u32(c, gs + ng, &total);
-    if (rc) return rc;
-    u32 e = 0;
-    rc = read_u32(c, (u32*)derr, &e);
-    if (rc) return rc;
-    if (e) return fail(c, VVGPU_ELIMIT, "near/far traversal stack overflow");
-    c->nentries = total;
-    c->g_leaf.get<int>(total, &ok); c->g_mask.get<u32>(total, &ok);
-    NEED(ok);
-    k_group_ptr<<<cdiv(ng + 1, 256), 256, 0, st>>>(gs, c->g_ptr.as<long long>(), ng); CKLAUNCH();
-    k_traverse<true><<<grid, kTravWarps * 32, smem, st>>>(T, L, nl, ng, c->farc, c->Gv(), gcount, taylor, farcount, cap, derr, hvlist, nheavy_d, hvflag); CKLAUNCH();
-    for (int b = 0; b < (int)nheavy; b += hbatch) {
-        int nb = std::min(hbatch, (int)nheavy - b);
-        k_traverse_heavy<true><<<nb, kHeavyThreads, 0, st>>>(T, L, nl, hvlist + b, c->farc, c->Gv(), gcount, taylor, farcount, stacks, stride, derr); CKLAUNCH();
+        CK(cudaMemcpyAsync(c->h_pinned + 64, derr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int errbits = c->h_pinned[64];
+        const int nheavy = c->h_pinned[65];
+        long long nheavy_slots = 0;
+        if (!errbits && nheavy) {
+            // ---- fringe groups: top walk -> items -> one walk per item
+            nheavy_slots = (long long)nheavy * (item_cap + 1) * kItemSlots;
+            sbase = c->slot_base.get_keep<long long>((size_t)(nreg_slots + nheavy_slots) + 1, &ok, st);
+            scount = c->slot_count.get_keep<int>((size_t)(nreg_slots + nheavy_slots) + 1, &ok, st);
+            int* inode = c->hv_inode.get<int>((size_t)nheavy * item_cap, &ok);
+            u32* imask = c->hv_imask.get<u32>((size_t)nheavy * item_cap, &ok);
+            int* icount = c->hv_icount.get<int>(nheavy, &ok);
+            double* tpart = c->hv_tpart.get<double>((size_t)nheavy * (item_cap + 1) * 32 * 5, &ok);
+            NEED(ok);
+            CK(cudaMemsetAsync(scount + nreg_slots, 0, sizeof(int) * (nheavy_slots + 1), st));
+            CK(cudaMemsetAsync(icount, 0, sizeof(int) * nheavy, st));
+            TravOut OH{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase + nreg_slots, scount + nreg_slots, derr};
+            TravItems I{inode, imask, icount, item_cap, cut};
+            k_traverse<1><<<cdiv(nheavy, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
+                T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
+            k_traverse<2><<<cdiv((long long)nheavy * item_cap, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
+                T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
+            k_heavy_taylor<<<nheavy, 32, 0, st>>>(hvlist, nheavy, nl, tpart, icount, item_cap, taylor, farcount); CKLAUNCH();
+            CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            errbits = c->h_pinned[64];
+        }
+        if (errbits & 1) { c->pool_cap *= 2; continue; }   // pool too small: grow and walk again
+        if (errbits & 2) return fail(c, VVGPU_ELIMIT, "near/far traversal stack overflow");
+        if (errbits & 4) return fail(c, VVGPU_ELIMIT, "a heavy-group item overflowed its chunk slots");
+        // ---- unit table: the non-empty slots in slot order
+        const long long nslots_total = nreg_slots + nheavy_slots;
+        u32* rank = c->scan_out.get<u32>((size_t)nslots_total + 2, &ok);
+        int* ufirst = c->u_first.get<int>(ng + 1, &ok);
+        int* unum = c->u_num.get<int>(ng + 1, &ok);
+        u32* nsl = c->u_tmp.get<u32>((size_t)ng + 2, &ok);
+        u32* usb = c->u_sbase.get<u32>(ng + 1, &ok);
+        NEED(ok);
+        int rc = scan_flags(c, SlotFlag{scount}, nslots_total, rank);
+        if (rc) return rc;
+        u32 nunits = 0;
+        rc = read_u32(c, rank + nslots_total, &nunits);
+        if (rc) return rc;
+        c->nunits = (int)nunits;
+        int* ugroup = c->u_group.get<int>(std::max<u32>(nunits, 1), &ok);
+        long long* ubase = c->u_base.get<long long>(std::max<u32>(nunits, 1), &ok);
+        int* ucount = c->u_count.get<int>(std::max<u32>(nunits, 1), &ok);
+        NEED(ok);
+        k_units_fill<<<cdiv(nslots_total, 256), 256, 0, st>>>(nslots_total, nreg_slots, rank, sbase, scount, hvlist, item_cap,
+                                                             ugroup, ubase, ucount); CKLAUNCH();
+        k_units_groups<<<cdiv(ng, 128), 128, 0, st>>>(ng, rank, ufirst, unum); CKLAUNCH();
+        if (nheavy) { k_units_heavy<<<cdiv(nheavy, 128), 128, 0, st>>>(nheavy, nreg_slots, item_cap, hvlist, rank, ufirst, unum); CKLAUNCH(); }
+        k_unit_slots<<<cdiv(ng, 128), 128, 0, st>>>(L, nl, ng, unum, nsl); CKLAUNCH();
+        rc = scan_flags(c, FlagArray{nsl}, ng, usb);
+        if (rc) return rc;
+        u32 nslots = 0;
+        rc = read_u32(c, usb + ng, &nslots);
+        if (rc) return rc;
+        c->nslots = nslots;
+        c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
+        NEED(ok);
+        break;
     }
     c->lists_ready = true;
-    // work units (<= kUnitEntries list entries each) and the scratch slots of multi-unit groups
-    u32* nun = c->u_tmp.get<u32>(2 * (size_t)ng + 2, &ok);
-    u32* nsl = nun + ng + 1;
-    int* ufirst = c->u_first.get<int>(ng + 1, &ok);
-    u32* sbase = c->u_sbase.get<u32>(ng + 1, &ok);
-    NEED(ok);
-    k_unit_count<<<cdiv(ng, 128), 128, 0, st>>>(L, c->Gv(), nl, ng, nun, nsl); CKLAUNCH();
-    rc = scan_flags(c, FlagArray{nun}, ng, (u32*)ufirst);
-    if (!rc) rc = scan_flags(c, FlagArray{nsl}, ng, sbase);
-    if (rc) return rc;
-    c->h_ufirst.resize(ng + 1);
-    CK(cudaMemcpyAsync(c->h_ufirst.data(), ufirst, sizeof(int) * (ng + 1), cudaMemcpyDeviceToHost, st));
-    u32 nslots = 0;
-    rc = read_u32(c, sbase + ng, &nslots);
-    if (rc) return rc;
-    c->nunits = c->h_ufirst[ng];
-    c->nslots = nslots;
-    int* ugroup = c->u_group.get<int>(c->nunits, &ok);
-    c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
-    NEED(ok);
-    k_unit_fill<<<cdiv(ng, 128), 128, 0, st>>>(ng, ufirst, ugroup); CKLAUNCH();
-    // shard: contiguous slices of groups balanced by unit count (units bound the work per CTA)
-    c->shard_g0 = 0; c->shard_g1 = ng;
-    if (c->nranks > 1) {
-        auto cut = [&](int r) {
-            int want = (int)((double)c->nunits * r / c->nranks);
-            return (int)(std::lower_bound(c->h_ufirst.begin(), c->h_ufirst.end(), want) - c->h_ufirst.begin());
-        };
-        c->shard_g0 = (c->rank == 0) ? 0 : std::min(cut(c->rank), ng);
-        c->shard_g1 = (c->rank == c->nranks - 1) ? ng : std::min(std::max(cut(c->rank + 1), c->shard_g0), ng);
-    }
+    c->lists_g0 = g0; c->lists_g1 = g1;
+    c->shard_g0 = g0; c->shard_g1 = g1;
     return 0;
 }
 
 template <class Op>
 int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
     static_assert(sizeof(typename Op::Part) <= sizeof(DiffOp::Part), "scratch is sized for the largest Part");
-    const int g0 = c->shard_g0, g1 = c->shard_g1;
-    if (g1 <= g0) return 0;
+    if (c->nunits <= 0) return 0;
     {
         bool ok = true;
         double4* s4 = c->src4.get<double4>(c->tn, &ok);
         NEED(ok);
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
-    const int nu = c->h_ufirst[g1] - c->h_ufirst[g0];
     CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
-    k_near<Op><<<nu, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
-    if (nu > g1 - g0) {  // some group has more than one unit
-        k_near_finalize<Op><<<g1 - g0, 256, 0, c->stream>>>(c->near_args(), op, g0, g1); CKLAUNCH();
+    k_near<Op><<<c->nunits, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
+    if (c->nslots > 0) {  // some group has more than one unit
+        k_near_finalize<Op><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
     }
     return 0;
 }
@@ -405,7 +441,7 @@ int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* lat
         bd = c->wall_d.get<u64>(nl, &ok); bk = c->wall_key.get<u64>(nl, &ok);
         NEED(ok);
         const int* sp = c->t_segperm[c->segcur].as<int>();
-        Units U{c->u_group.as<int>(), c->u_first.as<int>(), c->u_sbase.as<u32>()};
+        Units U = c->Uv();
         k_wall_init<<<cdiv(nl, 256), 256, 0, st>>>(nl, bd, bk); CKLAUNCH();
         k_wall_pass<1><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
         k_wall_pass<2><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
@@ -472,9 +508,9 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode, &c->t_pnode, &c->t_snode[0], &c->t_snode[1],
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->scan_seg, &c->part_n, &c->part_p, &c->part_s, &c->build_state,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
-                  &c->g_ptr, &c->g_leaf, &c->g_mask, &c->g_count, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
+                  &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
-                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list, &c->hv_flag, &c->hv_stack};
+                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
     c->ps[0].release(); c->ps[1].release();
@@ -602,7 +638,7 @@ int vvgpu_tree_build(vvgpu_ctx* c, int far_criteria, double min_node, double max
     if (rc) return rc;
     {
         PhaseTimer t(c, VVGPU_T_LISTS);
-        rc = lists_impl(c);
+        rc = lists_impl(c, c->nranks == 1);
     }
     if (rc) { c->built = false; return rc; }
     return 0;
@@ -711,12 +747,13 @@ int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes
     if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
     CK(cudaSetDevice(c->device));
     bool ok = true;
-    const int ng = c->ngroups, nl = c->nleaves;
-    double* d = c->d_pairs.get<double>(ng + 1, &ok);
+    const int nl = c->nleaves, nu = c->nunits;
+    double* d = c->d_pairs.get<double>(nu + 1, &ok);
     NEED(ok);
-    k_count_pairs<<<std::max(ng, 1), 128, 0, c->stream>>>(c->Lv(), nl, ng, c->Gv(), c->ps[c->cur].g.as<double>(), d); CKLAUNCH();
-    std::vector<double> h(ng), f(nl);
-    CK(cudaMemcpyAsync(h.data(), d, sizeof(double) * ng, cudaMemcpyDeviceToHost, c->stream));
+    k_count_pairs<<<std::max(nu, 1), 128, 0, c->stream>>>(c->Lv(), nl, nu, c->u_group.as<int>(), c->u_base.as<long long>(),
+                                                         c->u_count.as<int>(), c->Gv(), c->ps[c->cur].g.as<double>(), d); CKLAUNCH();
+    std::vector<double> h(nu), f(nl);
+    if (nu) CK(cudaMemcpyAsync(h.data(), d, sizeof(double) * nu, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(f.data(), c->farcount.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     double s = 0, t = 0;
@@ -756,11 +793,14 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         return launch_near(c, op);
     }
     // merge replay is order-dependent: every rank replays it over ALL groups (it is replicated, not sharded)
-    struct ShardGuard {
-        vvgpu_ctx* c; int g0, g1;
-        ShardGuard(vvgpu_ctx* c): c(c), g0(c->shard_g0), g1(c->shard_g1) { c->shard_g0 = 0; c->shard_g1 = c->ngroups; }
-        ~ShardGuard() { c->shard_g0 = g0; c->shard_g1 = g1; }
-    } guard(c);
+    struct Reshard {
+        vvgpu_ctx* c;
+        ~Reshard() { if (c->nranks > 1 && c->built) lists_impl(c, false); }   // back to this rank's slice
+    } reshard{c};
+    {
+        int rcl = lists_impl(c, true);
+        if (rcl) return rcl;
+    }
     // merging: iterate the tentative solution to its fixed point (see MergeState in vvgpu_near.cuh)
     double* ietmp = c->ie_tmp.get<double>(n, &ok);
     unsigned char* dyn = c->dyn.get<unsigned char>(n, &ok);

@@ -1,14 +1,20 @@
 // K2 — near/far classification (snode::FindNearNodes, libvvhd/src/TSortedTree.cpp:199-217).
 //
 // The reference walks the tree once per leaf and stores two pointer vectors per leaf. Here one
-// warp walks the tree once for a GROUP of 32 consecutive leaves (consecutive in DFS order =
+// warp walks the tree ONCE for a GROUP of 32 consecutive leaves (consecutive in DFS order =
 // contiguous in the permuted particle array): lanes hold up to 32 frontier nodes, each lane
-// tests its node against all 32 leaves with the reference's exact criterion and produces a
-// 32-bit mask of leaves for which the node is far / still near. Outputs:
-//   * per group, the list of near source leaves with the mask of target leaves that see them
-//     (two passes: count, then fill) — the only interaction list that is materialised;
-//   * per leaf, the four far-field Taylor coefficients of MConvectiveFast.cpp:48-69, accumulated
-//     on the fly, so far lists are never stored.
+// tests its node against the group's leaves with the reference's exact criterion and produces a
+// 32-bit mask of leaves for which the node is far / still near. Outputs of the single walk:
+//   * the near list of the group: (source leaf, mask of target leaves that see it) entries, appended
+//     to an entry pool in chunks of kUnitEntries. A chunk IS a work unit of the near-field kernels,
+//     so no counting pass is needed; chunks are claimed with one atomic add each (their placement in
+//     the pool is arbitrary, their content and their order within the group are deterministic);
+//   * per leaf, the four far-field Taylor coefficients of MConvectiveFast.cpp:48-69, accumulated on
+//     the fly, so far lists are never stored.
+// A few fringe groups see (almost) the whole tree. A warp that exceeds its iteration budget gives
+// up and the group is redone in two steps: one warp walks the top kTopDepth.. levels and turns every
+// still-near node of the cut level into an ITEM (node, mask); then one warp per item walks that
+// subtree. Items own their chunks and Taylor partials, which are combined in item order.
 // k_lists_dfs is the literal per-leaf walk, used only to export the reference's own lists
 // (vvgpu_tree_lists) to host code and tests.
 #pragma once
@@ -17,14 +23,26 @@
 namespace vv {
 
 constexpr int kGroupLeaves = 32;
-constexpr int kTravWarps = 4;  // warps per CTA in k_traverse
-constexpr int kTravBudget = 512;  // warp iterations before a group is declared heavy
-constexpr int kHeavyThreads = 1024;
+constexpr int kUnitEntries = 512;   // list entries per chunk = per work unit of the near-field kernels
+constexpr int kTravWarps = 4;       // warps per CTA in k_traverse
+constexpr int kTravBudget = 512;    // warp iterations before a group is declared heavy
+constexpr int kTravStack = 1024;    // stack entries per warp (shared memory)
+constexpr int kGroupSlots = 16;     // chunks a regular group may fill before it is declared heavy
+constexpr int kItemSlots = 64;      // chunks one item of a heavy group may fill
 
-struct GroupLists {
-    long long* ptr;  // ngroups + 1
-    int* leaf;       // source leaf index
-    u32* mask;       // target leaves (bit k = leaf group*32 + k) that have `leaf` in NearNodes
+struct GroupLists {   // the entry pool
+    int* leaf;        // source leaf index
+    u32* mask;        // target leaves (bit k = leaf group*32 + k) that have `leaf` in NearNodes
+};
+
+// where a walk puts its chunks: slot s of the walk -> (base, count) of its s-th chunk
+struct TravOut {
+    GroupLists G;
+    unsigned long long* cursor;   // next free pool entry
+    long long pool_cap;
+    long long* slot_base;
+    int* slot_count;
+    int* err;                     // bit 0: pool full, bit 1: stack overflow, bit 2: slot overflow in an item
 };
 
 // far iff dr.abs2() > farCriteria*HalfPerim*HalfPerim, HalfPerim = top.h + top.w + h + w
@@ -52,24 +70,60 @@ __device__ __forceinline__ void taylor_add(double cx, double cy, double mx, doub
     T4 += f2 * (dy * dy - dx * dx);
 }
 
-template <bool FILL>
+// MODE 0: a group from the root (budgeted; gives up -> heavy). MODE 1: top of a heavy group (nodes
+// shallower than cut_depth; still-near nodes AT cut_depth become items). MODE 2: one item of a heavy group.
+struct TravItems {
+    int* node;        // [nheavy * item_cap]
+    u32* mask;
+    int* count;       // [nheavy]
+    int item_cap;
+    int cut_depth;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(kTravWarps * 32)
-k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLists G, u32* gcount, double* taylor,
-           double* farcount, int stack_cap, int* err, int* heavy, int* nheavy, const unsigned char* is_heavy) {
+k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravOut O, double* taylor, double* farcount,
+           double* tpart /* MODE 1,2: per walk 32 x 5 partials */, const int* heavy_list, int nheavy, int* heavy_out,
+           int* nheavy_out, TravItems I) {
     extern __shared__ unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x * kTravWarps + warp;
-    // per-warp shared layout: int2 stack[stack_cap]; double lc[4][32]; double cm[32][6]
-    size_t per_warp = (size_t)stack_cap * sizeof(int2) + 4 * 32 * sizeof(double) + 32 * 6 * sizeof(double);
+    const int w = blockIdx.x * kTravWarps + warp;   // walk index
+    constexpr size_t per_warp = (size_t)kTravStack * sizeof(int2) + 4 * 32 * sizeof(double) + 32 * 6 * sizeof(double);
     unsigned char* base = smem_raw + per_warp * warp;
     int2* stack = (int2*)base;
-    double* lcx = (double*)(base + (size_t)stack_cap * sizeof(int2));
+    double* lcx = (double*)(base + (size_t)kTravStack * sizeof(int2));
     double* lcy = lcx + 32;
     double* lh = lcy + 32;
     double* lw = lh + 32;
     double* cm = lw + 32;
-    if (g >= ngroups) return;  // warps are independent: no block-level barrier below
-    if (FILL && is_heavy[g]) return;  // handled by k_traverse_heavy
+    // ---- which walk is this
+    int g, slot0, nslots, hidx = 0, seq = 0;
+    int start_node = 0;
+    u32 start_mask = 0;
+    if (MODE == 0) {
+        g = g0 + w;
+        if (g >= g1) return;   // warps are independent: no block-level barrier below
+        slot0 = g * kGroupSlots; nslots = kGroupSlots;
+    } else if (MODE == 1) {
+        hidx = w;
+        if (hidx >= nheavy) return;
+        g = heavy_list[hidx];
+        seq = 0;
+    } else {
+        hidx = w / I.item_cap;
+        if (hidx >= nheavy) return;
+        const int it = w - hidx * I.item_cap;
+        if (it >= I.count[hidx]) return;
+        g = heavy_list[hidx];
+        seq = it + 1;
+        start_node = I.node[(long long)hidx * I.item_cap + it];
+        start_mask = I.mask[(long long)hidx * I.item_cap + it];
+    }
+    long long walk = 0;   // index of this walk among the heavy walks (MODE 1, 2)
+    if (MODE != 0) {
+        walk = (long long)hidx * (I.item_cap + 1) + seq;
+        slot0 = (int)(walk * kItemSlots); nslots = kItemSlots;   // (offset by the regular slots, added by the caller in O)
+    }
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, nleaves - l0);
     double mycx = 0, mycy = 0;
@@ -78,23 +132,21 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
         lcx[lane] = mycx; lcy[lane] = mycy; lh[lane] = L.h[l0 + lane]; lw[lane] = L.w[l0 + lane];
     } else { lcx[lane] = 0; lcy[lane] = 0; lh[lane] = 0; lw[lane] = 0; }
     const u32 full = (nl == 32) ? 0xffffffffu : ((1u << nl) - 1u);
-    if (lane == 0) stack[0] = make_int2(0, (int)full);
+    if (lane == 0) stack[0] = (MODE == 2) ? make_int2(start_node, (int)start_mask) : make_int2(0, (int)full);
     int size = 1;
     __syncwarp();
     double T1 = 0, T2 = 0, T3 = 0, T4 = 0;
-    u32 cnt = 0;
     double nfar = 0;
-    const long long gbase = FILL ? G.ptr[g] : 0;
     int iters = 0;
+    // chunk bookkeeping (uniform across the warp)
+    int nchunk = 0, fill = kUnitEntries;   // "full": the first emission claims a chunk
+    long long cbase = 0;
+    int nitems = 0;
+    bool bail = false;
     while (size > 0) {
-        if (!FILL && ++iters > kTravBudget) {
-            // a fringe group that sees most of the tree: a single warp would serialise the whole
-            // step behind it, so it is handed to k_traverse_heavy (one 1024-thread CTA per group)
-            if (lane == 0) { heavy[atomicAdd(nheavy, 1)] = g; gcount[g] = 0; }
-            return;
-        }
+        if (MODE == 0 && ++iters > kTravBudget) { bail = true; break; }
         // near the capacity fall back to plain depth-first order (growth <= 1 per pop)
-        int take = (size > stack_cap - 80) ? 1 : min(size, 32);
+        int take = (size > kTravStack - 80) ? 1 : min(size, 32);
         int n = -1;
         u32 em = 0;
         if (lane < take) { int2 e = stack[size - 1 - lane]; n = e.x; em = (u32)e.y; }
@@ -111,37 +163,75 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
                 if (is_far(nx, ny, nhw, lcx[l], lcy[l], lh[l], lw[l], farc)) farm |= (1u << l);
             }
             nearm = em & ~farm;
-            if (FILL && farm) {
+            if (farm) {
                 cm[lane * 6 + 0] = T.cmp[3ll * n + 0]; cm[lane * 6 + 1] = T.cmp[3ll * n + 1];
                 cm[lane * 6 + 2] = T.cmp[3ll * n + 2]; cm[lane * 6 + 3] = T.cmm[3ll * n + 0];
                 cm[lane * 6 + 4] = T.cmm[3ll * n + 1]; cm[lane * 6 + 5] = T.cmm[3ll * n + 2];
             }
         }
-        // descend: both children inherit the still-near leaves (child 1 ends up on top)
+        // descend: both children inherit the still-near leaves (child 1 ends up on top). In the top
+        // walk of a heavy group the children at the cut depth become items instead.
         bool push = (n >= 0) && nearm && (c1 >= 0);
-        u32 pb = __ballot_sync(0xffffffffu, push);
-        int npush = 2 * __popc(pb);
-        if (size + npush > stack_cap) {
-            if (lane == 0) atomicExch(err, 1);
+        bool cut = false;
+        if (MODE == 1) cut = push && (T.depth[n] + 1 >= I.cut_depth);
+        const u32 pb = __ballot_sync(0xffffffffu, push && !cut);
+        const int npush = 2 * __popc(pb);
+        if (size + npush > kTravStack) {
+            if (lane == 0) atomicOr(O.err, 2);
             return;
         }
-        if (push) {
+        if (push && !cut) {
             int off = size + 2 * __popc(pb & lanemask_lt());
             stack[off] = make_int2(c1 + 1, (int)nearm);
             stack[off + 1] = make_int2(c1, (int)nearm);
         }
         size += npush;
-        // a near leaf: one list entry for the group
-        bool emit = (n >= 0) && nearm && (c1 < 0);
-        u32 eb = __ballot_sync(0xffffffffu, emit);
-        if (FILL && emit) {
-            long long k = gbase + cnt + __popc(eb & lanemask_lt());
-            G.leaf[k] = T.lstart[n];
-            G.mask[k] = nearm;
+        if (MODE == 1) {
+            const u32 cb = __ballot_sync(0xffffffffu, cut);
+            if (cut) {
+                const long long at = (long long)hidx * I.item_cap + nitems + 2 * __popc(cb & lanemask_lt());
+                I.node[at] = c1; I.mask[at] = nearm;
+                I.node[at + 1] = c1 + 1; I.mask[at + 1] = nearm;
+            }
+            nitems += 2 * __popc(cb);
         }
-        cnt += __popc(eb);
+        // a near leaf: one list entry for the group
+        const bool emit = (n >= 0) && nearm && (c1 < 0);
+        const u32 eb = __ballot_sync(0xffffffffu, emit);
+        if (eb) {
+            const int k = __popc(eb);
+            int pos = fill + __popc(eb & lanemask_lt());
+            long long nbase = cbase;
+            if (fill + k > kUnitEntries) {   // (part of) this batch goes to a fresh chunk
+                if (nchunk >= nslots) {
+                    if (MODE == 0) { bail = true; break; }
+                    if (lane == 0) atomicOr(O.err, 4);
+                    return;
+                }
+                unsigned long long nb = 0;
+                if (lane == 0) {
+                    nb = atomicAdd(O.cursor, (unsigned long long)kUnitEntries);
+                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = kUnitEntries;
+                    O.slot_base[slot0 + nchunk] = (long long)nb;
+                }
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if ((long long)nb + kUnitEntries > O.pool_cap) {
+                    if (lane == 0) atomicOr(O.err, 1);
+                    return;
+                }
+                nbase = (long long)nb;
+                nchunk++;
+            }
+            if (emit) {
+                const long long at = (pos < kUnitEntries) ? (cbase + pos) : (nbase + (pos - kUnitEntries));
+                O.G.leaf[at] = T.lstart[n];
+                O.G.mask[at] = nearm;
+            }
+            if (fill + k > kUnitEntries) { fill = fill + k - kUnitEntries; cbase = nbase; }
+            else fill += k;
+        }
         // far nodes: transpose (node lane x leaf bit) -> (leaf lane x node bit) and accumulate
-        u32 anyfar = __ballot_sync(0xffffffffu, farm != 0);
+        const u32 anyfar = __ballot_sync(0xffffffffu, farm != 0);
         if (anyfar) {
             __syncwarp();
             u32 mine = 0;
@@ -151,150 +241,88 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int ngroups, double farc, GroupLis
                 if (lane == l) mine = tm;
             }
             nfar += (double)__popc(mine);
-            if (FILL) {
-                while (mine) {
-                    int j = __ffs(mine) - 1;
-                    mine &= mine - 1;
-                    const double* c = cm + j * 6;
-                    taylor_add(mycx, mycy, c[0], c[1], c[2], T1, T2, T3, T4);
-                    taylor_add(mycx, mycy, c[3], c[4], c[5], T1, T2, T3, T4);
-                }
+            while (mine) {
+                int j = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const double* c = cm + j * 6;
+                taylor_add(mycx, mycy, c[0], c[1], c[2], T1, T2, T3, T4);
+                taylor_add(mycx, mycy, c[3], c[4], c[5], T1, T2, T3, T4);
             }
         }
         __syncwarp();
     }
-    if (!FILL) {
-        if (lane == 0) gcount[g] = cnt;
-        if (lane < nl && farcount) farcount[l0 + lane] = nfar;
-    } else if (lane < nl) {
-        double* t = taylor + 4ll * (l0 + lane);
-        t[0] = T1 * k1_2Pi; t[1] = T2 * k1_2Pi; t[2] = T3 * k1_Pi; t[3] = T4 * k1_2Pi;  // :66-69
+    if (MODE == 0 && bail) {
+        // a fringe group that sees most of the tree: a single warp would serialise the whole step behind
+        // it. Its chunks are dropped (count 0) and the group is redone as a heavy one.
+        if (lane == 0) {
+            heavy_out[atomicAdd(nheavy_out, 1)] = g;
+            for (int k = 0; k < min(nchunk, nslots); k++) O.slot_count[slot0 + k] = 0;
+        }
+        return;
+    }
+    if (lane == 0 && nchunk > 0) O.slot_count[slot0 + nchunk - 1] = fill;
+    if (MODE == 0) {
+        if (lane < nl) {
+            double* t = taylor + 4ll * (l0 + lane);
+            t[0] = T1 * k1_2Pi; t[1] = T2 * k1_2Pi; t[2] = T3 * k1_Pi; t[3] = T4 * k1_2Pi;  // :66-69
+            if (farcount) farcount[l0 + lane] = nfar;
+        }
+    } else {
+        double* t = tpart + (walk * 32 + lane) * 5;
+        t[0] = T1; t[1] = T2; t[2] = T3; t[3] = T4; t[4] = nfar;
+        if (MODE == 1 && lane == 0) I.count[hidx] = nitems;
     }
 }
 
-// Cooperative traversal of one HEAVY group by a 1024-thread CTA: the same walk as k_traverse with a
-// 1024-wide frontier and the stack in global memory (at most one entry per tree node). Entry order
-// and the Taylor sums are deterministic (block-wide prefix sums, warp partials combined in order).
-template <bool FILL>
-__global__ void __launch_bounds__(kHeavyThreads)
-k_traverse_heavy(TreeDev T, LeafDev L, int nleaves, const int* heavy, double farc, GroupLists G, u32* gcount,
-                 double* taylor, double* farcount, int2* stacks, long long stack_stride, int* err) {
-    __shared__ double lcx[32], lcy[32], lh[32], lw[32];
-    __shared__ int wn[32][32];
-    __shared__ int wpush[33], wemit[33];
-    __shared__ double acc[4][32];
-    __shared__ double accn[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = heavy[blockIdx.x];
-    int2* stack = stacks + stack_stride * blockIdx.x;
-    const int l0 = g * kGroupLeaves;
-    const int nl = min(kGroupLeaves, nleaves - l0);
-    if (tid < 32) {
-        bool in = tid < nl;
-        lcx[tid] = in ? L.cx[l0 + tid] : 0; lcy[tid] = in ? L.cy[l0 + tid] : 0;
-        lh[tid] = in ? L.h[l0 + tid] : 0; lw[tid] = in ? L.w[l0 + tid] : 0;
-        acc[0][tid] = acc[1][tid] = acc[2][tid] = acc[3][tid] = 0; accn[tid] = 0;
+// Taylor coefficients of the leaves of heavy groups: partials of the top walk and of the items, in order
+__global__ void k_heavy_taylor(const int* heavy_list, int nheavy, int nleaves, const double* tpart, const int* item_count,
+                               int item_cap, double* taylor, double* farcount) {
+    const int hidx = blockIdx.x, lane = threadIdx.x;
+    if (hidx >= nheavy || lane >= 32) return;
+    const int l = heavy_list[hidx] * kGroupLeaves + lane;
+    if (l >= nleaves) return;
+    double s[5] = {0, 0, 0, 0, 0};
+    const int nw = item_count[hidx] + 1;
+    for (int q = 0; q < nw; q++) {
+        const double* t = tpart + (((long long)hidx * (item_cap + 1) + q) * 32 + lane) * 5;
+        for (int k = 0; k < 5; k++) s[k] += t[k];
     }
-    const u32 full = (nl == 32) ? 0xffffffffu : ((1u << nl) - 1u);
-    if (tid == 0) stack[0] = make_int2(0, (int)full);
-    __syncthreads();
-    const double mycx = lcx[lane], mycy = lcy[lane];
-    int size = 1;
-    double T1 = 0, T2 = 0, T3 = 0, T4 = 0, nfar = 0;
-    u32 cnt = 0;
-    const long long gbase = FILL ? G.ptr[g] : 0;
-    while (size > 0) {
-        const int take = min(size, kHeavyThreads);
-        int n = -1;
-        u32 em = 0;
-        if (tid < take) { int2 e = stack[size - 1 - tid]; n = e.x; em = (u32)e.y; }
-        size -= take;
-        u32 farm = 0, nearm = 0;
-        int c1 = -1;
-        if (n >= 0) {
-            double nx = T.x[n], ny = T.y[n];
-            double nhw = VV_ADD(T.h[n], T.w[n]);
-            c1 = T.ch1[n];
-            for (u32 mm = em; mm; mm &= mm - 1) {
-                const int l = __ffs(mm) - 1;
-                if (is_far(nx, ny, nhw, lcx[l], lcy[l], lh[l], lw[l], farc)) farm |= (1u << l);
-            }
-            nearm = em & ~farm;
-        }
-        wn[warp][lane] = n;
-        const bool push = (n >= 0) && nearm && (c1 >= 0);
-        const bool emit = (n >= 0) && nearm && (c1 < 0);
-        const u32 pb = __ballot_sync(0xffffffffu, push), eb = __ballot_sync(0xffffffffu, emit);
-        if (lane == 0) { wpush[warp] = __popc(pb); wemit[warp] = __popc(eb); }
-        __syncthreads();  // also orders the stack reads above before the pushes below
-        if (warp == 0) {
-            int a = wpush[lane], b = wemit[lane], ia = a, ib = b;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-                if (lane >= o) { ia += ta; ib += tb; }
-            }
-            wpush[lane] = ia - a; wemit[lane] = ib - b;
-            if (lane == 31) { wpush[32] = ia; wemit[32] = ib; }
-        }
-        __syncthreads();
-        if (size + 2 * wpush[32] > stack_stride) {  // cannot happen: every node is pushed at most once
-            if (tid == 0) atomicExch(err, 1);
-            return;
-        }
-        if (push) {
-            int off = size + 2 * (wpush[warp] + __popc(pb & lanemask_lt()));
-            stack[off] = make_int2(c1 + 1, (int)nearm);
-            stack[off + 1] = make_int2(c1, (int)nearm);
-        }
-        if (FILL && emit) {
-            long long k = gbase + cnt + wemit[warp] + __popc(eb & lanemask_lt());
-            G.leaf[k] = T.lstart[n];
-            G.mask[k] = nearm;
-        }
-        size += 2 * wpush[32];
-        cnt += wemit[32];
-        // far nodes of this warp's 32 frontier nodes -> lane = leaf
-        if (__ballot_sync(0xffffffffu, farm != 0)) {
-            u32 mine = 0;
-#pragma unroll
-            for (int l = 0; l < 32; l++) {
-                u32 tm = __ballot_sync(0xffffffffu, (farm >> l) & 1u);
-                if (lane == l) mine = tm;
-            }
-            nfar += (double)__popc(mine);
-            if (FILL) {
-                while (mine) {
-                    int j = __ffs(mine) - 1;
-                    mine &= mine - 1;
-                    const int nj = wn[warp][j];
-                    taylor_add(mycx, mycy, T.cmp[3ll * nj], T.cmp[3ll * nj + 1], T.cmp[3ll * nj + 2], T1, T2, T3, T4);
-                    taylor_add(mycx, mycy, T.cmm[3ll * nj], T.cmm[3ll * nj + 1], T.cmm[3ll * nj + 2], T1, T2, T3, T4);
-                }
-            }
-        }
-        __syncthreads();  // pushes visible, wn / wpush / wemit free for the next round
-    }
-    for (int w = 0; w < kHeavyThreads / 32; w++) {  // warp partials, in warp order
-        if (warp == w) { acc[0][lane] += T1; acc[1][lane] += T2; acc[2][lane] += T3; acc[3][lane] += T4; accn[lane] += nfar; }
-        __syncthreads();
-    }
-    if (!FILL) {
-        if (tid == 0) gcount[g] = cnt;
-        if (tid < nl && farcount) farcount[l0 + tid] = accn[tid];
-    } else if (tid < nl) {
-        double* t = taylor + 4ll * (l0 + tid);
-        t[0] = acc[0][tid] * k1_2Pi; t[1] = acc[1][tid] * k1_2Pi; t[2] = acc[2][tid] * k1_Pi; t[3] = acc[3][tid] * k1_2Pi;
-    }
-}
-__global__ void k_mark_heavy(const int* heavy, int nheavy, unsigned char* is_heavy) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nheavy) is_heavy[heavy[i]] = 1;
+    double* t = taylor + 4ll * l;
+    t[0] = s[0] * k1_2Pi; t[1] = s[1] * k1_2Pi; t[2] = s[2] * k1_Pi; t[3] = s[3] * k1_2Pi;
+    if (farcount) farcount[l] = s[4];
 }
 
-__global__ void k_group_ptr(const u32* gscan, long long* ptr, int ngroups) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= ngroups) ptr[i] = gscan[i];
+// ---- units: the non-empty chunk slots, in slot order (regular groups first, then heavy walks) ----------
+struct SlotFlag {
+    const int* count;
+    __device__ __forceinline__ u32 operator()(long long i) const { return count[i] > 0 ? 1u : 0u; }
+};
+// slot -> group: regular slots are group-major; heavy slots are (heavy group, walk)-major
+__global__ void k_units_fill(long long nslots_total, long long nreg_slots, const u32* __restrict__ rank,
+                             const long long* __restrict__ slot_base, const int* __restrict__ slot_count,
+                             const int* __restrict__ heavy_list, int item_cap, int* ugroup, long long* ubase, int* ucount) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots_total || slot_count[s] <= 0) return;
+    int g;
+    if (s < nreg_slots) g = (int)(s / kGroupSlots);
+    else g = heavy_list[(s - nreg_slots) / ((long long)(item_cap + 1) * kItemSlots)];
+    const u32 u = rank[s];
+    ugroup[u] = g; ubase[u] = slot_base[s]; ucount[u] = slot_count[s];
+}
+// group -> its unit range. Regular: from the ranks at its first / one-past-last slot.
+__global__ void k_units_groups(int ngroups, const u32* __restrict__ rank, int* ufirst, int* unum) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const u32 a = rank[(long long)g * kGroupSlots], b = rank[(long long)(g + 1) * kGroupSlots];
+    ufirst[g] = (int)a; unum[g] = (int)(b - a);
+}
+__global__ void k_units_heavy(int nheavy, long long nreg_slots, int item_cap, const int* __restrict__ heavy_list,
+                              const u32* __restrict__ rank, int* ufirst, int* unum) {
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nheavy) return;
+    const long long per = (long long)(item_cap + 1) * kItemSlots;
+    const u32 a = rank[nreg_slots + h * per], b = rank[nreg_slots + (h + 1) * per];
+    ufirst[heavy_list[h]] = (int)a; unum[heavy_list[h]] = (int)(b - a);
 }
 
 // ---- literal per-leaf walk, for export only ---------------------------------------------------
@@ -330,11 +358,13 @@ __global__ void k_lists_dfs(TreeDev T, LeafDev L, int nleaves, double farc, u32*
     if (!FILL) { ncount[l] = nn; fcount[l] = nf; }
 }
 
-// near-pair count of one group: sum over entries of (#targets g!=0 in masked leaves) x (#sources g!=0)
-__global__ void k_count_pairs(LeafDev L, int nleaves, int ngroups, GroupLists G, const double* __restrict__ pg,
-                              double* out) {
-    int g = blockIdx.x;
-    if (g >= ngroups) return;
+// near-pair count of one work unit: sum over its entries of (#targets g!=0 in masked leaves) x (#sources g!=0)
+__global__ void k_count_pairs(LeafDev L, int nleaves, int nunits, const int* __restrict__ ugroup,
+                              const long long* __restrict__ ubase, const int* __restrict__ ucount, GroupLists G,
+                              const double* __restrict__ pg, double* out) {
+    int u = blockIdx.x;
+    if (u >= nunits) return;
+    const int g = ugroup[u];
     __shared__ int nz[kGroupLeaves];
     __shared__ double acc[32];
     int l0 = g * kGroupLeaves, nl = min(kGroupLeaves, nleaves - l0);
@@ -346,7 +376,8 @@ __global__ void k_count_pairs(LeafDev L, int nleaves, int ngroups, GroupLists G,
     }
     __syncthreads();
     double s = 0;
-    for (long long e = G.ptr[g] + threadIdx.x; e < G.ptr[g + 1]; e += blockDim.x) {
+    const long long e0 = ubase[u], e1 = e0 + ucount[u];
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         int sl = G.leaf[e];
         u32 m = G.mask[e];
         int ns = 0;
@@ -361,7 +392,7 @@ __global__ void k_count_pairs(LeafDev L, int nleaves, int ngroups, GroupLists G,
     if (threadIdx.x == 0) {
         double t = 0;
         for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += acc[k];
-        out[g] = t;
+        out[u] = t;
     }
 }
 

@@ -33,20 +33,22 @@ constexpr int kLwWarps = 4;
 constexpr int kLwThreads = kLwWarps * 32;
 constexpr int kMaxT = 15;           // targets per pass of a warp
 constexpr int kIdxCap = 1024;       // flat source indices buffered per warp
-constexpr int kUnitEntries = 512;   // list entries per work unit (bounds the work of one CTA)
 constexpr u32 kFullMask = 0xffffffffu;
 
 struct Particles {
     double *x, *y, *g, *vx, *vy, *ie;
 };
 
-// Work units: a group whose list is longer than kUnitEntries is cut into several units (a few
-// fringe leaves see tens of thousands of near leaves). Units of such a group
-// park their partial per-target state in `scratch`; k_near_finalize combines them in unit order.
+// Work units = the chunks the traversal filled (vvgpu_lists.cuh). A group whose list is longer than one
+// chunk has several units (a few fringe leaves see tens of thousands of near leaves);
+// they park their partial per-target state in `scratch` and k_near_finalize combines them in unit order.
 struct Units {
-    const int* group;       // unit -> group
-    const int* first;       // group -> first unit (ngroups + 1)
-    const u32* sbase;       // group -> first scratch slot (ngroups + 1)
+    const int* group;        // unit -> group
+    const long long* base;   // unit -> first entry in the pool
+    const int* count;        // unit -> entries
+    const int* first;        // group -> first unit
+    const int* num;          // group -> number of units
+    const u32* sbase;        // group -> first scratch slot
 };
 
 struct NearArgs {
@@ -168,13 +170,13 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     const int u = A.u0 + blockIdx.x;
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
-    const bool multi = (A.U.first[g + 1] - A.U.first[g]) > 1;
+    const bool multi = A.U.num[g] > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
     if (tid == 0) { S.next = 0; S.anyseg = 0; }
-    const long long e0 = A.G.ptr[g] + (long long)chunk * kUnitEntries;
-    const int ne = (int)(min(A.G.ptr[g + 1], e0 + kUnitEntries) - e0);
+    const long long e0 = A.U.base[u];
+    const int ne = A.U.count[u];
     __syncthreads();
     // ---- the unit's entry table, once per CTA
     for (int e = tid; e < ne; e += kLwThreads) {
@@ -381,7 +383,7 @@ template <class Op>
 __global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, int g0, int g1) {
     const int g = g0 + blockIdx.x;
     if (g >= g1) return;
-    const int nu = A.U.first[g + 1] - A.U.first[g];
+    const int nu = A.U.num[g];
     if (nu <= 1) return;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
@@ -401,22 +403,14 @@ __global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, int g0
     }
 }
 
-// unit bookkeeping: units per group, scratch slots per group
-__global__ void k_unit_count(LeafDev L, GroupLists G, int nleaves, int ngroups, u32* nunits, u32* nslots) {
+// scratch slots per group: multi-unit groups park one partial state per (unit, particle)
+__global__ void k_unit_slots(LeafDev L, int nleaves, int ngroups, const int* __restrict__ unum, u32* nslots) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ngroups) return;
-    long long ne = G.ptr[g + 1] - G.ptr[g];
-    u32 nu = (u32)((ne + kUnitEntries - 1) / kUnitEntries);
-    if (nu == 0) nu = 1;
+    const int nu = unum[g];
     int l0 = g * kGroupLeaves, nl = min(kGroupLeaves, nleaves - l0);
     u32 T = (u32)(L.last[l0 + nl - 1] - L.first[l0]);
-    nunits[g] = nu;
-    nslots[g] = nu > 1 ? nu * T : 0;
-}
-__global__ void k_unit_fill(int ngroups, const int* first, int* group) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ngroups) return;
-    for (int u = first[g]; u < first[g + 1]; u++) group[u] = g;
+    nslots[g] = nu > 1 ? (u32)nu * T : 0;
 }
 
 // per-phase packed source records (one 32-byte load per staged source instead of four scattered ones)
@@ -813,9 +807,8 @@ __global__ void __launch_bounds__(256) k_wall_pass(LeafDev L, GroupLists G, Unit
     const int u = blockIdx.x;
     if (u >= nunits) return;
     const int g = U.group[u];
-    const int chunk = u - U.first[g];
-    const long long e0 = G.ptr[g] + (long long)chunk * kUnitEntries;
-    const long long e1 = min(G.ptr[g + 1], e0 + kUnitEntries);
+    const long long e0 = U.base[u];
+    const long long e1 = e0 + U.count[u];
     for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int sl = G.leaf[e];
         const int sf = L.sfirst[sl], se = L.slast[sl];

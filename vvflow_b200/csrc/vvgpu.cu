@@ -101,7 +101,7 @@ struct vvgpu_ctx {
     std::vector<int> h_lvl;
     int lists_g0 = 0, lists_g1 = 0;
     Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list,
-        hv_inode, hv_imask, hv_icount, hv_tpart;
+        hv_inode, hv_imask, hv_icount, hv_tpart, hv_off;
     int nunits = 0;
     size_t nslots = 0;
     bool lists_ready = false;
@@ -365,6 +365,11 @@ int lists_impl(vvgpu_ctx* c, bool all) {
             k_traverse<2><<<cdiv((long long)nheavy * item_cap, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
                 T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
             k_heavy_taylor<<<nheavy, 32, 0, st>>>(hvlist, nheavy, nl, tpart, icount, item_cap, taylor, farcount); CKLAUNCH();
+            {
+                int* hoff = c->hv_off.get<int>(2 * (size_t)nheavy_slots + 2, &ok);
+                NEED(ok);
+                k_heavy_pack<<<nheavy, 1024, 0, st>>>(nheavy, item_cap, OH, hoff); CKLAUNCH();
+            }
             CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             errbits = c->h_pinned[64];
@@ -508,7 +513,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode, &c->t_pnode, &c->t_snode[0], &c->t_snode[1],
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->scan_seg, &c->part_n, &c->part_p, &c->part_s, &c->build_state,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
-                  &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
+                  &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
                   &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();

@@ -25,7 +25,7 @@ namespace vv {
 constexpr int kGroupLeaves = 32;
 constexpr int kUnitEntries = 512;   // list entries per chunk = per work unit of the near-field kernels
 constexpr int kTravWarps = 4;       // warps per CTA in k_traverse
-constexpr int kTravBudget = 512;    // warp iterations before a group is declared heavy
+constexpr int kTravBudget = 256;    // warp iterations before a group is declared heavy (the mean is ~150)
 constexpr int kTravStack = 1024;    // stack entries per warp (shared memory)
 constexpr int kGroupSlots = 16;     // chunks a regular group may fill before it is declared heavy
 constexpr int kItemSlots = 64;      // chunks one item of a heavy group may fill
@@ -62,8 +62,16 @@ __device__ __forceinline__ void taylor_add(double cx, double cy, double mx, doub
     if (mg == 0) return;
     double dx = cx - mx, dy = cy - my;
     double a = dx * dx + dy * dy;
-    double f1 = mg / a;
-    double f2 = f1 / a;
+    // 1/a by MUFU.RCP64H + two Newton steps (relative error ~2^-79 before rounding): the coefficients only
+    // feed velocities (1e-10 bar), and two IEEE divisions per monopole were a third of this kernel
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    double f1 = mg * r;
+    double f2 = f1 * r;
     T1 -= f1 * dy;
     T2 += f1 * dx;
     T3 += f2 * dy * dx;
@@ -290,6 +298,58 @@ __global__ void k_heavy_taylor(const int* heavy_list, int nheavy, int nleaves, c
     double* t = taylor + 4ll * l;
     t[0] = s[0] * k1_2Pi; t[1] = s[1] * k1_2Pi; t[2] = s[2] * k1_Pi; t[3] = s[3] * k1_2Pi;
     if (farcount) farcount[l] = s[4];
+}
+
+// The walks of a heavy group leave many short chunks (one tail per item). Pack them, in walk order, into
+// dense chunks of a fresh pool region, so that the near-field kernels see full work units. One CTA per
+// heavy group; `off` is scratch of the same shape as the group's slot range.
+__global__ void __launch_bounds__(1024) k_heavy_pack(int nheavy, int item_cap, TravOut O, int* off) {
+    const int h = blockIdx.x;
+    if (h >= nheavy) return;
+    __shared__ u32 sh[1024 / 32 + 1];
+    __shared__ long long region;
+    __shared__ int total_s, nlive_s;
+    const long long per = (long long)(item_cap + 1) * kItemSlots;
+    long long* sbase = O.slot_base + h * per;
+    int* scount = O.slot_count + h * per;
+    int* doff = off + h * per;                              // dense offset of every slot
+    int* live = off + (long long)nheavy * per + h * per;    // the slots that hold entries, in order
+    u32 carry = 0, lcarry = 0;
+    for (long long b = 0; b < per; b += 1024) {
+        const long long s = b + threadIdx.x;
+        const u32 v = (s < per) ? (u32)scount[s] : 0u;
+        u32 total, ltotal;
+        const u32 ex = block_exclusive_scan<1024>(v, &total, sh);
+        const u32 lex = block_exclusive_scan<1024>(v ? 1u : 0u, &ltotal, sh);
+        if (s < per) doff[s] = (int)(carry + ex);
+        if (v) live[lcarry + lex] = (int)s;
+        carry += total; lcarry += ltotal;
+    }
+    if (threadIdx.x == 0) {
+        nlive_s = (int)lcarry;
+        total_s = (int)carry;
+        const unsigned long long need = ((unsigned long long)carry + kUnitEntries - 1) / kUnitEntries * kUnitEntries;
+        const unsigned long long at = atomicAdd(O.cursor, need);
+        region = (long long)at;
+        if ((long long)(at + need) > O.pool_cap) { atomicOr(O.err, 1); region = -1; }
+    }
+    __syncthreads();
+    if (region < 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = warp; q < nlive_s; q += 32) {
+        const long long s = live[q];
+        const int n = scount[s];
+        const long long src = sbase[s], dst = region + doff[s];
+        for (int k = lane; k < n; k += 32) { O.G.leaf[dst + k] = O.G.leaf[src + k]; O.G.mask[dst + k] = O.G.mask[src + k]; }
+    }
+    __syncthreads();
+    const int total = total_s;
+    for (long long s = threadIdx.x; s < per; s += 1024) {
+        const long long first = s * kUnitEntries;
+        const bool used = first < total;
+        sbase[s] = used ? region + first : 0;
+        scount[s] = used ? (int)min((long long)kUnitEntries, total - first) : 0;
+    }
 }
 
 // ---- units: the non-empty chunk slots, in slot order (regular groups first, then heavy walks) ----------

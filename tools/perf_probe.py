@@ -10,6 +10,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from vvflow_b200 import capi  # noqa: E402
+if os.environ.get('VVGPU_LIB'):
+    capi.LIB_PATH = os.environ['VVGPU_LIB']
 
 ctx = capi.Context(0)
 print("fp64 peak TFLOP/s:", ctx.fp64_peak())

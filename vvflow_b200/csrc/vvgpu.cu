@@ -2,6 +2,7 @@
 // Device code lives in the vvgpu_*.cuh headers next to this file. There is no CPU fallback:
 // every entry point either runs the CUDA kernels or returns an error.
 #include "../../include/vvgpu.h"
+#include "vvgpu_conv.cuh"
 #include "vvgpu_move.cuh"
 #include "vvgpu_tree_coop.cuh"
 
@@ -422,7 +423,7 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
     if (c->nunits <= 0) return 0;
     {
         bool ok = true;
-        double4* s4 = c->src4.get<double4>(c->tn, &ok);
+        double4* s4 = c->src4.get<double4>((size_t)c->tn + 1, &ok);
         NEED(ok);
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
@@ -430,6 +431,21 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
     k_near<Op><<<c->nunits, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<Op><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
+    }
+    return 0;
+}
+
+// K4: dedicated kernel (vvgpu_conv.cuh); record tn of the packed sources is the dummy (g = 0) that pads the index lists
+int launch_conv(vvgpu_ctx* c, ConvOp op) {
+    if (c->nunits <= 0) return 0;
+    bool ok = true;
+    double4* s4 = c->src4.get<double4>((size_t)c->tn + 1, &ok);
+    NEED(ok);
+    k_pack_src<ConvOp><<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), nullptr, s4); CKLAUNCH();
+    CK(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvShared)));
+    k_conv<<<c->nunits, kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
+    if (c->nslots > 0) {  // some group has more than one unit
+        k_near_finalize<ConvOp><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
     }
     return 0;
 }
@@ -907,7 +923,7 @@ int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, cons
     NEED(ok);
     if (nsink) CK(cudaMemcpyAsync(ds, sinks_xyg, 3 * nsink * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     ConvOp op{inf_vx, inf_vy, dt * k1_Pi, c->taylor.as<double>(), ds, (int)nsink};
-    int rc = launch_near(c, op);
+    int rc = launch_conv(c, op);
     if (rc) return rc;
     if (c->any_body_flow && c->nbody) {
         BodyFull B{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),

@@ -1,0 +1,265 @@
+// K4 — the convective near field, MConvectiveFast::near_nodes_influence + biot_savart
+// (libvvhd/src/MConvectiveFast.cpp:116-137) and the per-particle assembly of process_all_lists (:76-86).
+//
+// Same work decomposition as the other near-field passes (vvgpu_near.cuh): a CTA owns one work unit
+// (a group of 32 consecutive leaves x <= 512 entries of its near list), its warps pull target leaves
+// from a shared counter, and a warp expands the source leaves of its leaf into a flat list of particle
+// indices in shared memory. What differs is the streaming: LANES HOLD SOURCES, the leaf's <= 15 targets
+// are broadcast from shared memory and 2 x 15 accumulators stay in registers, so every lane does useful
+// FP64 work on every pair and only one cross-lane reduction per leaf is needed.
+//
+// What the ncu source view of the previous version showed (profiles/r1_ncu_near_leafwarp_conv.txt) and
+// what this version does about it:
+//   * 14 % of the executed instructions were per-iteration bookkeeping (moving the prefetched records
+//     into place, re-creating the dummy record, per-lane bounds predicates)  ->  the loop is unrolled
+//     twice over ping-pong registers (no moves) and the index list is padded with the index of a dummy
+//     record (g = 0) up to a whole iteration, so the loop carries no per-lane predicates;
+//   * the FP64 chains stalled on the MUFU result with only 3 warps per scheduler  ->  leaves with more
+//     than 10 live targets (three target groups) stream ONE source per lane and iteration, leaves with
+//     fewer stream TWO: tools/microbench4.cu measured 1.42 and 1.50 T pairs/s for these two shapes at
+//     3 CTAs per SM, against 1.25 T for two sources with three groups (register pressure throttles
+//     ptxas' interleaving of independent pairs).
+#pragma once
+#include "vvgpu_near.cuh"
+
+namespace vv {
+
+#ifndef VV_CV_MINB
+#define VV_CV_MINB 3
+#endif
+#ifndef VV_CV_FLUSH
+#define VV_CV_FLUSH 1024
+#endif
+#ifndef VV_CV_NS
+#define VV_CV_NS 2
+#endif
+#ifndef VV_CV_WARPS
+#define VV_CV_WARPS 4
+#endif
+constexpr int kCvWarps = VV_CV_WARPS;
+constexpr int kCvThreads = kCvWarps * 32;
+constexpr int kCvFlush = VV_CV_FLUSH;          // drain the index buffer once it holds this many sources
+constexpr int kCvPiece = 16;                   // sources appended per entry and round
+constexpr int kCvCap = kCvFlush + 32 * kCvPiece + 64;
+
+struct CvWarp {
+    int idx[kCvCap];           // flat list of source particle indices
+    double2 txy[kMaxT + 1];    // target positions, broadcast to all lanes
+};
+struct CvShared {
+    int4 ent[kUnitEntries];    // first particle, count of the entry's leaf, target-leaf mask
+    int bounds[kGroupLeaves + 1];
+    int next;                  // next target leaf of the group to hand out
+    CvWarp w[kCvWarps];
+};
+
+// rotl(dr) * g / (|dr|^2 + eps^2). Reciprocal = rcp.approx.ftz.f64 (MUFU.RCP64H, relative error
+// e0 <= 2^-19.9 measured on B200, tools/microbench2.cu) + one Newton step: 1/den = r0 (1 + e) up to
+// e0^2 <= 2^-39.8 ~ 1e-12 per pair, two orders below the 1e-10 bar on velocities. 9 FP64 ops / pair.
+__device__ __forceinline__ void cv_pair(const double2 p, const double4 s, double& ax, double& ay) {
+    const double dx = p.x - s.x, dy = p.y - s.y;
+    const double den = fma(dx, dx, fma(dy, dy, s.w));
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
+    const double e = fma(-den, r0, 1.0);
+    const double gr = s.z * r0;
+    const double w = fma(gr, e, gr);
+    ax = fma(-dy, w, ax);
+    ay = fma(dx, w, ay);
+}
+
+template <int NS, int BASE, int N>
+__device__ __forceinline__ void cv_group(const double2* txy, const double4& s, const double4& s2, double (&ax)[kMaxT],
+                                         double (&ay)[kMaxT]) {
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        const double2 p = txy[BASE + t];   // one broadcast load serves both sources of the lane
+        cv_pair(p, s, ax[BASE + t], ay[BASE + t]);
+        if (NS == 2) cv_pair(p, s2, ax[BASE + t], ay[BASE + t]);
+    }
+}
+
+// The nt <= 15 live targets of a pass sit in slots [0, p) u [5, 5 + 5 * nfull): a partial group of
+// p = nt - 5 * nfull in 1..5 targets at base 0 and nfull in 0..2 FULL groups of five at bases 5 and 10. Only
+// the partial group needs one code body per size; the instruction footprint of the streaming loop is
+// what bounds this kernel's shape (a loop of more than ~30 KB thrashes the instruction cache: ncu
+// showed stall_no_instruction at 55 % of all samples for a two-variant build).
+struct CvGroups {
+    int p, nfull;
+    __device__ __forceinline__ void set(int nt) { nfull = (nt - 1) / 5; p = nt - 5 * nfull; }
+    __device__ __forceinline__ int slot(int k) const { return (k < p) ? k : (5 + (k - p)); }   // k-th live target -> slot
+    __device__ __forceinline__ bool used(int t) const { return (t < 5) ? (t < p) : (t < 5 + 5 * nfull); }
+};
+
+template <int NS>
+__device__ __forceinline__ void cv_groups(const double2* txy, const double4& s, const double4& s2, const CvGroups& G,
+                                          double (&ax)[kMaxT], double (&ay)[kMaxT]) {
+    if (G.nfull > 0) {
+        cv_group<NS, 5, 5>(txy, s, s2, ax, ay);
+        if (G.nfull > 1) cv_group<NS, 10, 5>(txy, s, s2, ax, ay);
+    }
+    if (G.p >= 4) {
+        if (G.p == 5) cv_group<NS, 0, 5>(txy, s, s2, ax, ay);
+        else cv_group<NS, 0, 4>(txy, s, s2, ax, ay);
+    } else if (G.p == 3) cv_group<NS, 0, 3>(txy, s, s2, ax, ay);
+    else if (G.p == 2) cv_group<NS, 0, 2>(txy, s, s2, ax, ay);
+    else cv_group<NS, 0, 1>(txy, s, s2, ax, ay);
+}
+
+// nit iterations of 32 * NS sources; idx[0 .. nit * 32 * NS) are valid indices (padded with the dummy record)
+template <int NS>
+__device__ __forceinline__ void cv_stream(const double4* __restrict__ src4, const double2* txy, const int* idx, int nit,
+                                          const CvGroups& G, double (&ax)[kMaxT], double (&ay)[kMaxT], int lane) {
+    constexpr int STEP = 32 * NS;
+    const int* ip = idx + lane;
+    double4 a0 = src4[ip[0]], a1 = a0;
+    if (NS == 2) a1 = src4[ip[32]];
+    double4 b0 = a0, b1 = a1;
+    int it = 0;
+    for (;;) {
+        if (it + 1 < nit) {   // prefetch the next records behind this iteration's math
+            b0 = src4[ip[STEP]];
+            if (NS == 2) b1 = src4[ip[STEP + 32]];
+        }
+        cv_groups<NS>(txy, a0, a1, G, ax, ay);
+        if (++it >= nit) break;
+        if (it + 1 < nit) {
+            a0 = src4[ip[2 * STEP]];
+            if (NS == 2) a1 = src4[ip[2 * STEP + 32]];
+        }
+        cv_groups<NS>(txy, b0, b1, G, ax, ay);
+        if (++it >= nit) break;
+        ip += 2 * STEP;
+    }
+}
+
+__global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, ConvOp op, int dummy) {
+    extern __shared__ __align__(16) unsigned char near_smem[];
+    CvShared& S = *reinterpret_cast<CvShared*>(near_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = A.u0 + blockIdx.x;
+    const int g = A.U.group[u];
+    const int chunk = u - A.U.first[g];
+    const bool multi = A.U.num[g] > 1;
+    const int l0 = g * kGroupLeaves;
+    const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
+    if (tid == 0) S.next = 0;
+    const long long e0 = A.U.base[u];
+    const int ne = A.U.count[u];
+    // ---- the unit's entry table, once per CTA
+    for (int e = tid; e < ne; e += kCvThreads) {
+        const int sl = A.G.leaf[e0 + e];
+        const int f = A.L.first[sl];
+        S.ent[e] = make_int4(f, A.L.last[sl] - f, (int)A.G.mask[e0 + e], 0);
+    }
+    __syncthreads();
+    const int t0 = S.bounds[0], t1 = S.bounds[nl];
+    CvWarp& W = S.w[warp];
+    ConvOp::Part* scratch = (ConvOp::Part*)A.scratch;
+    const size_t sbase = multi ? ((size_t)A.U.sbase[g] + (size_t)chunk * (t1 - t0)) : 0;
+
+    for (;;) {
+        int lt = 0;
+        if (lane == 0) lt = atomicAdd(&S.next, 1);
+        lt = __shfl_sync(kFullMask, lt, 0);
+        if (lt >= nl) break;
+        const int leaf = l0 + lt;
+        const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
+        for (int tb = pf; tb < pl; tb += kMaxT) {
+            const int np = min(kMaxT, pl - tb);
+            ConvOp::Tgt tg;
+            const int i = tb + lane;
+            const bool live = op.init(tg, A, i, leaf, lane < np);
+            const u32 lm = __ballot_sync(kFullMask, live);
+            const int nt = __popc(lm);
+            if (nt == 0) continue;
+            CvGroups GR;
+            GR.set(nt);
+            const int myt = live ? GR.slot(__popc(lm & lanemask_lt())) : -1;
+            if (live) W.txy[myt] = make_double2(tg.x, tg.y);
+            double ax[kMaxT], ay[kMaxT];
+#pragma unroll
+            for (int t = 0; t < kMaxT; t++) { ax[t] = 0; ay[t] = 0; }
+            constexpr int kNS = VV_CV_NS, step = 32 * kNS;
+            __syncwarp();
+            // ---- scan the entry table, expand the kept leaves into source indices, stream them
+            int fill = 0, eb = 0, cnt = 0, f = 0;
+            for (;;) {
+                bool pending = __any_sync(kFullMask, cnt > 0);
+                while (fill < kCvFlush && (pending || eb < ne)) {
+                    if (!pending) {
+                        const int e = eb + lane;
+                        eb += 32;
+                        if (e < ne) {
+                            const int4 en = S.ent[e];
+                            f = en.x;
+                            cnt = (((u32)en.z >> lt) & 1u) ? en.y : 0;
+                        }
+                        pending = __any_sync(kFullMask, cnt > 0);
+                        continue;
+                    }
+                    const int c = min(cnt, kCvPiece);
+                    int inc = c;   // inclusive scan; the shuffle's own predicate says whether the source lane exists
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                        asm volatile("{ .reg .pred p; .reg .s32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.s32 %0, %0, t; }"
+                                     : "+r"(inc) : "r"(o));
+                    const int tot = __shfl_sync(kFullMask, inc, 31);
+                    int* dst = W.idx + fill + inc - c;
+#pragma unroll
+                    for (int k = 0; k < kCvPiece; k++)
+                        if (k < c) dst[k] = f + k;
+                    fill += tot; cnt -= c; f += c;
+                    pending = __any_sync(kFullMask, cnt > 0);
+                }
+                const bool final = !pending && eb >= ne;
+                int nit, upto;
+                if (final) {   // pad the last iteration with the dummy record
+                    nit = (fill + step - 1) / step;
+                    upto = nit * step;
+                    if (fill + lane < upto) W.idx[fill + lane] = dummy;
+                    if (fill + lane + 32 < upto) W.idx[fill + lane + 32] = dummy;
+                } else {
+                    nit = fill / step;
+                    upto = nit * step;
+                }
+                __syncwarp();
+                if (nit > 0) {
+                    cv_stream<kNS>(A.src4, W.txy, W.idx, nit, GR, ax, ay, lane);
+                }
+                if (final) break;
+                // the incomplete last iteration goes to the front of the next drain
+                const int carry = fill - upto;
+                int v = 0, v2 = 0;
+                if (lane < carry) v = W.idx[upto + lane];
+                if (lane + 32 < carry) v2 = W.idx[upto + lane + 32];
+                __syncwarp();
+                if (lane < carry) W.idx[lane] = v;
+                if (lane + 32 < carry) W.idx[lane + 32] = v2;
+                fill = carry;
+                __syncwarp();
+            }
+            // ---- lane sums -> the lane that owns the target
+#pragma unroll
+            for (int t = 0; t < kMaxT; t++) {
+                if (GR.used(t)) {
+                    double vx = ax[t], vy = ay[t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        vx += __shfl_xor_sync(kFullMask, vx, o);
+                        vy += __shfl_xor_sync(kFullMask, vy, o);
+                    }
+                    if (myt == t) op.take(tg, vx, vy);
+                }
+            }
+            if (live) {
+                if (multi) scratch[sbase + (i - t0)] = op.part(tg);
+                else op.finish(tg, A, i, leaf);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace vv

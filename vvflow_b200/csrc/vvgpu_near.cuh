@@ -1,31 +1,21 @@
-// K3 / K4 / K5 — the three near-field passes over the reference's (leaf, near leaf) pair set:
+// K3 / K5 — the two near-field passes with short, pruned source lists (K4, the convective pass, has its
+// own kernel in vvgpu_conv.cuh and shares the work decomposition, the operators' finish/combine code and
+// k_near_finalize with this file):
 //   EpsOp   MEpsilonFast::epsv + merge decision        (libvvhd/src/MEpsilonFast.cpp:128-173)
-//   ConvOp  MConvectiveFast::near_nodes_influence      (libvvhd/src/MConvectiveFast.cpp:116-137)
-//           + the per-particle assembly of process_all_lists (:76-86)
 //   DiffOp  MDiffusiveFast::process_vort_list          (libvvhd/src/MDiffusiveFast.cpp:8-48,93-123)
+//   ConvOp  per-particle assembly of MConvectiveFast::process_all_lists (:76-86)
 //
 // Layout ("leaf-warp"): a CTA owns one work unit = one group of 32 consecutive leaves x <= 512
 // entries of the group's near list. Its warps pull TARGET LEAVES from a shared counter; a warp
-// scans the unit's entry table, keeps the source leaves whose mask bit names its leaf (and, for
-// epsilon / diffusive, whose box is within the leaf's exact reach), expands them into a flat
-// list of source particle indices in shared memory and streams that list:
-//   * ConvOp — lanes hold SOURCES (one 32-byte packed record per lane, prefetched), the leaf's
-//     <= 15 targets are broadcast from shared memory, 2 x 15 accumulators stay in registers and
-//     are reduced across lanes once per leaf. Every lane does useful FP64 work on every pair.
-//   * EpsOp / DiffOp — the pruned lists are short; the warp is split into nt x m sub-lanes
-//     (m = 32 / nt), each target's sources are dealt round-robin to its m sub-lanes and the
-//     partial states are merged with a segmented shuffle reduction.
+// scans the unit's entry table, keeps the source leaves whose mask bit names its leaf and whose box
+// is within the leaf's exact reach, expands them into a flat list of source particle indices in
+// shared memory and streams that list: the warp is split into nt x m sub-lanes (m = 32 / nt), each
+// target's sources are dealt round-robin to its m sub-lanes and the partial states are merged with a
+// segmented shuffle reduction.
 // A leaf normally holds < 16 particles (Tree_MaxListSize); leaves made by the min-node-size rule
 // can hold more and are processed in chunks of 15 targets.
 #pragma once
 #include "vvgpu_lists.cuh"
-
-#ifndef VV_CONV_MINB
-#define VV_CONV_MINB 3
-#endif
-#ifndef VV_CONV_LANES_SRC
-#define VV_CONV_LANES_SRC 1
-#endif
 
 namespace vv {
 
@@ -69,11 +59,10 @@ struct NearArgs {
 
 template <class Op>
 struct LwWarpT {
-    static constexpr int kCap = Op::kLanesAreSources ? kIdxCap : kIdxCap / 2;
+    static constexpr int kCap = kIdxCap / 2;
     static constexpr int kFlush = kCap / 2;
     int idx[kCap];                                             // flat list of source particle indices
-    double2 txy[Op::kLanesAreSources ? kMaxT + 1 : 1];         // ConvOp: target positions, broadcast to all lanes
-    double tsave[Op::kLanesAreSources ? 1 : kMaxT][16];        // sub-lane ops: target states handed to the sub-lanes
+    double tsave[kMaxT][16];                                   // target states handed to the sub-lanes
     int tpart[kMaxT + 1];                                      // particle index of each target slot
 };
 template <class Op>
@@ -96,70 +85,6 @@ __device__ __forceinline__ T shfl_down_struct(const T& v, int o) {
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(T) / 4); k++) b[k] = __shfl_down_sync(kFullMask, a[k], o);
     return r;
-}
-
-// ---- ConvOp streaming: lanes = sources, targets from shared memory, accumulators in registers.
-// The nt <= 15 targets of a pass sit in up to three groups of at most five slots (bases 0, 5, 10)
-// of as equal size as possible, so that every group offers 3-5 independent dependency chains
-// (tools/microbench3.cu: 9+ chains per SM sub-partition fill the FP64 pipe). One copy of the code
-// serves every target count: per-count variants overflow the instruction cache (ncu:
-// stall_no_instruction dominated a 15-variant build).
-struct LwGroups {
-    int s[3];   // slots used in each group
-    __device__ __forceinline__ void set(int nt) {
-        const int ng = (nt + 4) / 5, q = nt / ng, r = nt - q * ng;
-        s[0] = q + (0 < r ? 1 : 0);
-        s[1] = (ng > 1) ? q + (1 < r ? 1 : 0) : 0;
-        s[2] = (ng > 2) ? q : 0;
-    }
-    __device__ __forceinline__ int slot(int k) const {   // k-th live target -> slot
-        if (k < s[0]) return k;
-        k -= s[0];
-        if (k < s[1]) return 5 + k;
-        return 10 + (k - s[1]);
-    }
-    __device__ __forceinline__ bool used(int t) const { return (t % 5) < s[t / 5]; }
-};
-
-template <class Op, int BASE, int N>
-__device__ __forceinline__ void lw_group(const Op& op, const LwWarpT<Op>& W, const double4& s, const double4& s2,
-                                         double (&ax)[kMaxT], double (&ay)[kMaxT]) {
-#pragma unroll
-    for (int t = 0; t < N; t++) {
-        const double2 p = W.txy[BASE + t];   // one broadcast load serves both sources of the lane
-        op.pair(p, s, ax[BASE + t], ay[BASE + t]);
-        op.pair(p, s2, ax[BASE + t], ay[BASE + t]);
-    }
-}
-
-// Two sources per lane and iteration (64 per warp): halves the shared-memory loads, branches and
-// loop overhead per pair and doubles the independent chains in flight.
-template <class Op>
-__device__ __forceinline__ void lw_stream(const Op& op, const NearArgs& A, const LwWarpT<Op>& W, const int* idx,
-                                          double (&ax)[kMaxT], double (&ay)[kMaxT], int nit, int fill, const LwGroups& G,
-                                          int lane) {
-    double4 s = (lane < fill) ? A.src4[idx[lane]] : Op::dummy();
-    double4 s2 = (lane + 32 < fill) ? A.src4[idx[lane + 32]] : Op::dummy();
-    for (int it = 0; it < nit; it++) {
-        double4 nx = Op::dummy(), nx2 = Op::dummy();
-        const int k = (it + 1) * 64 + lane;
-        if (k < fill) nx = A.src4[idx[k]];   // prefetch the next records behind this iteration's math
-        if (k + 32 < fill) nx2 = A.src4[idx[k + 32]];
-#define VV_GROUP(BASE, SZ)                                                     \
-        if (SZ >= 4) {                                                         \
-            if (SZ == 5) lw_group<Op, BASE, 5>(op, W, s, s2, ax, ay);          \
-            else lw_group<Op, BASE, 4>(op, W, s, s2, ax, ay);                  \
-        } else if (SZ == 3) lw_group<Op, BASE, 3>(op, W, s, s2, ax, ay);       \
-        else if (SZ == 2) lw_group<Op, BASE, 2>(op, W, s, s2, ax, ay);         \
-        else lw_group<Op, BASE, 1>(op, W, s, s2, ax, ay);
-        VV_GROUP(0, G.s[0])
-        if (G.s[1]) {
-            VV_GROUP(5, G.s[1])
-            if (G.s[2]) { VV_GROUP(10, G.s[2]) }
-        }
-#undef VV_GROUP
-        s = nx; s2 = nx2;
-    }
 }
 
 template <class Op>
@@ -231,149 +156,90 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
                 }
                 R2 *= 1.000000001;  // the skip stays strictly conservative against rounding in the gap
             }
-            // sub-lane layout of EpsOp / DiffOp
-            int m = 1, myslot = 0, sub = 0;
-            bool active = false;
-            typename Op::Tgt my;
-            double ax[kMaxT], ay[kMaxT];
-            LwGroups GR;
-            if constexpr (Op::kLanesAreSources) {
-                GR.set(nt);
-                if (live) W.txy[GR.slot(slot)] = make_double2(tg.x, tg.y);
-#pragma unroll
-                for (int t = 0; t < kMaxT; t++) { ax[t] = 0; ay[t] = 0; }
-            } else {
-                static_assert(sizeof(typename Op::Tgt) <= sizeof(W.tsave[0]), "tsave slot too small");
-                if (live) { *reinterpret_cast<typename Op::Tgt*>(W.tsave[slot]) = tg; W.tpart[slot] = i; }
-                m = 32 / nt;
-                myslot = lane / m;
-                sub = lane - myslot * m;
-                active = myslot < nt;
-            }
+            // sub-lane layout: nt x m lanes, m = 32 / nt
+            static_assert(sizeof(typename Op::Tgt) <= sizeof(W.tsave[0]), "tsave slot too small");
+            if (live) { *reinterpret_cast<typename Op::Tgt*>(W.tsave[slot]) = tg; W.tpart[slot] = i; }
+            const int m = 32 / nt;
+            const int myslot = lane / m;
+            const int sub = lane - myslot * m;
+            const bool active = myslot < nt;
             __syncwarp();
-            if constexpr (!Op::kLanesAreSources) {
-                my = *reinterpret_cast<const typename Op::Tgt*>(W.tsave[active ? myslot : 0]);
-                // wall segments of the near leaves (MDiffusiveFast.cpp:26-34): one sub-lane per target
-                if (Op::kSegments && S.anyseg && active && sub == 0) {
-                    for (int e = 0; e < ne; e++) {
-                        if (!((S.emk[e] >> lt) & 1u)) continue;
-                        const int4 en = S.ent[e];
-                        if (en.w > 0) op.segments(my, A, en.z, en.z + en.w);
-                    }
+            typename Op::Tgt my = *reinterpret_cast<const typename Op::Tgt*>(W.tsave[active ? myslot : 0]);
+            // wall segments of the near leaves (MDiffusiveFast.cpp:26-34): one sub-lane per target
+            if (Op::kSegments && S.anyseg && active && sub == 0) {
+                for (int e = 0; e < ne; e++) {
+                    if (!((S.emk[e] >> lt) & 1u)) continue;
+                    const int4 en = S.ent[e];
+                    if (en.w > 0) op.segments(my, A, en.z, en.z + en.w);
                 }
             }
             // ---- scan the entry table, expand the kept leaves into source indices, stream them
             int fill = 0, eb = 0, cnt = 0, f = 0;
             for (;;) {
-                const int* ip = W.idx;
-                int nit = 0, upto = 0, carry = 0;
-                bool final = false;
-                {
-                    // refill: until the buffer is worth draining or the table is exhausted
-                    bool pending = __any_sync(kFullMask, cnt > 0);
-                    while (fill < kFlush && (pending || eb < ne)) {
-                        if (!pending) {
-                            const int e = eb + lane;
-                            eb += 32;
-                            if (e < ne && ((S.emk[e] >> lt) & 1u)) {
-                                const int4 en = S.ent[e];
-                                f = en.x; cnt = en.y;
-                                if constexpr (Op::kFilter) if (cnt) {
-                                    const double* b = S.ebox[e];
-                                    const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
-                                    const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
-                                    if (gx * gx + gy * gy > R2) cnt = 0;
-                                }
+                // refill: until the buffer is worth draining or the table is exhausted
+                bool pending = __any_sync(kFullMask, cnt > 0);
+                while (fill < kFlush && (pending || eb < ne)) {
+                    if (!pending) {
+                        const int e = eb + lane;
+                        eb += 32;
+                        if (e < ne && ((S.emk[e] >> lt) & 1u)) {
+                            const int4 en = S.ent[e];
+                            f = en.x; cnt = en.y;
+                            if constexpr (Op::kFilter) if (cnt) {
+                                const double* b = S.ebox[e];
+                                const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
+                                const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
+                                if (gx * gx + gy * gy > R2) cnt = 0;
                             }
-                            pending = __any_sync(kFullMask, cnt > 0);
-                            continue;
                         }
-                        const int c = min(cnt, kPiece);
-                        int inc = c;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int t = __shfl_up_sync(kFullMask, inc, o);
-                            if (lane >= o) inc += t;
-                        }
-                        const int tot = __shfl_sync(kFullMask, inc, 31);
-                        int* dst = W.idx + fill + inc - c;
-                        for (int k = 0; k < c; k++) dst[k] = f + k;
-                        fill += tot; cnt -= c; f += c;
                         pending = __any_sync(kFullMask, cnt > 0);
+                        continue;
                     }
-                    __syncwarp();
-                    final = !pending && eb >= ne;
-                    constexpr int kStep = Op::kLanesAreSources ? 64 : 32;   // sources per streaming iteration
-                    nit = final ? ((fill + kStep - 1) / kStep) : (fill / kStep);
-                    upto = final ? fill : (nit * kStep);
-                    carry = final ? 0 : (fill - upto);
-                }
-                if constexpr (Op::kLanesAreSources) {
-                    if (nit > 0) lw_stream(op, A, W, ip, ax, ay, nit, upto, GR, lane);
-                    if (ip == W.idx) {   // the incomplete last iteration goes to the front of the next drain
-                        int v = 0, v2 = 0;
-                        if (lane < carry) v = W.idx[upto + lane];
-                        if (lane + 32 < carry) v2 = W.idx[upto + lane + 32];
-                        __syncwarp();
-                        if (lane < carry) W.idx[lane] = v;
-                        if (lane + 32 < carry) W.idx[lane + 32] = v2;
-                        __syncwarp();
-                        fill = carry;
+                    const int c = min(cnt, kPiece);
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFullMask, inc, o);
+                        if (lane >= o) inc += t;
                     }
-                } else {
-                    if (active) {   // four loads in flight per lane before the first is used
-                        for (int k = sub; k < fill; k += 4 * m) {
-                            int j[4];
-                            typename Op::Src v[4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int kk = k + q * m;
-                                j[q] = (kk < fill) ? W.idx[kk] : -1;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) v[q] = (j[q] >= 0) ? Op::fetch(A, j[q]) : Op::none();
-#pragma unroll
-                            for (int q = 0; q < 4; q++) op.use(my, A, v[q], j[q]);
-                        }
-                    }
-                    __syncwarp();
-                    fill = 0;
-                }
-                if (final) break;
-            }
-            if constexpr (Op::kLanesAreSources) {
-                // lane sums -> the lane that owns the target
-#pragma unroll
-                const int myt = live ? GR.slot(slot) : -1;
-#pragma unroll
-                for (int t = 0; t < kMaxT; t++) {
-                    if (GR.used(t)) {
-                        double vx = ax[t], vy = ay[t];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            vx += __shfl_xor_sync(kFullMask, vx, o);
-                            vy += __shfl_xor_sync(kFullMask, vy, o);
-                        }
-                        if (myt == t) op.take(tg, vx, vy);
-                    }
-                }
-                if (live) {
-                    if (multi) scratch[sbase + (i - t0)] = op.part(tg);
-                    else op.finish(tg, A, i, leaf);
-                }
-            } else {
-                // merge the m sub-lane states of every target into its first sub-lane
-                for (int o = 1; o < m; o <<= 1) {
-                    const typename Op::Part q = shfl_down_struct(op.part(my), o);
-                    if (active && sub + o < m) op.combine(my, q);
-                }
-                if (active && sub == 0) {
-                    const int ip = W.tpart[myslot];
-                    if (multi) scratch[sbase + (ip - t0)] = op.part(my);
-                    else op.finish(my, A, ip, leaf);
+                    const int tot = __shfl_sync(kFullMask, inc, 31);
+                    int* dst = W.idx + fill + inc - c;
+                    for (int k = 0; k < c; k++) dst[k] = f + k;
+                    fill += tot; cnt -= c; f += c;
+                    pending = __any_sync(kFullMask, cnt > 0);
                 }
                 __syncwarp();
+                const bool final = !pending && eb >= ne;
+                if (active) {   // four loads in flight per lane before the first is used
+                    for (int k = sub; k < fill; k += 4 * m) {
+                        int j[4];
+                        typename Op::Src v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int kk = k + q * m;
+                            j[q] = (kk < fill) ? W.idx[kk] : -1;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) v[q] = (j[q] >= 0) ? Op::fetch(A, j[q]) : Op::none();
+#pragma unroll
+                        for (int q = 0; q < 4; q++) op.use(my, A, v[q], j[q]);
+                    }
+                }
+                __syncwarp();
+                fill = 0;
+                if (final) break;
             }
+            // merge the m sub-lane states of every target into its first sub-lane
+            for (int o = 1; o < m; o <<= 1) {
+                const typename Op::Part q = shfl_down_struct(op.part(my), o);
+                if (active && sub + o < m) op.combine(my, q);
+            }
+            if (active && sub == 0) {
+                const int ip = W.tpart[myslot];
+                if (multi) scratch[sbase + (ip - t0)] = op.part(my);
+                else op.finish(my, A, ip, leaf);
+            }
+            __syncwarp();
         }
     }
 }
@@ -418,14 +284,13 @@ template <class Op>
 __global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4* out) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) out[j] = Op::pack(P, j, dyn);
+    else if (j == n) out[j] = make_double4(0., 0., 0., 1.);   // dummy record (g = 0): pads K4's index lists
 }
 
 // ------------------------------------------------------------------------------------------ K4
 struct ConvOp {
     static constexpr bool kSegments = false;
     static constexpr bool kFilter = false;
-    static constexpr bool kLanesAreSources = VV_CONV_LANES_SRC;
-    static constexpr int kMinBlocks = VV_CONV_LANES_SRC ? VV_CONV_MINB : 10;   // 128 threads x 3: up to 170 registers for the 30 accumulators
     double inf_vx, inf_vy, eps2_div_srcg;
     const double* taylor;  // 4 per leaf
     const double* sinks;   // (x,y,g) triples
@@ -499,7 +364,6 @@ struct DiffOp {
     // only sources within 8 eps of a target contribute (:101): leaves farther than that from the whole
     // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
     static constexpr bool kFilter = true;
-    static constexpr bool kLanesAreSources = false;
     static constexpr int kMinBlocks = 5;
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
@@ -611,7 +475,6 @@ struct EpsOp {
     // a source leaf whose box is farther from the leaf's targets than the largest seeded second-neighbour
     // distance cannot hold a closer neighbour of any of them: exact pruning
     static constexpr bool kFilter = true;
-    static constexpr bool kLanesAreSources = false;
     static constexpr int kMinBlocks = 6;
     MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
     MergeState B_;      // recomputed solution (decision mode only)

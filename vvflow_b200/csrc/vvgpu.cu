@@ -3,6 +3,7 @@
 // every entry point either runs the CUDA kernels or returns an error.
 #include "../../include/vvgpu.h"
 #include "vvgpu_conv.cuh"
+#include "vvgpu_diff.cuh"
 #include "vvgpu_move.cuh"
 #include "vvgpu_tree_coop.cuh"
 
@@ -101,7 +102,7 @@ struct vvgpu_ctx {
     long long pool_cap = 0;
     std::vector<int> h_lvl;
     int lists_g0 = 0, lists_g1 = 0;
-    Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, lbox, wall_d, wall_key, hv_list,
+    Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, src2, lbox, wall_d, wall_key, hv_list,
         hv_inode, hv_imask, hv_icount, hv_tpart, hv_off;
     int nunits = 0;
     size_t nslots = 0;
@@ -450,6 +451,24 @@ int launch_conv(vvgpu_ctx* c, ConvOp op) {
     return 0;
 }
 
+// K5: dedicated kernel (vvgpu_diff.cuh)
+int launch_diff(vvgpu_ctx* c, DiffOp op) {
+    if (c->nunits <= 0) return 0;
+    bool ok = true;
+    double4* s4 = c->src4.get<double4>((size_t)c->tn + 1, &ok);
+    NEED(ok);
+    double2* xy = c->src2.get<double2>(2 * ((size_t)c->tn + 1), &ok);
+    NEED(ok);
+    double2* xyn = xy + (size_t)c->tn + 1;
+    k_pack_diff<<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), s4, xy, xyn); CKLAUNCH();
+    CK(cudaFuncSetAttribute(k_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)));
+    k_diff<<<c->nunits, kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
+    if (c->nslots > 0) {  // some group has more than one unit
+        k_near_finalize<DiffOp><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
+    }
+    return 0;
+}
+
 // per-leaf merge criterion / epsilon restriction / nearest segment (MEpsilonFast.cpp:26-47)
 int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* latt) {
     cudaStream_t st = c->stream;
@@ -531,7 +550,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
-                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
+                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
     c->ps[0].release(); c->ps[1].release();
@@ -948,7 +967,7 @@ int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
             NEED(ok);
             k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), MergeState{}, lb); CKLAUNCH();
             DiffOp op{re, c->d_fric.as<double>()};
-            int rc = launch_near(c, op);
+            int rc = launch_diff(c, op);
             if (rc) return rc;
         }
     }

@@ -18,6 +18,7 @@
 #include "vvgpu_tree.cuh"
 
 #include <cooperative_groups.h>
+#include <cstdio>
 
 namespace vv {
 namespace cg = cooperative_groups;
@@ -94,50 +95,101 @@ __device__ __forceinline__ void coop_scan_apply(F f, long long n, const u32* par
     }
 }
 
-// Stretch of freshly created nodes: fold every object into the box of its (pending) node
-__device__ __forceinline__ void coop_bbox(const TreeDev& T, const int* snode, const double* px, const double* py, int n,
-                                          const double* sx, const double* sy, const int* seg_perm, int nseg,
-                                          long long gtid, long long gsize) {
-    const long long total = (long long)n + nseg;
-    const long long rounds = (total + gsize - 1) / gsize;
-    for (long long r = 0; r < rounds; r++) {   // whole warps stay together for the shuffles below
-        const long long i = r * gsize + gtid;
-        int node = -1;
-        double x = 0, y = 0;
-        if (i < n) { node = T.pnode[i]; x = px[i]; y = py[i]; }
-        else if (i < total) { int k = (int)(i - n); node = snode[k]; int s = seg_perm[k]; x = sx[s]; y = sy[s]; }
-        if (node >= 0 && T.status[node] != ST_PENDING) node = -1;
-        const int n0 = __shfl_sync(0xffffffffu, node, 0);
-        const bool uniform = __all_sync(0xffffffffu, node == n0);
-        if (uniform) {
-            if (n0 < 0) continue;
-            u64 ex = enc_ordered(x), ey = enc_ordered(y);
-            u64 mnx = ex, mxx = ex, mny = ey, mxy = ey;
+// The per-particle phases below walk the arrays with a grid stride. Every item needs a chain of three or
+// four DEPENDENT gathers (pnode -> node record -> scan values), ~700 cycles each from L2: done one item at
+// a time that chain was the whole cost of a phase (ncu: 11.7 % issue-active, 2.7 ms for 22 levels at N = 1M).
+// Items are therefore processed in batches of kCoopBatch with the loads of a stage issued back to back.
+constexpr int kCoopBatch = 4;
+
+// Stretch of freshly created nodes: fold every object into the box of its (pending) node.
+// Objects of one node are contiguous, so a warp first reduces every RUN of equal node ids among its 32
+// consecutive objects (segmented min/max scan) and only the last lane of a run touches the node's box;
+// warps that lie entirely inside one node hand their result to warp 0 through shared memory, which reduces
+// runs of equal nodes once more. Without this the top levels funnel N/32 atomics into the same four words
+// and the deep levels issue four atomics per particle (the phase was 29 % of the build: 0.78 of 2.7 ms).
+struct BoxSlot { int node; u64 mnx, mny, mxx, mxy; };
+
+__device__ __forceinline__ void seg_minmax(int node, u64& mnx, u64& mny, u64& mxx, u64& mxy, int lane) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                u64 t;
-                t = __shfl_xor_sync(0xffffffffu, mnx, o); mnx = t < mnx ? t : mnx;
-                t = __shfl_xor_sync(0xffffffffu, mxx, o); mxx = t > mxx ? t : mxx;
-                t = __shfl_xor_sync(0xffffffffu, mny, o); mny = t < mny ? t : mny;
-                t = __shfl_xor_sync(0xffffffffu, mxy, o); mxy = t > mxy ? t : mxy;
-            }
-            if ((threadIdx.x & 31) == 0) {
-                u64* bb = T.bb + 4ll * n0;
-                atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny);
-                atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
-            }
-        } else if (node >= 0) {
-            u64* bb = T.bb + 4ll * node;
-            u64 ex = enc_ordered(x), ey = enc_ordered(y);
-            atomicMin(bb + 0, ex); atomicMin(bb + 1, ey);
-            atomicMax(bb + 2, ex); atomicMax(bb + 3, ey);
+    for (int o = 1; o < 32; o <<= 1) {
+        const int tn = __shfl_up_sync(0xffffffffu, node, o);
+        const u64 a = __shfl_up_sync(0xffffffffu, mnx, o), b = __shfl_up_sync(0xffffffffu, mny, o);
+        const u64 c = __shfl_up_sync(0xffffffffu, mxx, o), d = __shfl_up_sync(0xffffffffu, mxy, o);
+        if (lane >= o && tn == node) {   // runs are contiguous: equal ids o lanes apart lie in one run
+            mnx = a < mnx ? a : mnx; mny = b < mny ? b : mny;
+            mxx = c > mxx ? c : mxx; mxy = d > mxy ? d : mxy;
         }
     }
 }
+__device__ __forceinline__ void box_commit(const TreeDev& T, int node, u64 mnx, u64 mny, u64 mxx, u64 mxy) {
+    u64* bb = T.bb + 4ll * node;
+    atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny);
+    atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
+}
 
+__device__ __forceinline__ void coop_bbox(const TreeDev& T, const int* snode, const double* px, const double* py, int n,
+                                          const double* sx, const double* sy, const int* seg_perm, int nseg,
+                                          long long gtid, long long gsize, BoxSlot (*slots)[kCoopThreads / 32]) {
+    const long long total = (long long)n + nseg;
+    const long long rounds = (total + gsize - 1) / gsize;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long r0 = 0; r0 < rounds; r0 += kCoopBatch) {   // uniform trip count: barriers inside
+        int node[kCoopBatch];
+        double x[kCoopBatch], y[kCoopBatch];
+#pragma unroll
+        for (int k = 0; k < kCoopBatch; k++) {
+            const long long i = (r0 + k) * gsize + gtid;
+            node[k] = -1; x[k] = 0; y[k] = 0;
+            if (r0 + k < rounds) {
+                if (i < n) { node[k] = T.pnode[i]; x[k] = px[i]; y[k] = py[i]; }
+                else if (i < total) { const int q = (int)(i - n); node[k] = snode[q]; const int s = seg_perm[q]; x[k] = sx[s]; y[k] = sy[s]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kCoopBatch; k++)
+            if (node[k] >= 0 && T.status[node[k]] != ST_PENDING) node[k] = -1;
+#pragma unroll
+        for (int k = 0; k < kCoopBatch; k++) {
+            u64 mnx = enc_ordered(x[k]), mny = enc_ordered(y[k]), mxx = mnx, mxy = mny;
+            // segment positions [n, total) follow the particles: a warp that straddles n holds runs of both kinds
+            seg_minmax(node[k], mnx, mny, mxx, mxy, lane);
+            const int nxt = __shfl_down_sync(0xffffffffu, node[k], 1);
+            const bool runend = (lane == 31) || (nxt != node[k]);
+            const int n0 = __shfl_sync(0xffffffffu, node[k], 0);
+            const bool uniform = __all_sync(0xffffffffu, node[k] == n0);
+            if (uniform) {
+                if (lane == 31) { BoxSlot& sl = slots[k][warp]; sl.node = n0; sl.mnx = mnx; sl.mny = mny; sl.mxx = mxx; sl.mxy = mxy; }
+            } else {
+                if (lane == 31) slots[k][warp].node = -1;
+                if (runend && node[k] >= 0) box_commit(T, node[k], mnx, mny, mxx, mxy);
+            }
+        }
+        __syncthreads();
+        if (warp < kCoopBatch) {   // warp k folds the uniform warps' results of batch item k
+            const BoxSlot sl = slots[warp][lane];
+            int nd = sl.node;
+            u64 mnx = sl.mnx, mny = sl.mny, mxx = sl.mxx, mxy = sl.mxy;
+            seg_minmax(nd, mnx, mny, mxx, mxy, lane);
+            const int nxt = __shfl_down_sync(0xffffffffu, nd, 1);
+            if (((lane == 31) || (nxt != nd)) && nd >= 0) box_commit(T, nd, mnx, mny, mxx, mxy);
+        }
+        __syncthreads();
+    }
+}
+
+#ifdef VV_TREE_TIMING
+#define VV_TT(k) do { if (gtid == 0) { long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); tt_[k] += now_ - tlast_; tlast_ = now_; } } while (0)
+#else
+#define VV_TT(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A) {
+#ifdef VV_TREE_TIMING
+    long long tt_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast_));
+#endif
     cg::grid_group grid = cg::this_grid();
     __shared__ u32 sh[kCoopThreads / 32 + 1];
+    __shared__ BoxSlot slots[kCoopBatch][kCoopThreads / 32];
     TreeDev T = A.T;
     const int n = A.n, nseg = A.nseg;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,9 +206,9 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
     }
     for (long long i = gtid; i < n; i += gsize) { T.pnode[i] = 0; A.perm[i] = (int)i; }
     for (long long k = gtid; k < nseg; k += gsize) { A.snode[0][k] = 0; A.segperm[0][k] = (int)k; }
-    grid.sync();
-    coop_bbox(T, A.snode[0], A.px, A.py, n, A.sx, A.sy, A.segperm[0], nseg, gtid, gsize);
-    grid.sync();
+    grid.sync(); VV_TT(8);
+    coop_bbox(T, A.snode[0], A.px, A.py, n, A.sx, A.sy, A.segperm[0], nseg, gtid, gsize, slots);
+    grid.sync(); VV_TT(8);
 
     int a0 = 0, a1 = 1, d = 0;
     bool failed = false;
@@ -185,13 +237,13 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
             T.axis[nn] = (h < w) ? 1 : 0;  // :87
             A.splitflag[k] = leaf ? 0u : 1u;
         }
-        grid.sync();
+        grid.sync(); VV_TT(0);
         // ---- P2: tile sums of the three flag arrays
         const int* segin = A.segperm[segcur];
         coop_tile_sums(FlagArray{A.splitflag}, na, A.partN, sh);
         coop_tile_sums(PartFlag{T, A.px, A.py}, n, A.partP, sh);
         if (nseg) coop_tile_sums(SegFlag{T, A.sx, A.sy, segin}, nseg, A.partS, sh);
-        grid.sync();
+        grid.sync(); VV_TT(1);
         // ---- P3: scans. Every CTA derives the same split count, so the exit is grid-uniform.
         const u32 nsplit = coop_prefix(A.partN, ((long long)na + kCoopTile - 1) / kCoopTile, sh);
         if (nsplit == 0) break;
@@ -220,23 +272,46 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
             if (k == nseg - 1) A.Gs[nseg] = inc;
         });
         // leaves of this level keep ch1 = -1 (written above only for tiles that exist: na >= 1)
-        grid.sync();
+        grid.sync(); VV_TT(2);
         // ---- P4: partner table of the Hoare partition + child ranges; stable split of the segments
-        for (long long p = gtid; p < n; p += gsize) {
-            const int node = T.pnode[p];
-            if (T.status[node] != ST_SPLIT) continue;
-            const int f = T.first[node], l = T.last[node];
-            const u32 Gf = A.G[f];
-            const int m = (int)(A.G[l] - Gf);
-            const int rel = (int)p - f;
-            const int le = (int)(A.G[p] - Gf);
-            const bool isless = A.G[p + 1] != A.G[p];
-            if (p == f) {
-                const int c = T.ch1[node];
-                T.first[c] = f; T.last[c] = f + m;
-                T.first[c + 1] = f + m; T.last[c + 1] = l;
+        for (long long p0 = gtid; p0 < n; p0 += (long long)kCoopBatch * gsize) {
+            int node[kCoopBatch], f[kCoopBatch], l[kCoopBatch];
+            u32 Gp[kCoopBatch], Gp1[kCoopBatch], Gf[kCoopBatch], Gl[kCoopBatch];
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                const long long p = p0 + (long long)k * gsize;
+                node[k] = (p < n) ? T.pnode[p] : -1;
+                Gp[k] = 0; Gp1[k] = 0;
+                if (p < n) { Gp[k] = A.G[p]; Gp1[k] = A.G[p + 1]; }
             }
-            if (rel >= m && isless) A.tmpR[f + (m - le - 1)] = (int)p;
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++)
+                if (node[k] >= 0 && T.status[node[k]] != ST_SPLIT) node[k] = -1;
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                f[k] = 0; l[k] = 0;
+                if (node[k] >= 0) { f[k] = T.first[node[k]]; l[k] = T.last[node[k]]; }
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                Gf[k] = 0; Gl[k] = 0;
+                if (node[k] >= 0) { Gf[k] = A.G[f[k]]; Gl[k] = A.G[l[k]]; }
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                if (node[k] < 0) continue;
+                const long long p = p0 + (long long)k * gsize;
+                const int m = (int)(Gl[k] - Gf[k]);
+                const int rel = (int)p - f[k];
+                const int le = (int)(Gp[k] - Gf[k]);
+                const bool isless = Gp1[k] != Gp[k];
+                if (p == f[k]) {
+                    const int c = T.ch1[node[k]];
+                    T.first[c] = f[k]; T.last[c] = f[k] + m;
+                    T.first[c + 1] = f[k] + m; T.last[c + 1] = l[k];
+                }
+                if (rel >= m && isless) A.tmpR[f[k] + (m - le - 1)] = (int)p;
+            }
         }
         if (nseg) {
             int* pout = A.segperm[segcur ^ 1];
@@ -259,41 +334,74 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
                 nout[dst] = isless ? c : c + 1;
             }
         }
-        grid.sync();
+        grid.sync(); VV_TT(3);
         // ---- P5: in-place swaps (each pair is touched by exactly one thread) and the new node ids
-        for (long long p = gtid; p < n; p += gsize) {
-            const int node = T.pnode[p];
-            if (T.status[node] != ST_SPLIT) continue;
-            const int f = T.first[node], l = T.last[node];
-            const u32 Gf = A.G[f];
-            const int m = (int)(A.G[l] - Gf);
-            const int rel = (int)p - f;
-            const int le = (int)(A.G[p] - Gf);
-            const bool isless = A.G[p + 1] != A.G[p];
-            if (rel < m && !isless) {
-                const int q = A.tmpR[f + (rel - le)];
-                double t;
-                t = A.px[p]; A.px[p] = A.px[q]; A.px[q] = t;
-                t = A.py[p]; A.py[p] = A.py[q]; A.py[q] = t;
-                t = A.pg[p]; A.pg[p] = A.pg[q]; A.pg[q] = t;
-                int ti = A.perm[p]; A.perm[p] = A.perm[q]; A.perm[q] = ti;
+        for (long long p0 = gtid; p0 < n; p0 += (long long)kCoopBatch * gsize) {
+            int node[kCoopBatch], f[kCoopBatch], l[kCoopBatch], c1[kCoopBatch], q[kCoopBatch];
+            u32 Gp[kCoopBatch], Gp1[kCoopBatch], Gf[kCoopBatch], Gl[kCoopBatch];
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                const long long p = p0 + (long long)k * gsize;
+                node[k] = (p < n) ? T.pnode[p] : -1;
+                Gp[k] = 0; Gp1[k] = 0;
+                if (p < n) { Gp[k] = A.G[p]; Gp1[k] = A.G[p + 1]; }
             }
-            T.pnode[p] = T.ch1[node] + (rel >= m ? 1 : 0);
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++)
+                if (node[k] >= 0 && T.status[node[k]] != ST_SPLIT) node[k] = -1;
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                f[k] = 0; l[k] = 0; c1[k] = 0;
+                if (node[k] >= 0) { f[k] = T.first[node[k]]; l[k] = T.last[node[k]]; c1[k] = T.ch1[node[k]]; }
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                Gf[k] = 0; Gl[k] = 0;
+                if (node[k] >= 0) { Gf[k] = A.G[f[k]]; Gl[k] = A.G[l[k]]; }
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {   // partner of every not-less element of the left part
+                q[k] = -1;
+                if (node[k] < 0) continue;
+                const long long p = p0 + (long long)k * gsize;
+                const int m = (int)(Gl[k] - Gf[k]);
+                const int rel = (int)p - f[k];
+                const int le = (int)(Gp[k] - Gf[k]);
+                const bool isless = Gp1[k] != Gp[k];
+                if (rel < m && !isless) q[k] = A.tmpR[f[k] + (rel - le)];
+                T.pnode[p] = c1[k] + (rel >= m ? 1 : 0);
+            }
+            double ax[kCoopBatch], ay[kCoopBatch], ag[kCoopBatch], bx[kCoopBatch], by[kCoopBatch], bg[kCoopBatch];
+            int ai[kCoopBatch], bi[kCoopBatch];
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                if (q[k] < 0) continue;
+                const long long p = p0 + (long long)k * gsize;
+                ax[k] = A.px[p]; ay[k] = A.py[p]; ag[k] = A.pg[p]; ai[k] = A.perm[p];
+                bx[k] = A.px[q[k]]; by[k] = A.py[q[k]]; bg[k] = A.pg[q[k]]; bi[k] = A.perm[q[k]];
+            }
+#pragma unroll
+            for (int k = 0; k < kCoopBatch; k++) {
+                if (q[k] < 0) continue;
+                const long long p = p0 + (long long)k * gsize;
+                A.px[p] = bx[k]; A.py[p] = by[k]; A.pg[p] = bg[k]; A.perm[p] = bi[k];
+                A.px[q[k]] = ax[k]; A.py[q[k]] = ay[k]; A.pg[q[k]] = ag[k]; A.perm[q[k]] = ai[k];
+            }
         }
         if (nseg) { segcur ^= 1; T.snode = A.snode[segcur]; }
-        grid.sync();
+        grid.sync(); VV_TT(4);
         // ---- P6: Stretch of the children
-        coop_bbox(T, A.snode[segcur], A.px, A.py, n, A.sx, A.sy, A.segperm[segcur], nseg, gtid, gsize);
+        coop_bbox(T, A.snode[segcur], A.px, A.py, n, A.sx, A.sy, A.segperm[segcur], nseg, gtid, gsize, slots);
         a0 = a1; a1 += 2 * (int)nsplit;
         if (gtid == 0) A.st->lvl[d + 2] = a1;
-        grid.sync();
+        grid.sync(); VV_TT(5);
     }
     if (failed) {
         if (gtid == 0) A.st->err = 1;
         return;
     }
     const int depth = d;
-    grid.sync();   // lvl[] complete and visible
+    grid.sync(); VV_TT(8);   // lvl[] complete and visible
     // ---- bottom-up: subtree sizes, +/- centres of mass (CalculateCMass, :150-197)
     for (int dd = depth; dd >= 0; dd--) {
         const int b0 = A.st->lvl[dd], b1 = A.st->lvl[dd + 1];
@@ -330,7 +438,7 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
                 } else { cm[0] = T.x[nn]; cm[1] = T.y[nn]; cm[2] = 0; }
             }
         }
-        grid.sync();
+        grid.sync(); VV_TT(6);
     }
     // ---- top-down: DFS leaf index and pre-order id
     for (int dd = 0; dd <= depth; dd++) {
@@ -345,9 +453,13 @@ __global__ void __launch_bounds__(kCoopThreads, 1) k_tree_build_coop(CoopArgs A)
             T.pre[c] = T.pre[nn] + 1;
             T.pre[c + 1] = T.pre[nn] + 1 + T.nn[c];
         }
-        grid.sync();
+        grid.sync(); VV_TT(7);
     }
     if (gtid == 0) { A.st->nnodes = a1; A.st->depth = depth; A.st->nleaves = T.nl[0]; }
+#ifdef VV_TREE_TIMING
+    if (gtid == 0) printf("tree timing us: P1 %.0f P2 %.0f P3 %.0f P4 %.0f P5 %.0f P6 %.0f up %.0f down %.0f other %.0f (depth %d)\n",
+                          tt_[0] * 1e-3, tt_[1] * 1e-3, tt_[2] * 1e-3, tt_[3] * 1e-3, tt_[4] * 1e-3, tt_[5] * 1e-3, tt_[6] * 1e-3, tt_[7] * 1e-3, tt_[8] * 1e-3, depth);
+#endif
 }
 
 }  // namespace vv

@@ -3,7 +3,7 @@
 (tree build -> epsilon/merge -> convective Biot-Savart -> diffusive -> move/clean,
 utils/vvflow/vvflow.cpp:246-257) on BASELINE config 2: a synthetic Lamb-Oseen vortex cloud, N = 1M.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles N]
 
 Under torchrun (N > 1) one rank per GPU: targets are sharded, sources replicated by all-gathers.
 Prints ONE JSON line on rank 0. `value` = steps/s with the particle state resident in HBM;
@@ -88,6 +88,16 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------ reference arm
+def _omp_threads(n):
+    """thread count of the OpenMP runtime the reference build is linked against"""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 def reference_arm(args):
     """The reference's own CPU implementation (oracle/_ref: libvvhd sources compiled unmodified; else
     the C restatement) on this box's host cores. One step = tree build on the full cloud + epsilon,
@@ -98,10 +108,26 @@ def reference_arm(args):
     n = args.n
     rec = lamb_oseen_cloud(n)
     from oracle import pyref
-    cores = 1  # README.md:70 / pytest/conftest.py:24: OMP_NUM_THREADS=1 is the reference's own setting
-    os.environ["OMP_NUM_THREADS"] = str(cores)
     kind = "reference" if pyref.available() else "port"
     stride = max(1, args.ref_stride)
+    # Threads: the reference recommends OMP_NUM_THREADS=1 (README.md:70, pytest/conftest.py:24) because its
+    # OpenMP loops over leaves do not scale. Both settings are tried on a coarser sample and
+    # the faster one is used for the measured steps, so the arm runs with all the threads it can USE.
+    cores, calib = 1, {}
+    if kind == "reference":
+        ncpu = os.cpu_count() or 1
+        for th in sorted({1, ncpu}):
+            _omp_threads(th)
+            r = pyref.Ref(re=RE, dt=DT, inf_vx=INF_VX, inf_vy=INF_VY)
+            r.set_list(rec[:, :3])
+            r.tree_params(FAR, 0.0, DBL_MAX)
+            t0 = time.perf_counter(); r.tree_build(); tb = time.perf_counter() - t0
+            r.sample_leaves(stride * 8, 0)
+            t0 = time.perf_counter(); r.epsilon(True); r.convective(); r.diffusive(); tl = time.perf_counter() - t0
+            r.tree_destroy(); r.close()
+            calib[str(th)] = tb + 8 * stride * tl
+        cores = int(min(calib, key=calib.get))
+        _omp_threads(cores)
     times = []
     pairs_rate = []
     for it in range(args.warmup + args.steps):
@@ -145,7 +171,9 @@ def reference_arm(args):
         "interactions_per_s": float(np.mean(pairs_rate)),
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": kind,
                          "sample": f"full tree build + every {stride}-th leaf for epsilon/convective/diffusive, "
-                                   f"times x{stride}; OMP_NUM_THREADS=1 as the reference recommends"},
+                                   f"times x{stride}; OpenMP threads = the faster of 1 (the reference's recommended "
+                                   f"setting) and all {os.cpu_count()} host cores on a x8 coarser sample",
+                         "thread_calibration_s_per_step": calib},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -317,15 +345,20 @@ def ours(args):
             "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "steps/s", "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * int(nout)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "k_near<ConvOp> (K4 convective near field)",
+            "roofline": {"bound": "fp64", "kernel": "k_conv (K4 convective near field)",
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None,
-                         # ncu dram__bytes_read+write of this kernel at N=1M (profiles/r1_ncu_near_leafwarp.txt)
-                         "traffic": 9.3e7 if n == 1_000_000 and world == 1 else None,
+                         # ncu dram__bytes_read + dram__bytes_write of this kernel at N=1M, per launch
+                         # (profiles/r1_ncu_kernels_v5.txt: 83.4 MB + 19.6 MB)
+                         "traffic": 1.03e8 if n == 1_000_000 and world == 1 else None,
+                         "ncu_fp64_pipe_pct": 57.5 if n == 1_000_000 and world == 1 else None,
                          "note": "FP64-pipe bound (no tensor cores: N-body gather). achieved = 11 flop x near pairs / "
                                  "CUDA-event time of the phase on the library's stream; peak = DFMA micro-benchmark "
                                  "measured in this run (MEASURED_PEAKS.json holds HBM %s GB/s and bf16 only). "
-                                 "HBM traffic of the kernel is ~0.09 GB vs 39.7 GFLOP: compute-bound." % peaks.get("hbm_gbs")},
+                                 "HBM traffic of the kernel is ~0.10 GB vs 39.7 GFLOP: compute-bound. ncu_fp64_pipe_pct = "
+                                 "sm__inst_executed_pipe_fp64 of the committed ncu capture (not measured in this run): the "
+                                 "pipe is busier than frac says because a pair costs 9 FP64 instructions, of which only "
+                                 "7 are FMAs, for the 11 flop the metric counts." % peaks.get("hbm_gbs")},
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "checksum_sum_g": checksum,
@@ -342,7 +375,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--particles", dest="n", type=int, default=1_000_000,
+                    help="N of the synthetic cloud (not `--n`: torchrun would read that as one of its own options)")
     ap.add_argument("--ref-stride", type=int, default=64, help="CPU arms: every stride-th leaf is evaluated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

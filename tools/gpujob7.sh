@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 --n 4000000 > gpurun_out/bench_2gpu_4M.json 2> gpurun_out/bench_2gpu_4M.err
-timeout 600 python bench.py --steps 5 --warmup 3 --n 4000000 --no-cpu-baseline > gpurun_out/bench_1gpu_4M.json 2> gpurun_out/bench_1gpu_4M.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 --particles 4000000 > gpurun_out/bench_2gpu_4M.json 2> gpurun_out/bench_2gpu_4M.err
+timeout 600 python bench.py --steps 5 --warmup 3 --particles 4000000 --no-cpu-baseline > gpurun_out/bench_1gpu_4M.json 2> gpurun_out/bench_1gpu_4M.err
 for f in bench_1gpu bench_2gpu bench_1gpu_4M bench_2gpu_4M; do echo == $f; python - <<PY
 import json
 try:

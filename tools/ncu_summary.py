@@ -20,10 +20,10 @@ for r in rows[2:]:
             i = hdr.index(w); print('   ', w, r[i], units[i])
     st = []
     for i, h in enumerate(hdr):
-        if 'issue_stalled' in h and h.endswith('per_warp_active.pct') and 'not_issued' not in h:
+        if h.startswith('smsp__pcsamp_warps_issue_stalled_') and not h.endswith('_not_issued'):
             try:
-                v = float(r[i])
-                if v > 2: st.append((v, h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_warp_active.pct', '')))
+                st.append((float(r[i]), h.replace('smsp__pcsamp_warps_issue_stalled_', '')))
             except ValueError:
                 pass
-    print('    stalls (% of warp-active):', ', '.join(f'{n} {v:.0f}' for v, n in sorted(st, reverse=True)))
+    tot = sum(v for v, _ in st) or 1.0
+    print('    warp-state samples (% of all):', ', '.join(f'{n} {v / tot * 100:.1f}' for v, n in sorted(st, reverse=True)[:9]))

@@ -8,17 +8,17 @@
 // are broadcast from shared memory and 2 x 15 accumulators stay in registers, so every lane does useful
 // FP64 work on every pair and only one cross-lane reduction per leaf is needed.
 //
-// What the ncu source view of the previous version showed (profiles/r1_ncu_near_leafwarp_conv.txt) and
-// what this version does about it:
+// What the ncu source view of the previous version (k_near<ConvOp>) showed and what this kernel does about it
+// (profiles/README.md):
 //   * 14 % of the executed instructions were per-iteration bookkeeping (moving the prefetched records
 //     into place, re-creating the dummy record, per-lane bounds predicates)  ->  the loop is unrolled
 //     twice over ping-pong registers (no moves) and the index list is padded with the index of a dummy
 //     record (g = 0) up to a whole iteration, so the loop carries no per-lane predicates;
-//   * the FP64 chains stalled on the MUFU result with only 3 warps per scheduler  ->  leaves with more
-//     than 10 live targets (three target groups) stream ONE source per lane and iteration, leaves with
-//     fewer stream TWO: tools/microbench4.cu measured 1.42 and 1.50 T pairs/s for these two shapes at
-//     3 CTAs per SM, against 1.25 T for two sources with three groups (register pressure throttles
-//     ptxas' interleaving of independent pairs).
+//   * the unrolled loop must stay small: a build with two loop variants (41 KB of hot code) ran 2 x slower
+//     with stall_no_instruction at 55 % of all samples  ->  targets are laid out partial-group-first
+//     (CvGroups below), which needs one code body per size only for the partial group (18 KB).
+// tools/microbench4.cu bounds this loop shape (two sources per lane, 30 accumulators, 3 CTAs per SM) at
+// 1.33 T pairs/s with three target groups and 1.50 T with two; the kernel reaches 1.06-1.14 T in the step.
 #pragma once
 #include "vvgpu_near.cuh"
 

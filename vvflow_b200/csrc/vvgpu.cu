@@ -340,8 +340,8 @@ int lists_impl(vvgpu_ctx* c, bool all) {
         TravOut O{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase, scount, derr};
         TravItems I0{nullptr, nullptr, nullptr, item_cap, cut};
         if (g1 > g0) {
-            k_traverse<0><<<cdiv(g1 - g0, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
-                T, L, nl, g0, g1, c->farc, O, taylor, farcount, nullptr, nullptr, 0, hvlist, derr + 1, I0); CKLAUNCH();
+            k_traverse_cta<0><<<g1 - g0, kTcWarps * 32, 0, st>>>(T, L, nl, g0, g1, c->farc, O, taylor, farcount, hvlist, derr + 1,
+                                                                  nullptr, nullptr, 0, I0); CKLAUNCH();
         }
         CK(cudaMemcpyAsync(c->h_pinned + 64, derr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -364,9 +364,9 @@ int lists_impl(vvgpu_ctx* c, bool all) {
             TravItems I{inode, imask, icount, item_cap, cut};
             k_traverse<1><<<cdiv(nheavy, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
                 T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
-            k_traverse<2><<<cdiv((long long)nheavy * item_cap, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
-                T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
-            k_heavy_taylor<<<nheavy, 32, 0, st>>>(hvlist, nheavy, nl, tpart, icount, item_cap, taylor, farcount); CKLAUNCH();
+            k_traverse_cta<2><<<nheavy * item_cap, kTcWarps * 32, 0, st>>>(T, L, nl, 0, 0, c->farc, OH, taylor, farcount, nullptr, nullptr,
+                                                                          tpart, hvlist, nheavy, I); CKLAUNCH();
+            k_heavy_taylor<<<nheavy, 256, 0, st>>>(hvlist, nheavy, nl, tpart, icount, item_cap, taylor, farcount); CKLAUNCH();
             {
                 int* hoff = c->hv_off.get<int>(2 * (size_t)nheavy_slots + 2, &ok);
                 NEED(ok);

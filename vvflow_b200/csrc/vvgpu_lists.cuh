@@ -282,19 +282,221 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravO
     }
 }
 
+// The regular walk, one CTA per group. A single warp's walk is ~150 dependent iterations (up to the budget of
+// 256), so a kernel of one-warp walks ends with its LONGEST walk: 1.7 ms at N = 1M for 0.6 ms of FP64 work, and
+// no faster when the groups are sharded over GPUs. Here kTcWarps warps pop up to 32 * kTcWarps frontier nodes per
+// iteration from one shared stack and advance in lock-step; offsets of the pushed children and of the emitted
+// list entries come from a cross-warp prefix of the per-warp counts, so the result is deterministic. Every
+// warp keeps Taylor partials for the 32 leaves (lane = leaf); they are summed in warp order at the end.
+#ifndef VV_TC_WARPS
+#define VV_TC_WARPS 4
+#endif
+constexpr int kTcWarps = VV_TC_WARPS;
+constexpr int kTcStack = 2048;
+constexpr int kTcBudgetNodes = kTravBudget * 32;   // the same bound on visited nodes as the one-warp walk
+
+// MODE 0: a group from the root (budgeted; gives up -> heavy). MODE 2: one item of a heavy group (k_traverse<1>
+// made the items), blockIdx.x = heavy index * item_cap + item.
+template <int MODE>
+__global__ void __launch_bounds__(kTcWarps * 32)
+k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravOut O, double* taylor, double* farcount,
+               int* heavy_out, int* nheavy_out, double* tpart, const int* heavy_list, int nheavy, TravItems I) {
+    __shared__ int2 stack[kTcStack];
+    __shared__ double lcx[32], lcy[32], lh[32], lw[32];
+    __shared__ double cmw[kTcWarps][32 * 6];
+    __shared__ double tsum[kTcWarps][32][5];
+    __shared__ int wpush[kTcWarps], wemit[kTcWarps];
+    __shared__ long long s_nbase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int g, slot0, nslots;
+    int start_node = 0;
+    u32 start_mask = 0;
+    long long walk = 0;
+    if (MODE == 0) {
+        g = g0 + blockIdx.x;
+        if (g >= g1) return;
+        slot0 = g * kGroupSlots; nslots = kGroupSlots;
+    } else {
+        const int hidx = blockIdx.x / I.item_cap;
+        const int it = blockIdx.x - hidx * I.item_cap;
+        if (hidx >= nheavy || it >= I.count[hidx]) return;
+        g = heavy_list[hidx];
+        start_node = I.node[(long long)hidx * I.item_cap + it];
+        start_mask = I.mask[(long long)hidx * I.item_cap + it];
+        walk = (long long)hidx * (I.item_cap + 1) + it + 1;
+        slot0 = (int)(walk * kItemSlots); nslots = kItemSlots;   // (offset by the regular slots, added by the caller in O)
+    }
+    const int l0 = g * kGroupLeaves;
+    const int nl = min(kGroupLeaves, nleaves - l0);
+    if (warp == 0) {
+        if (lane < nl) { lcx[lane] = L.cx[l0 + lane]; lcy[lane] = L.cy[l0 + lane]; lh[lane] = L.h[l0 + lane]; lw[lane] = L.w[l0 + lane]; }
+        else { lcx[lane] = 0; lcy[lane] = 0; lh[lane] = 0; lw[lane] = 0; }
+    }
+    const u32 full = (nl == 32) ? 0xffffffffu : ((1u << nl) - 1u);
+    if (tid == 0) stack[0] = (MODE == 2) ? make_int2(start_node, (int)start_mask) : make_int2(0, (int)full);
+    __syncthreads();
+    const double mycx = lcx[lane], mycy = lcy[lane];
+    double* cm = cmw[warp];
+    int size = 1;
+    double T1 = 0, T2 = 0, T3 = 0, T4 = 0, nfar = 0;
+    int nchunk = 0, fill = kUnitEntries;   // uniform across the CTA; "full": the first emission claims a chunk
+    long long cbase = 0;
+    int visited = 0;
+    bool bail = false;
+    while (size > 0) {
+        if (MODE == 0 && visited > kTcBudgetNodes) { bail = true; break; }
+        // near the capacity fall back to plain depth-first order (growth <= 1 per pop)
+        const int take = (size > kTcStack - 2 * 32 * kTcWarps - 8) ? 1 : min(size, 32 * kTcWarps);
+        visited += take;
+        const int k = warp * 32 + lane;
+        int n = -1;
+        u32 em = 0;
+        if (k < take) { const int2 e = stack[size - 1 - k]; n = e.x; em = (u32)e.y; }
+        const int base = size - take;
+        __syncthreads();   // every pop is read before a push may overwrite it
+        u32 farm = 0, nearm = 0;
+        int c1 = -1;
+        if (n >= 0) {
+            const double nx = T.x[n], ny = T.y[n];
+            const double nhw = VV_ADD(T.h[n], T.w[n]);
+            c1 = T.ch1[n];
+            for (u32 mm = em; mm; mm &= mm - 1) {  // only the leaves that still see this subtree
+                const int l = __ffs(mm) - 1;
+                if (is_far(nx, ny, nhw, lcx[l], lcy[l], lh[l], lw[l], farc)) farm |= (1u << l);
+            }
+            nearm = em & ~farm;
+            if (farm) {
+                cm[lane * 6 + 0] = T.cmp[3ll * n + 0]; cm[lane * 6 + 1] = T.cmp[3ll * n + 1];
+                cm[lane * 6 + 2] = T.cmp[3ll * n + 2]; cm[lane * 6 + 3] = T.cmm[3ll * n + 0];
+                cm[lane * 6 + 4] = T.cmm[3ll * n + 1]; cm[lane * 6 + 5] = T.cmm[3ll * n + 2];
+            }
+        }
+        const bool push = (n >= 0) && nearm && (c1 >= 0);
+        const bool emit = (n >= 0) && nearm && (c1 < 0);
+        const u32 pb = __ballot_sync(0xffffffffu, push);
+        const u32 eb = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) { wpush[warp] = 2 * __popc(pb); wemit[warp] = __popc(eb); }
+        __syncthreads();
+        int pbefore = 0, ptotal = 0, ebefore = 0, etotal = 0;
+#pragma unroll
+        for (int w = 0; w < kTcWarps; w++) {
+            const int a = wpush[w], b = wemit[w];
+            if (w < warp) { pbefore += a; ebefore += b; }
+            ptotal += a; etotal += b;
+        }
+        if (base + ptotal > kTcStack) {
+            if (tid == 0) atomicOr(O.err, 2);
+            return;
+        }
+        // descend: both children inherit the still-near leaves (child 1 ends up on top)
+        if (push) {
+            const int off = base + pbefore + 2 * __popc(pb & lanemask_lt());
+            stack[off] = make_int2(c1 + 1, (int)nearm);
+            stack[off + 1] = make_int2(c1, (int)nearm);
+        }
+        size = base + ptotal;
+        // near leaves: one list entry each for the group
+        if (etotal) {
+            const int pos = fill + ebefore + __popc(eb & lanemask_lt());
+            long long nbase = cbase;
+            const bool cross = fill + etotal > kUnitEntries;   // (part of) this batch goes to a fresh chunk
+            if (cross) {
+                if (nchunk >= nslots) {
+                    if (MODE == 0) { bail = true; break; }
+                    if (tid == 0) atomicOr(O.err, 4);
+                    return;
+                }
+                if (tid == 0) {
+                    const unsigned long long nb = atomicAdd(O.cursor, (unsigned long long)kUnitEntries);
+                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = kUnitEntries;
+                    O.slot_base[slot0 + nchunk] = (long long)nb;
+                    s_nbase = (long long)nb;
+                }
+                __syncthreads();
+                nbase = s_nbase;
+                if (nbase + kUnitEntries > O.pool_cap) {
+                    if (tid == 0) atomicOr(O.err, 1);
+                    return;
+                }
+                nchunk++;
+            }
+            if (emit) {
+                const long long at = (pos < kUnitEntries) ? (cbase + pos) : (nbase + (pos - kUnitEntries));
+                O.G.leaf[at] = T.lstart[n];
+                O.G.mask[at] = nearm;
+            }
+            if (cross) { fill = fill + etotal - kUnitEntries; cbase = nbase; }
+            else fill += etotal;
+        }
+        // far nodes of this warp: transpose (node lane x leaf bit) -> (leaf lane x node bit) and accumulate
+        const u32 anyfar = __ballot_sync(0xffffffffu, farm != 0);
+        if (anyfar) {
+            __syncwarp();
+            u32 mine = 0;
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const u32 tm = __ballot_sync(0xffffffffu, (farm >> l) & 1u);
+                if (lane == l) mine = tm;
+            }
+            nfar += (double)__popc(mine);
+            while (mine) {
+                const int j = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const double* c = cm + j * 6;
+                taylor_add(mycx, mycy, c[0], c[1], c[2], T1, T2, T3, T4);
+                taylor_add(mycx, mycy, c[3], c[4], c[5], T1, T2, T3, T4);
+            }
+        }
+        __syncthreads();   // pushes visible, counters and s_nbase reusable
+    }
+    if (bail) {
+        // a fringe group that sees most of the tree: its chunks are dropped (count 0) and the group is redone
+        // as a heavy one (per-subtree items)
+        if (tid == 0) {
+            heavy_out[atomicAdd(nheavy_out, 1)] = g;
+            for (int q = 0; q < min(nchunk, nslots); q++) O.slot_count[slot0 + q] = 0;
+        }
+        return;
+    }
+    if (tid == 0 && nchunk > 0) O.slot_count[slot0 + nchunk - 1] = fill;
+    tsum[warp][lane][0] = T1; tsum[warp][lane][1] = T2; tsum[warp][lane][2] = T3; tsum[warp][lane][3] = T4; tsum[warp][lane][4] = nfar;
+    __syncthreads();
+    if (warp == 0) {
+        double s5[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < kTcWarps; w++)
+            for (int q = 0; q < 5; q++) s5[q] += tsum[w][lane][q];
+        if (MODE == 0) {
+            if (lane < nl) {
+                double* t = taylor + 4ll * (l0 + lane);
+                t[0] = s5[0] * k1_2Pi; t[1] = s5[1] * k1_2Pi; t[2] = s5[2] * k1_Pi; t[3] = s5[3] * k1_2Pi;  // :66-69
+                if (farcount) farcount[l0 + lane] = s5[4];
+            }
+        } else {
+            double* t = tpart + (walk * 32 + lane) * 5;
+            for (int q = 0; q < 5; q++) t[q] = s5[q];
+        }
+    }
+}
+
 // Taylor coefficients of the leaves of heavy groups: partials of the top walk and of the items, in order
-__global__ void k_heavy_taylor(const int* heavy_list, int nheavy, int nleaves, const double* tpart, const int* item_count,
-                               int item_cap, double* taylor, double* farcount) {
-    const int hidx = blockIdx.x, lane = threadIdx.x;
-    if (hidx >= nheavy || lane >= 32) return;
+__global__ void __launch_bounds__(256) k_heavy_taylor(const int* heavy_list, int nheavy, int nleaves, const double* tpart,
+                                                      const int* item_count, int item_cap, double* taylor, double* farcount) {
+    __shared__ double part[8][32][5];
+    const int hidx = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (hidx >= nheavy) return;
     const int l = heavy_list[hidx] * kGroupLeaves + lane;
-    if (l >= nleaves) return;
     double s[5] = {0, 0, 0, 0, 0};
     const int nw = item_count[hidx] + 1;
-    for (int q = 0; q < nw; q++) {
+    for (int q = warp; q < nw; q += 8) {   // fixed assignment of walks to warps: deterministic
         const double* t = tpart + (((long long)hidx * (item_cap + 1) + q) * 32 + lane) * 5;
         for (int k = 0; k < 5; k++) s[k] += t[k];
     }
+    for (int k = 0; k < 5; k++) part[warp][lane][k] = s[k];
+    __syncthreads();
+    if (warp != 0 || l >= nleaves) return;
+    for (int k = 0; k < 5; k++) s[k] = 0;
+    for (int w = 0; w < 8; w++)
+        for (int k = 0; k < 5; k++) s[k] += part[w][lane][k];
     double* t = taylor + 4ll * l;
     t[0] = s[0] * k1_2Pi; t[1] = s[1] * k1_2Pi; t[2] = s[2] * k1_Pi; t[3] = s[3] * k1_2Pi;
     if (farcount) farcount[l] = s[4];

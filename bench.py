@@ -282,10 +282,19 @@ def ours(args):
 
     # interaction counts of the final state's tree (work done per step)
     ctx.tree_build(FAR, 0.0, DBL_MAX)
-    near_pairs, far_nodes = ctx.count_interactions()
+    local_pairs, local_far = ctx.count_interactions()   # of this rank's slice of the leaf groups
     nn, nl, depth = ctx.tree_counts()
     ctx.tree_destroy()
     ctx.phase_times()
+    near_pairs, far_nodes = local_pairs, local_far
+    conv_ms_max = phase_sum["conv"] / args.steps
+    if world > 1:
+        t = torch.tensor([local_pairs, local_far], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        near_pairs, far_nodes = float(t[0].item()), float(t[1].item())
+        t = torch.tensor([conv_ms_max], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        conv_ms_max = float(t[0].item())
 
     # ---- e2e: host records in, host records out, every step
     for _ in range(min(args.warmup, 2)):
@@ -313,12 +322,8 @@ def ours(args):
     # ---- roofline of the dominant kernel family: K4 convective, FP64 pipe
     fp64_peak = ctx.fp64_peak()
     conv_ms = phase_sum["conv"] / args.steps
-    # this rank's share of the pairs (targets are sharded); rank 0 reports its own kernel
-    share = 1.0
-    if world > 1:
-        f, l = ctx_range = stepper.bounds[rank]
-        share = float(l - f) / max(n, 1)
-    flops = 11.0 * near_pairs * share
+    # targets are sharded: rank 0 reports its own kernel on its own pairs
+    flops = 11.0 * local_pairs
     achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
     if rank == 0:
@@ -339,7 +344,7 @@ def ours(args):
                        "near_pairs_per_step": near_pairs, "far_nodes_per_step": far_nodes,
                        "parallelism": f"target-sharded x{world}, sources replicated by all-gather" if world > 1 else "1 GPU",
                        "l2": "256 MB memset between steps (inside the timed region) flushes the 126 MB L2"},
-            "interactions_per_s": near_pairs * share / (conv_ms * 1e-3) if conv_ms > 0 else None,
+            "interactions_per_s": near_pairs / (conv_ms_max * 1e-3) if conv_ms_max > 0 else None,
             "phase_ms": {k: v / args.steps for k, v in phase_sum.items()},
             "device_ms_per_step": dev_ms / args.steps,
             "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "steps/s", "ms_per_step": e2e_ms_per_step,

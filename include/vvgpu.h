@@ -124,6 +124,9 @@ int vvgpu_move_and_clean(vvgpu_ctx* ctx, double dt_eff, double remove_eps, int r
 int vvgpu_set_shard(vvgpu_ctx* ctx, int rank, int nranks);
 /* particle range [*first, *last) this rank owns after tree_build */
 int vvgpu_shard_range(vvgpu_ctx* ctx, size_t* first, size_t* last);
+/* every rank's range, [first_last[2r], first_last[2r+1]): the tree and the cut are replicated, so no
+ * communication is needed to learn the other ranks' slices */
+int vvgpu_shard_bounds(vvgpu_ctx* ctx, size_t* first_last, size_t nranks);
 /* device pointers of the SoA arrays (x y g vx vy ieps), for NCCL all-gathers by the host layer */
 int vvgpu_particle_arrays_dev(vvgpu_ctx* ctx, int list, double** arrays6, size_t* n);
 /* tell the context that ieps / (x,y,g) of non-owned particles were filled in by the caller */

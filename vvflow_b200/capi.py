@@ -19,7 +19,7 @@ SYMBOLS = [
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
     "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_diffusive", "vvgpu_move_and_clean",
-    "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
+    "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_shard_bounds", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
 ]
 
@@ -74,6 +74,7 @@ def load():
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
         "vvgpu_set_shard": [vp, C.c_int, C.c_int],
         "vvgpu_shard_range": [vp, C.POINTER(sz), C.POINTER(sz)],
+        "vvgpu_shard_bounds": [vp, C.POINTER(sz), sz],
         "vvgpu_particle_arrays_dev": [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)],
         "vvgpu_after_exchange": [vp, C.c_int],
         "vvgpu_stream": [vp, C.POINTER(vp)],
@@ -239,6 +240,12 @@ class Context:
     # ---- sharding / interop
     def set_shard(self, rank, nranks):
         self._ck(self.L.vvgpu_set_shard(self.h, rank, nranks))
+
+    def shard_bounds(self, nranks):
+        """all ranks' [first, last) particle ranges as a (nranks, 2) int64 array (computed locally)"""
+        buf = (C.c_size_t * (2 * nranks))()
+        self._ck(self.L.vvgpu_shard_bounds(self.h, buf, nranks))
+        return np.array(list(buf), dtype=np.int64).reshape(nranks, 2)
 
     def shard_range(self):
         a, b = C.c_size_t(), C.c_size_t()

@@ -1051,6 +1051,29 @@ int vvgpu_shard_range(vvgpu_ctx* c, size_t* first, size_t* last) {
     *first = a; *last = b;
     return 0;
 }
+int vvgpu_shard_bounds(vvgpu_ctx* c, size_t* first_last, size_t nranks) {
+    if (!c || !first_last || (int)nranks != c->nranks) return fail(c, VVGPU_EINVAL, "shard_bounds: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (nranks > 32) return fail(c, VVGPU_ELIMIT, "shard_bounds: more than 32 ranks");
+    CK(cudaSetDevice(c->device));
+    // the tree is replicated and the groups are cut by the same formula on every rank (lists_impl), so each
+    // rank can name every rank's particle range: rank r starts at the first particle of its first leaf
+    const int ng = c->ngroups;
+    int nread = 0;
+    for (size_t r = 1; r < nranks; r++) {
+        const int lf = (int)((long long)ng * (long long)r / (long long)nranks) * kGroupLeaves;
+        if (lf < c->nleaves) {
+            CK(cudaMemcpyAsync(c->h_pinned + r, c->l_first.as<int>() + lf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            nread++;
+        } else c->h_pinned[r] = (int)c->tn;
+    }
+    if (nread) CK(cudaStreamSynchronize(c->stream));
+    for (size_t r = 0; r < nranks; r++) {
+        first_last[2 * r] = r ? (size_t)c->h_pinned[r] : 0;
+        first_last[2 * r + 1] = (r + 1 < nranks) ? (size_t)c->h_pinned[r + 1] : (size_t)c->tn;
+    }
+    return 0;
+}
 int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* n) {
     if (!c || list != VVGPU_LIST_VORTEX || !arrays6) return VVGPU_EINVAL;
     Particles p = c->ps[c->cur].view();

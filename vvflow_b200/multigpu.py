@@ -66,6 +66,12 @@ class ShardedStep:
     def __init__(self, ctx, rank, world, device, group=None):
         self.ctx, self.rank, self.world, self.device, self.group = ctx, rank, world, device, group
         ctx.set_shard(rank, world)
+        # On a GPU the collectives are enqueued relative to the LIBRARY's stream (torch sees it as an external
+        # stream): NCCL orders itself against that stream with events, so a phase boundary needs no host
+        # synchronisation at all.
+        self.ext = None
+        if world > 1 and torch.device(device).type == "cuda" and hasattr(ctx, "stream"):
+            self.ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device(device))
 
     def _tensors(self):
         if hasattr(self.ctx, "tensors"):       # test doubles hand out CPU tensors directly
@@ -74,19 +80,30 @@ class ShardedStep:
         return [dev_tensor(p, n, self.device) for p in ptrs]
 
     def _gather(self, which):
-        self.ctx.synchronize()                 # the library runs on its own stream
+        if self.ext is not None:
+            with torch.cuda.stream(self.ext):
+                ts = self._tensors()
+                for k in which:
+                    allgather_slices(ts[k], self.bounds, self.rank, self.group)
+            return
+        self.ctx.synchronize()                 # CPU test doubles / no stream handle: plain host ordering
         ts = self._tensors()
         for k in which:
             allgather_slices(ts[k], self.bounds, self.rank, self.group)
         if torch.device(self.device).type == "cuda":
             torch.cuda.synchronize(self.device)
 
+    def _bounds(self):
+        if hasattr(self.ctx, "shard_bounds"):  # the tree and the cut are replicated: no communication needed
+            return self.ctx.shard_bounds(self.world)
+        first, last = self.ctx.shard_range()
+        return slice_bounds(first, last, self.group)
+
     def step(self, far, min_node, max_node, merge, inf_vx, inf_vy, dt, re, viscous=True):
         ctx = self.ctx
         ctx.tree_build(far, min_node, max_node)
         if self.world > 1:
-            first, last = ctx.shard_range()
-            self.bounds = slice_bounds(first, last, self.group)
+            self.bounds = self._bounds()
             check_tiling(self.bounds, ctx.n)
             merged = 0
             if merge:

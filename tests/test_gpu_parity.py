@@ -17,10 +17,10 @@ pytestmark = pytest.mark.gpu
 VTOL = 1e-10  # relative tolerance on velocities / integral sums stated by north_star
 
 
-def run_pair(ctx, port, xyg, bodies=(), merge=True, re=600.0, dt=0.05, inf=(1.0, 0.0), far=8, stop=None):
+def run_pair(ctx, port, xyg, bodies=(), merge=True, re=600.0, dt=0.05, inf=(1.0, 0.0), far=8, stop=None, tree=None):
     """Drive oracle and GPU through the hot path (vvflow.cpp:246-257), comparing after every phase."""
     bodies = list(bodies)
-    mn, mx = cases.tree_params(bodies)
+    mn, mx = tree if tree is not None else cases.tree_params(bodies)
     pb = cases.port_bodies(port, bodies)
     P = port.Port(xyg=xyg, bodies=pb)
     from vvflow_b200 import vvhd
@@ -146,6 +146,15 @@ def test_duplicates_and_lines(ctx, port):
     run_pair(ctx, port, a)
     b = np.zeros((40, 3)); b[:, 0] = rng.uniform(0, 1, 40); b[:, 2] = 1.0  # all on y = 0
     run_pair(ctx, port, b)
+
+
+@pytest.mark.parametrize("sign", ["same", "mixed"])
+def test_big_leaves(ctx, port, sign):
+    """minNodeSize stops the subdivision early (TSortedTree.cpp:45-47): leaves of ~60 particles, so that the
+    near-field kernels run several 15-target passes per leaf and expand source leaves in pieces"""
+    xyg = cases.cloud(20000, "uniform", sign, seed=77)
+    out = run_pair(ctx, port, xyg, tree=(0.06, 1e300), merge=(sign == "mixed"))
+    assert out["leaves"] < 20000 // 30
 
 
 @pytest.mark.parametrize("n,seed", [(200, 1), (2000, 2), (20000, 3)])

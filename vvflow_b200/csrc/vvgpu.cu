@@ -337,7 +337,10 @@ int lists_impl(vvgpu_ctx* c, bool all) {
         CK(cudaMemsetAsync(derr, 0, 4 * sizeof(int), st));
         CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
         CK(cudaMemsetAsync(scount, 0, sizeof(int) * (nreg_slots + 1), st));
-        TravOut O{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase, scount, derr};
+        // chunk = work unit of the near kernels: long chunks save the per-unit prologue and the parking of partial
+        // states (most groups then are ONE unit), short ones keep every SM busy when there are few groups
+        const int unit = ng >= 2000 ? kUnitEntries : (ng >= 600 ? std::min(512, kUnitEntries) : 256);
+        TravOut O{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase, scount, derr, unit};
         TravItems I0{nullptr, nullptr, nullptr, item_cap, cut};
         if (g1 > g0) {
             k_traverse_cta<0><<<g1 - g0, kTcWarps * 32, 0, st>>>(T, L, nl, g0, g1, c->farc, O, taylor, farcount, hvlist, derr + 1,
@@ -360,7 +363,7 @@ int lists_impl(vvgpu_ctx* c, bool all) {
             NEED(ok);
             CK(cudaMemsetAsync(scount + nreg_slots, 0, sizeof(int) * (nheavy_slots + 1), st));
             CK(cudaMemsetAsync(icount, 0, sizeof(int) * nheavy, st));
-            TravOut OH{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase + nreg_slots, scount + nreg_slots, derr};
+            TravOut OH{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase + nreg_slots, scount + nreg_slots, derr, unit};
             TravItems I{inode, imask, icount, item_cap, cut};
             k_traverse<1><<<cdiv(nheavy, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
                 T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();

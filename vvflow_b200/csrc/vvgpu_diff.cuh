@@ -41,7 +41,7 @@ struct DfWarp {
 struct DfShared {
     int4 ent[kUnitEntries];    // first particle, count, first segment, segment count of the entry's leaf
     u32 emk[kUnitEntries];     // target-leaf mask
-    double ebox[kUnitEntries][4];
+    float4 ebox[kUnitEntries];   // source-leaf box, rounded OUTWARD to float: the skip below stays conservative
     int bounds[kGroupLeaves + 1];
     int next;
     int anyseg;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
         S.ent[e] = en;
         S.emk[e] = A.G.mask[e0 + e];
         const double* b = A.lbox + 5ll * sl;
-        S.ebox[e][0] = b[0]; S.ebox[e][1] = b[1]; S.ebox[e][2] = b[2]; S.ebox[e][3] = b[3];
+        S.ebox[e] = make_float4(__double2float_rd(b[0]), __double2float_ru(b[1]), __double2float_rd(b[2]), __double2float_ru(b[3]));
     }
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
                             const int4 en = S.ent[e];
                             f = en.x; cnt = en.y;
                             if (cnt) {
-                                const double* b = S.ebox[e];
-                                const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
-                                const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
+                                const float4 b = S.ebox[e];
+                                const double gx = fmax(0., fmax((double)b.x - bx1, bx0 - (double)b.y));
+                                const double gy = fmax(0., fmax((double)b.z - by1, by0 - (double)b.w));
                                 if (gx * gx + gy * gy > R2) cnt = 0;
                             }
                         }

@@ -23,7 +23,10 @@
 namespace vv {
 
 constexpr int kGroupLeaves = 32;
-constexpr int kUnitEntries = 512;   // list entries per chunk = per work unit of the near-field kernels
+#ifndef VV_UNIT_ENTRIES
+#define VV_UNIT_ENTRIES 768
+#endif
+constexpr int kUnitEntries = VV_UNIT_ENTRIES;   // list entries per chunk = per work unit of the near-field kernels
 constexpr int kTravWarps = 4;       // warps per CTA in k_traverse
 constexpr int kTravBudget = 256;    // warp iterations before a group is declared heavy (the mean is ~150)
 constexpr int kTravStack = 1024;    // stack entries per warp (shared memory)
@@ -43,6 +46,8 @@ struct TravOut {
     long long* slot_base;
     int* slot_count;
     int* err;                     // bit 0: pool full, bit 1: stack overflow, bit 2: slot overflow in an item
+    int unit;                     // entries per chunk (<= kUnitEntries, the capacity of the near kernels' tables):
+                                  // small problems use shorter chunks so that there are enough work units to fill the GPU
 };
 
 // far iff dr.abs2() > farCriteria*HalfPerim*HalfPerim, HalfPerim = top.h + top.w + h + w
@@ -147,7 +152,7 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravO
     double nfar = 0;
     int iters = 0;
     // chunk bookkeeping (uniform across the warp)
-    int nchunk = 0, fill = kUnitEntries;   // "full": the first emission claims a chunk
+    int nchunk = 0, fill = O.unit;   // "full": the first emission claims a chunk
     long long cbase = 0;
     int nitems = 0;
     bool bail = false;
@@ -210,7 +215,7 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravO
             const int k = __popc(eb);
             int pos = fill + __popc(eb & lanemask_lt());
             long long nbase = cbase;
-            if (fill + k > kUnitEntries) {   // (part of) this batch goes to a fresh chunk
+            if (fill + k > O.unit) {   // (part of) this batch goes to a fresh chunk
                 if (nchunk >= nslots) {
                     if (MODE == 0) { bail = true; break; }
                     if (lane == 0) atomicOr(O.err, 4);
@@ -218,12 +223,12 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravO
                 }
                 unsigned long long nb = 0;
                 if (lane == 0) {
-                    nb = atomicAdd(O.cursor, (unsigned long long)kUnitEntries);
-                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = kUnitEntries;
+                    nb = atomicAdd(O.cursor, (unsigned long long)O.unit);
+                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = O.unit;
                     O.slot_base[slot0 + nchunk] = (long long)nb;
                 }
                 nb = __shfl_sync(0xffffffffu, nb, 0);
-                if ((long long)nb + kUnitEntries > O.pool_cap) {
+                if ((long long)nb + O.unit > O.pool_cap) {
                     if (lane == 0) atomicOr(O.err, 1);
                     return;
                 }
@@ -231,11 +236,11 @@ k_traverse(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravO
                 nchunk++;
             }
             if (emit) {
-                const long long at = (pos < kUnitEntries) ? (cbase + pos) : (nbase + (pos - kUnitEntries));
+                const long long at = (pos < O.unit) ? (cbase + pos) : (nbase + (pos - O.unit));
                 O.G.leaf[at] = T.lstart[n];
                 O.G.mask[at] = nearm;
             }
-            if (fill + k > kUnitEntries) { fill = fill + k - kUnitEntries; cbase = nbase; }
+            if (fill + k > O.unit) { fill = fill + k - O.unit; cbase = nbase; }
             else fill += k;
         }
         // far nodes: transpose (node lane x leaf bit) -> (leaf lane x node bit) and accumulate
@@ -339,7 +344,7 @@ k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, T
     double* cm = cmw[warp];
     int size = 1;
     double T1 = 0, T2 = 0, T3 = 0, T4 = 0, nfar = 0;
-    int nchunk = 0, fill = kUnitEntries;   // uniform across the CTA; "full": the first emission claims a chunk
+    int nchunk = 0, fill = O.unit;   // uniform across the CTA; "full": the first emission claims a chunk
     long long cbase = 0;
     int visited = 0;
     bool bail = false;
@@ -399,7 +404,7 @@ k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, T
         if (etotal) {
             const int pos = fill + ebefore + __popc(eb & lanemask_lt());
             long long nbase = cbase;
-            const bool cross = fill + etotal > kUnitEntries;   // (part of) this batch goes to a fresh chunk
+            const bool cross = fill + etotal > O.unit;   // (part of) this batch goes to a fresh chunk
             if (cross) {
                 if (nchunk >= nslots) {
                     if (MODE == 0) { bail = true; break; }
@@ -407,25 +412,25 @@ k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, T
                     return;
                 }
                 if (tid == 0) {
-                    const unsigned long long nb = atomicAdd(O.cursor, (unsigned long long)kUnitEntries);
-                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = kUnitEntries;
+                    const unsigned long long nb = atomicAdd(O.cursor, (unsigned long long)O.unit);
+                    if (nchunk > 0) O.slot_count[slot0 + nchunk - 1] = O.unit;
                     O.slot_base[slot0 + nchunk] = (long long)nb;
                     s_nbase = (long long)nb;
                 }
                 __syncthreads();
                 nbase = s_nbase;
-                if (nbase + kUnitEntries > O.pool_cap) {
+                if (nbase + O.unit > O.pool_cap) {
                     if (tid == 0) atomicOr(O.err, 1);
                     return;
                 }
                 nchunk++;
             }
             if (emit) {
-                const long long at = (pos < kUnitEntries) ? (cbase + pos) : (nbase + (pos - kUnitEntries));
+                const long long at = (pos < O.unit) ? (cbase + pos) : (nbase + (pos - O.unit));
                 O.G.leaf[at] = T.lstart[n];
                 O.G.mask[at] = nearm;
             }
-            if (cross) { fill = fill + etotal - kUnitEntries; cbase = nbase; }
+            if (cross) { fill = fill + etotal - O.unit; cbase = nbase; }
             else fill += etotal;
         }
         // far nodes of this warp: transpose (node lane x leaf bit) -> (leaf lane x node bit) and accumulate
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(1024) k_heavy_pack(int nheavy, int item_cap, T
     if (threadIdx.x == 0) {
         nlive_s = (int)lcarry;
         total_s = (int)carry;
-        const unsigned long long need = ((unsigned long long)carry + kUnitEntries - 1) / kUnitEntries * kUnitEntries;
+        const unsigned long long need = ((unsigned long long)carry + O.unit - 1) / O.unit * O.unit;
         const unsigned long long at = atomicAdd(O.cursor, need);
         region = (long long)at;
         if ((long long)(at + need) > O.pool_cap) { atomicOr(O.err, 1); region = -1; }
@@ -547,10 +552,10 @@ __global__ void __launch_bounds__(1024) k_heavy_pack(int nheavy, int item_cap, T
     __syncthreads();
     const int total = total_s;
     for (long long s = threadIdx.x; s < per; s += 1024) {
-        const long long first = s * kUnitEntries;
+        const long long first = s * O.unit;
         const bool used = first < total;
         sbase[s] = used ? region + first : 0;
-        scount[s] = used ? (int)min((long long)kUnitEntries, total - first) : 0;
+        scount[s] = used ? (int)min((long long)O.unit, total - first) : 0;
     }
 }
 

@@ -280,6 +280,9 @@ def ours(args):
     total_ms = float(t[1].item())  # max over ranks; wall bracketed by barrier+synchronize on both sides
     ms_per_step = total_ms / args.steps
 
+    if dbg:
+        print(f"[dbg] rank {rank}: " + " ".join(f"{k}={v / args.steps:.2f}" for k, v in phase_sum.items())
+              + f" sum={sum(phase_sum.values()) / args.steps:.2f} wall/step={wall_ms / args.steps:.2f}", file=sys.stderr)
     # interaction counts of the final state's tree (work done per step)
     ctx.tree_build(FAR, 0.0, DBL_MAX)
     local_pairs, local_far = ctx.count_interactions()   # of this rank's slice of the leaf groups

@@ -47,6 +47,31 @@ def allgather_slices(full, bounds, rank, group=None):
     return full
 
 
+def allgather_padded(fulls, bounds, rank, group=None):
+    """Same result as allgather_slices for every tensor in `fulls`, with ONE collective for all of them: the
+    slices are padded to the longest one, gathered with all_gather (equal sizes), and written back with one
+    concatenation per tensor. One broadcast per rank and array (allgather_slices) costs world x len(fulls)
+    collectives per phase boundary, which dominated the step at 8 GPUs."""
+    world = bounds.shape[0]
+    lens = [int(bounds[r, 1] - bounds[r, 0]) for r in range(world)]
+    L = max(max(lens), 1)
+    k = len(fulls)
+    a, b = int(bounds[rank, 0]), int(bounds[rank, 1])
+    send = torch.zeros((k, L), dtype=fulls[0].dtype, device=fulls[0].device)
+    for i, f in enumerate(fulls):
+        send[i, : b - a] = f[a:b]
+    if dist.get_backend(group) == "nccl":
+        recv = torch.empty((world, k, L), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        parts = [recv[r] for r in range(world)]
+    else:
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send, group=group)
+    for i, f in enumerate(fulls):
+        torch.cat([parts[r][i, : lens[r]] for r in range(world)], out=f)
+    return fulls
+
+
 class DevArray:
     """torch view of a raw device pointer owned by libvvgpu (no copy)"""
 
@@ -83,13 +108,11 @@ class ShardedStep:
         if self.ext is not None:
             with torch.cuda.stream(self.ext):
                 ts = self._tensors()
-                for k in which:
-                    allgather_slices(ts[k], self.bounds, self.rank, self.group)
+                allgather_padded([ts[k] for k in which], self.bounds, self.rank, self.group)
             return
         self.ctx.synchronize()                 # CPU test doubles / no stream handle: plain host ordering
         ts = self._tensors()
-        for k in which:
-            allgather_slices(ts[k], self.bounds, self.rank, self.group)
+        allgather_padded([ts[k] for k in which], self.bounds, self.rank, self.group)
         if torch.device(self.device).type == "cuda":
             torch.cuda.synchronize(self.device)
 

@@ -357,13 +357,13 @@ def ours(args):
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None,
                          # ncu dram__bytes_read + dram__bytes_write of this kernel at N=1M, per launch
-                         # (profiles/r1_ncu_kernels_v5.txt: 83.4 MB + 19.6 MB)
-                         "traffic": 1.03e8 if n == 1_000_000 and world == 1 else None,
-                         "ncu_fp64_pipe_pct": 57.5 if n == 1_000_000 and world == 1 else None,
+                         # (profiles/r1_ncu_kernels_v6.txt: 97.2 MB + 13.2 MB)
+                         "traffic": 1.10e8 if n == 1_000_000 and world == 1 else None,
+                         "ncu_fp64_pipe_pct": 58.9 if n == 1_000_000 and world == 1 else None,
                          "note": "FP64-pipe bound (no tensor cores: N-body gather). achieved = 11 flop x near pairs / "
                                  "CUDA-event time of the phase on the library's stream; peak = DFMA micro-benchmark "
                                  "measured in this run (MEASURED_PEAKS.json holds HBM %s GB/s and bf16 only). "
-                                 "HBM traffic of the kernel is ~0.10 GB vs 39.7 GFLOP: compute-bound. ncu_fp64_pipe_pct = "
+                                 "HBM traffic of the kernel is ~0.11 GB vs 39.7 GFLOP: compute-bound. ncu_fp64_pipe_pct = "
                                  "sm__inst_executed_pipe_fp64 of the committed ncu capture (not measured in this run): the "
                                  "pipe is busier than frac says because a pair costs 9 FP64 instructions, of which only "
                                  "7 are FMAs, for the 11 flop the metric counts." % peaks.get("hbm_gbs")},

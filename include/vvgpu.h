@@ -109,6 +109,12 @@ int vvgpu_epsilon_probe(vvgpu_ctx* ctx, int* ncandidates);
  * dt = S->dt (sink epsilon, :160), sinks = Space::SourceList as (x,y,g) triples -------------- */
 int vvgpu_convective(vvgpu_ctx* ctx, double inf_vx, double inf_vy, double dt, const double* sinks_xyg,
                      size_t nsink);
+/* ---- MConvectiveFast::velocity(TVec p), MConvectiveFast.cpp:20-34 (sensors, vvplot rasters):
+ * velocity at npts arbitrary points xy (x, y pairs, host) -> vxy_out (vx, vy pairs, host). Needs a built tree
+ * (fails like stree::findNode, TSortedTree.cpp:286-288, otherwise) and the _1_eps of the current particle set
+ * (vvgpu_epsilon of this step, or the values passed in with the particles). ---------------------------------- */
+int vvgpu_velocity_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double inf_vx, double inf_vy, double dt,
+                      const double* sinks_xyg, size_t nsink, double* vxy_out);
 /* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
  * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
 int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);

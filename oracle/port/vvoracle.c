@@ -454,6 +454,58 @@ void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double
     }
 }
 
+/* MConvectiveFast::velocity, MConvectiveFast.cpp:20-34: velocity at an arbitrary point = near particles of the
+ * point's leaf (near_nodes_influence, :116-137) + the leaf's far nodes as eps = 0 monopoles AT THE POINT
+ * (far_nodes_influence, :139-151; CMp/CMm carry _1_eps = inf, TSortedTree.cpp:25,179) + sinks + bodies + inf_speed.
+ * Note the far part differs from the step loop's Taylor expansion about the leaf centre (:48-69). */
+void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double inf_vx, double inf_vy, double dt,
+                     const double* sinks, int64_t nsink, const double* xy, int64_t npts, double* out) {
+    static const vvo_bodies nobody;
+    if (!b) b = &nobody;
+    for (int64_t q = 0; q < npts; q++) {
+        const double px = xy[2 * q], py = xy[2 * q + 1];
+        const int64_t node = vvo_find_node(t, px, py);
+        const int64_t l = t->leaf[node];
+        double resx = 0, resy = 0;
+        double rx = 0, ry = 0;
+        for (int64_t k = t->near_ptr[l]; k < t->near_ptr[l + 1]; k++) {
+            int64_t nn = t->leaf_node[t->near_idx[k]];
+            for (int64_t j = t->vfirst[nn]; j < t->vlast[nn]; j++) {
+                if (!p->g[j]) continue;
+                double dx = px - p->x[j], dy = py - p->y[j];
+                double w = p->g[j] / (dx * dx + dy * dy + sqr(1. / p->ieps[j]));
+                rx += -dy * w; ry += dx * w;
+            }
+        }
+        resx += rx * C_1_2PI; resy += ry * C_1_2PI;
+        rx = 0; ry = 0;
+        for (int64_t k = t->far_ptr[l]; k < t->far_ptr[l + 1]; k++) {
+            const double* P = t->cmp + 3 * t->far_idx[k];
+            const double* M = t->cmm + 3 * t->far_idx[k];
+            double dx = px - P[0], dy = py - P[1];
+            double w = P[2] / (dx * dx + dy * dy + 0.);
+            rx += -dy * w; ry += dx * w;
+            dx = px - M[0]; dy = py - M[1];
+            w = M[2] / (dx * dx + dy * dy + 0.);
+            rx += -dy * w; ry += dx * w;
+        }
+        resx += rx * C_1_2PI; resy += ry * C_1_2PI;
+        double sx = 0, sy = 0;
+        double eps2_div_srcg = dt * C_1_PI;
+        for (int64_t k = 0; k < nsink; k++) {
+            double dx = px - sinks[3 * k], dy = py - sinks[3 * k + 1], sg = sinks[3 * k + 2];
+            double w = sg / (dx * dx + dy * dy + eps2_div_srcg * fabs(sg));
+            sx += dx * w; sy += dy * w;
+        }
+        resx += sx * C_1_2PI; resy += sy * C_1_2PI;
+        double bx, by;
+        body_list_influence(b, px, py, &bx, &by);
+        resx += bx; resy += by;
+        resx += inf_vx; resy += inf_vy;
+        out[2 * q] = resx; out[2 * q + 1] = resy;
+    }
+}
+
 /* ------------------------------------------------------------------ diffusive */
 
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)

@@ -7,6 +7,7 @@
  *   MConvectiveFast::process_all_lists  libvvhd/src/MConvectiveFast.cpp:36-114
  *   MDiffusiveFast::process_vort_list   libvvhd/src/MDiffusiveFast.cpp:8-48
  *   MFlowmove::move_and_clean (particle part)  libvvhd/src/MFlowmove.cpp:107-144,194-199
+ *   MConvectiveFast::velocity(p)    libvvhd/src/MConvectiveFast.cpp:20-34,139-151
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it. Parity is PINNED: tests/test_oracle_port.py checks every function here against
  * oracle/_ref/libvvref.so (the reference's own sources compiled unmodified) and against the
@@ -71,6 +72,9 @@ int64_t vvo_find_node(const vvo_tree* t, double px, double py);
 int64_t vvo_epsilon(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, int merge);
 void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double inf_vx, double inf_vy,
                     double dt, const double* sinks_xyg, int64_t nsink);
+/* MConvectiveFast::velocity (MConvectiveFast.cpp:20-34) at npts points xy -> out (vx, vy pairs); needs ieps */
+void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double inf_vx, double inf_vy, double dt,
+                     const double* sinks_xyg, int64_t nsink, const double* xy, int64_t npts, double* out);
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
 /* advect, drop |g|<remove_eps, drop in-body (accumulating dead sums), zero v. Compacts p in place,
  * returns the new n; *cleaned = number removed by the in-body test */

@@ -56,6 +56,8 @@ def lib():
         L.vvo_convective.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double,
                                      C.c_double, C.c_double, C.c_void_p, C.c_int64]
         L.vvo_diffusive.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double]
+        L.vvo_velocity_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double,
+                                      C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_move_and_clean.restype = C.c_int64
         L.vvo_move_and_clean.argtypes = [C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double, C.c_int,
                                          C.POINTER(C.c_int64)]
@@ -206,6 +208,15 @@ class Port:
     def convective(self, inf_vx=0.0, inf_vy=0.0, dt=0.0, sinks=None):
         s = np.zeros((0, 3)) if sinks is None else np.ascontiguousarray(sinks, dtype=np.float64).reshape(-1, 3)
         self.L.vvo_convective(self.tree, C.byref(self.p), self._b(), inf_vx, inf_vy, dt, _ptr(s), s.shape[0])
+
+    def velocity_at(self, xy, inf_vx=0.0, inf_vy=0.0, dt=0.0, sinks=None):
+        """MConvectiveFast::velocity at arbitrary points (needs a built tree and epsilon)"""
+        s = np.zeros((0, 3)) if sinks is None else np.ascontiguousarray(sinks, dtype=np.float64).reshape(-1, 3)
+        a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros_like(a)
+        self.L.vvo_velocity_at(self.tree, C.byref(self.p), self._b(), inf_vx, inf_vy, dt, _ptr(s), s.shape[0],
+                               _ptr(a), a.shape[0], _ptr(out))
+        return out
 
     def diffusive(self, re):
         self.L.vvo_diffusive(self.tree, C.byref(self.p), self._b(), re)

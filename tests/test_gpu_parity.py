@@ -197,6 +197,67 @@ def test_two_cylinders_moving(ctx, port):
     run_pair(ctx, port, xyg, bodies=[b1, b2])
 
 
+def _points_for(xyg, rng, n=2000):
+    lo, hi = xyg[:, :2].min(0), xyg[:, :2].max(0)
+    inside = rng.uniform(lo, hi, (n, 2))
+    on = xyg[rng.integers(0, xyg.shape[0], 50), :2]          # dr = 0 with a source (eps keeps it finite)
+    far = rng.uniform(lo - 3 * (hi - lo), hi + 3 * (hi - lo), (200, 2))
+    return np.concatenate([inside, on, far])
+
+
+@pytest.mark.parametrize("case", ["cloud", "cylinder", "moving_bodies_sinks"])
+def test_velocity_at_points(ctx, port, case):
+    """SURVEY 8(f) row 4: MConvectiveFast::velocity(p) (MConvectiveFast.cpp:20-34) against the oracle, which is
+    pinned bit-exact to the compiled reference for this function (tests/test_oracle_port.py). 1e-10 norm-wise."""
+    from vvflow_b200 import vvhd
+    rng = np.random.default_rng(31)
+    bodies, sinks = [], None
+    if case == "cloud":
+        xyg = cases.cloud(30000, "gauss", "mixed", seed=12)
+    elif case == "cylinder":
+        xyg = cases.around_cylinder(8000, sign="mixed", seed=13)
+        bodies = [cases.cylinder(0.5, 350)]
+    else:
+        b1 = cases.cylinder(0.5, 200, 0.0, 0.0)
+        b2 = cases.cylinder(0.5, 200, 2.0, 0.0)
+        b2.speed_slae = np.array([0.1, -0.05, 0.2]); b2.slip[:20] = 1; b2.g[:20] = 0.01; b2.axis = np.array([2.0, 0.0])
+        bodies = [b1, b2]
+        xyg = np.zeros((6000, 3))
+        xyg[:, 0] = rng.uniform(-1, 3.5, 6000); xyg[:, 1] = rng.uniform(-1.2, 1.2, 6000)
+        xyg[:, 2] = rng.uniform(-1, 1, 6000) / 6000
+        sinks = np.array([[0.3, 1.5, 0.2], [-2.0, 0.1, -0.1]])
+    mn, mx = cases.tree_params(bodies)
+    pb = cases.port_bodies(port, bodies)
+    P = port.Port(xyg=xyg, bodies=pb)
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    S.re, S.dt, S.inf_vx, S.inf_vy = 600.0, 0.05, 1.0, 0.25
+    if sinks is not None:
+        S.SourceList = sinks
+    tr = vvhd.TSortedTree(S, 8, mn, mx)
+    eps, conv = vvhd.MEpsilonFast(S, tr), vvhd.MConvectiveFast(S, tr)
+    with pytest.raises(RuntimeError):
+        conv.velocity((0.0, 0.0))                       # findNode on an unbuilt tree throws (TSortedTree.cpp:286-288)
+    try:
+        P.tree_build(8, mn, mx); tr.build()
+        eps.CalcEpsilonFast(True)
+        assert P.epsilon(True) == eps.Merged()
+        pts = _points_for(xyg, rng)
+        want = P.velocity_at(pts, 1.0, 0.25, 0.05, sinks)
+        got = conv.velocity(pts)
+        ok = np.isfinite(want).all(axis=1)
+        assert ok.sum() >= pts.shape[0] - 2
+        assert relerr(got[ok], want[ok]) <= VTOL, relerr(got[ok], want[ok])
+        one = conv.velocity(pts[7])
+        assert one.shape == (2,) and np.array_equal(one, got[7])
+        assert conv.velocity(np.zeros((0, 2))).shape == (0, 2)
+    finally:
+        if tr.built:
+            tr.destroy()
+        P.tree_destroy()
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

@@ -119,3 +119,35 @@ def test_python_body_matches_reference(ref):
     assert np.allclose(b.cofm, body[2:4], atol=1e-14)
     assert np.allclose(b.bl, body[4:6], atol=1e-15) and np.allclose(b.tr, body[6:8], atol=1e-15)
     assert abs(b.disc_r2 - body[8]) < 1e-14 and b.inside_valid == bool(body[9])
+
+
+def _query_points(xyg, rng, n=300):
+    """points inside the cloud, on particles (dr = 0 with a source), and far outside"""
+    lo, hi = xyg[:, :2].min(0), xyg[:, :2].max(0)
+    inside = rng.uniform(lo, hi, (n, 2))
+    on = xyg[rng.integers(0, xyg.shape[0], 20), :2]
+    far = rng.uniform(lo - 3 * (hi - lo), hi + 3 * (hi - lo), (40, 2))
+    return np.concatenate([inside, on, far])
+
+
+def test_velocity_at_matches_reference(port, ref):
+    """MConvectiveFast::velocity(p) (MConvectiveFast.cpp:20-34): the port, bit-exact against the compiled reference,
+    body-free cloud and cylinder (body_list_influence is 0 for a fixed no-slip body, the tree still holds segments)"""
+    rng = np.random.default_rng(5)
+    for with_body in (False, True):
+        xyg = cases.around_cylinder(4000, sign="mixed", seed=9) if with_body else cases.cloud(5000, "gauss", "mixed", seed=8)
+        r = ref.Ref(re=600, dt=0.05, inf_vx=1.0, inf_vy=0.25)
+        if with_body:
+            r.add_cylinder(0.5, 350)
+        r.set_list(xyg)
+        mn, mx = r.tree_params(8)
+        r.tree_build()
+        pb = port.Bodies.from_ref(r) if with_body else None
+        P = port.Port(xyg=xyg, bodies=pb)
+        P.tree_build(8, mn, mx)
+        assert r.epsilon(True) == P.epsilon(True)
+        pts = _query_points(xyg, rng)
+        v1 = r.velocity_at(pts)
+        v2 = P.velocity_at(pts, 1.0, 0.25, 0.05)
+        assert same(v1, v2), np.abs(v1 - v2).max()
+        r.tree_destroy(); P.tree_destroy()

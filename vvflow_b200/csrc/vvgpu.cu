@@ -4,6 +4,7 @@
 #include "../../include/vvgpu.h"
 #include "vvgpu_conv.cuh"
 #include "vvgpu_diff.cuh"
+#include "vvgpu_point.cuh"
 #include "vvgpu_move.cuh"
 #include "vvgpu_tree_coop.cuh"
 
@@ -110,7 +111,7 @@ struct vvgpu_ctx {
     // epsilon
     Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged;
     Buf mA[6], mB[6];
-    Buf d_sinks, d_pairs;
+    Buf d_sinks, d_pairs, pt_xy, pt_out;
 
     // shard
     int rank = 0, nranks = 1;
@@ -954,6 +955,38 @@ int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, cons
         k_body_influence<<<cdiv(c->tn, 128), 128, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), B); CKLAUNCH();
     }
     if (nsink) CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int vvgpu_velocity_at(vvgpu_ctx* c, const double* xy, size_t npts, double inf_vx, double inf_vy, double dt,
+                      const double* sinks_xyg, size_t nsink, double* vxy_out) {
+    if (!c || (npts && (!xy || !vxy_out)) || (nsink && !sinks_xyg)) return fail(c, VVGPU_EINVAL, "velocity_at: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "TTree::findNode(): tree is not built");   // TSortedTree.cpp:286-288
+    if (npts == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* dxy = c->pt_xy.get<double>(2 * npts, &ok);
+    double* dout = c->pt_out.get<double>(2 * npts, &ok);
+    double* ds = c->d_sinks.get<double>(3 * nsink, &ok);
+    int* derr = c->d_err.get<int>(4, &ok);
+    NEED(ok);
+    CK(cudaMemcpyAsync(dxy, xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (nsink) CK(cudaMemcpyAsync(ds, sinks_xyg, 3 * nsink * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(derr, 0, 4 * sizeof(int), c->stream));
+    PointArgs A;
+    A.T = c->T(); A.P = c->ps[c->cur].view(); A.npts = (int)npts; A.xy = dxy; A.out = dout;
+    A.farc = c->farc; A.inf_vx = inf_vx; A.inf_vy = inf_vy; A.eps2_div_srcg = dt * k1_Pi;
+    A.sinks = ds; A.nsink = (int)nsink;
+    A.B = BodyFull{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                   c->s_dlx.as<double>(), c->s_dly.as<double>(), c->s_g.as<double>(), c->s_ie.as<double>(),
+                   c->s_slip.as<int>(), c->b_first.as<int>(), c->b_prop.as<double>()};
+    A.body_flow = (c->any_body_flow && c->nbody) ? 1 : 0;
+    A.err = derr;
+    k_velocity_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
+    CK(cudaMemcpyAsync(vxy_out, dout, 2 * npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "velocity_at: traversal stack overflow");
     return 0;
 }
 

@@ -762,6 +762,43 @@ __device__ __forceinline__ void linear_source(double px, double py, double rx, d
     cplx_mul(br, bi, lr, li, mr, mi);
     cplx_div((q2 - q1) - mr, -mi, dlx, -dly, ox, oy);
 }
+// one segment's terms of body_list_influence (:172-215) at the point (px, py), accumulated before the 1/2pi factor
+__device__ __forceinline__ void body_slip_term(const BodyFull& B, int s, double px, double py, double& rx, double& ry) {
+    if (!B.slip[s]) return;
+    double dx = px - B.rx[s], dy = py - B.ry[s];
+    double ee = 1. / B.ie[s];
+    double k = B.g[s] / (dx * dx + dy * dy + ee * ee);
+    rx += -dy * k; ry += dx * k;
+}
+__device__ __forceinline__ void body_motion_term(const BodyFull& B, const double* bp, int s, double px, double py, double& rx,
+                                                 double& ry) {
+    const double sx = bp[9], sy = bp[10], so = bp[11], ax = bp[0], ay = bp[1];
+    double dx = px - B.rx[s], dy = py - B.ry[s];
+    double drabs2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+    double dlx = B.dlx[s], dly = B.dly[s];
+    if (drabs2 < VV_ADD(VV_MUL(dlx, dlx), VV_MUL(dly, dly))) {
+        double ux = B.cx[s] - ax, uy = B.cy[s] - ay;
+        double v1x = sx - so * uy, v1y = sy + so * ux;
+        double g1 = -(v1x * dlx + v1y * dly), q1 = -(-v1y * dlx + v1x * dly);
+        double wx = B.cx[s] + dlx - ax, wy = B.cy[s] + dly - ay;
+        double v2x = sx - so * wy, v2y = sy + so * wx;
+        double g2 = -(v2x * dlx + v2y * dly), q2 = -(-v2y * dlx + v2x * dly);
+        double ix, iy;
+        linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, g1, g2, ix, iy);
+        rx += -iy; ry += ix;
+        linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, q1, q2, ix, iy);
+        rx += ix; ry += iy;
+    } else {
+        double ux = B.rx[s] - ax, uy = B.ry[s] - ay;
+        double vx = sx - so * uy, vy = sy + so * ux;
+        double gg = -(vx * dlx + vy * dly), q = -(-vy * dlx + vx * dly);
+        double r = 1. / drabs2;
+        rx += (dx * q - dy * gg) * r;
+        ry += (dy * q + dx * gg) * r;
+    }
+}
+__device__ __forceinline__ bool body_moves(const double* bp) { return !(fabs(bp[9]) + fabs(bp[10]) + fabs(bp[11]) < 1E-10); }
+
 __global__ void k_body_influence(int n, Particles P, BodyFull B) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -771,43 +808,10 @@ __global__ void k_body_influence(int n, Particles P, BodyFull B) {
     for (int ib = 0; ib < B.nbody; ib++) {
         const double* bp = B.bprop + 16 * ib;
         const int f = B.bfirst[ib], e = B.bfirst[ib + 1];
-        if (bp[13] != 0) {  // any slip segment (TBody::get_slip)
-            for (int s = f; s < e; s++) {
-                if (!B.slip[s]) continue;
-                double dx = px - B.rx[s], dy = py - B.ry[s];
-                double ee = 1. / B.ie[s];
-                double k = B.g[s] / (dx * dx + dy * dy + ee * ee);
-                rx += -dy * k; ry += dx * k;
-            }
-        }
-        const double sx = bp[9], sy = bp[10], so = bp[11], ax = bp[0], ay = bp[1];
-        if (!(fabs(sx) + fabs(sy) + fabs(so) < 1E-10)) {
-            for (int s = f; s < e; s++) {
-                double dx = px - B.rx[s], dy = py - B.ry[s];
-                double drabs2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-                double dlx = B.dlx[s], dly = B.dly[s];
-                if (drabs2 < VV_ADD(VV_MUL(dlx, dlx), VV_MUL(dly, dly))) {
-                    double ux = B.cx[s] - ax, uy = B.cy[s] - ay;
-                    double v1x = sx - so * uy, v1y = sy + so * ux;
-                    double g1 = -(v1x * dlx + v1y * dly), q1 = -(-v1y * dlx + v1x * dly);
-                    double wx = B.cx[s] + dlx - ax, wy = B.cy[s] + dly - ay;
-                    double v2x = sx - so * wy, v2y = sy + so * wx;
-                    double g2 = -(v2x * dlx + v2y * dly), q2 = -(-v2y * dlx + v2x * dly);
-                    double ix, iy;
-                    linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, g1, g2, ix, iy);
-                    rx += -iy; ry += ix;
-                    linear_source(px, py, B.rx[s], B.ry[s], dlx, dly, q1, q2, ix, iy);
-                    rx += ix; ry += iy;
-                } else {
-                    double ux = B.rx[s] - ax, uy = B.ry[s] - ay;
-                    double vx = sx - so * uy, vy = sy + so * ux;
-                    double gg = -(vx * dlx + vy * dly), q = -(-vy * dlx + vx * dly);
-                    double r = 1. / drabs2;
-                    rx += (dx * q - dy * gg) * r;
-                    ry += (dy * q + dx * gg) * r;
-                }
-            }
-        }
+        if (bp[13] != 0)   // any slip segment (TBody::get_slip)
+            for (int s = f; s < e; s++) body_slip_term(B, s, px, py, rx, ry);
+        if (body_moves(bp))
+            for (int s = f; s < e; s++) body_motion_term(B, bp, s, px, py, rx, ry);
     }
     P.vx[i] += rx * k1_2Pi;
     P.vy[i] += ry * k1_2Pi;

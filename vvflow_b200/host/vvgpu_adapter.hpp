@@ -224,6 +224,24 @@ class MConvectiveFast {
                     "vvgpu_convective");
         }
 
+        TVec velocity(TVec p) const {   // MConvectiveFast.cpp:20-34 (sensors, X* rasters)
+            TVec v = TVec(0, 0);
+            velocity(&p, 1, &v);
+            return v;
+        }
+        // batched form for the raster evaluators: n points in, n velocities out, one device call
+        void velocity(const TVec* p, size_t n, TVec* out) const {
+            if (!tree->isBuilt()) throw std::invalid_argument("TTree::findNode(): tree is not built");   // TSortedTree.cpp:286-288
+            Device& D = *Device::of(S);
+            TVec inf = S->inf_speed();
+            std::vector<double> sinks, xy(2 * n), v(2 * n);
+            for (auto& lobj: S->SourceList) { sinks.push_back(lobj.r.x); sinks.push_back(lobj.r.y); sinks.push_back(lobj.g); }
+            for (size_t i = 0; i < n; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
+            D.check(vvgpu_velocity_at(D.ctx, xy.data(), n, inf.x, inf.y, double(S->dt), sinks.data(), S->SourceList.size(), v.data()),
+                    "vvgpu_velocity_at");
+            for (size_t i = 0; i < n; i++) out[i] = TVec(v[2 * i], v[2 * i + 1]);
+        }
+
     private:
         Space* S;
         const TSortedTree* tree;

@@ -234,6 +234,16 @@ class MConvectiveFast(_Module):
         S.ctx.convective(S.inf_vx, S.inf_vy, S.dt, S.SourceList if len(S.SourceList) else None)
         S._dev_newer = True
 
+    def velocity(self, p):
+        """TVec MConvectiveFast::velocity(TVec p) const, MConvectiveFast.cpp:20-34; `p` is (x, y) or an (n, 2)
+        array of points (the X* evaluators call it per raster point). Raises like stree::findNode when the tree
+        is not built."""
+        self._need_tree("TTree::findNode()")
+        S = self.S
+        pts = np.asarray(p, dtype=np.float64)
+        v = S.ctx.velocity_at(pts.reshape(-1, 2), S.inf_vx, S.inf_vy, S.dt, S.SourceList if len(S.SourceList) else None)
+        return v[0] if pts.ndim == 1 else v
+
 
 class MDiffusiveFast(_Module):
     def process_vort_list(self):

@@ -115,6 +115,11 @@ int vvgpu_convective(vvgpu_ctx* ctx, double inf_vx, double inf_vy, double dt, co
  * (vvgpu_epsilon of this step, or the values passed in with the particles). ---------------------------------- */
 int vvgpu_velocity_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double inf_vx, double inf_vy, double dt,
                       const double* sinks_xyg, size_t nsink, double* vxy_out);
+/* ---- static MEpsilonFast::eps2h(node, p) and ::h2(node, p), MEpsilonFast.cpp:66-107, with node = findNode(p)
+ * (what XVorticity.cpp:52,90 and XStreamfunction.cpp:89 evaluate): per point the squared distance to the
+ * second-nearest particle and to the nearest body segment (+inf without bodies) of the leaf's near leaves.
+ * eps2h_h2_out receives npts (eps2h, h2) pairs; bit-identical to the reference. ---------------------------- */
+int vvgpu_eps2h_h2_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double* eps2h_h2_out);
 /* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
  * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
 int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);

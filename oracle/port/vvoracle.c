@@ -506,6 +506,35 @@ void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b,
     }
 }
 
+/* MEpsilonFast::eps2h and ::h2 (static, MEpsilonFast.cpp:66-107) for node = findNode(p): squared distance to the
+ * second-nearest particle of the near leaves (zero distances skipped, g ignored; nearest if only one; lowest() if
+ * none) and squared distance to the nearest body segment of the near leaves (+inf if none). out = (eps2h, h2). */
+void vvo_eps2h_h2_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, const double* xy, int64_t npts,
+                     double* out) {
+    for (int64_t q = 0; q < npts; q++) {
+        const double px = xy[2 * q], py = xy[2 * q + 1];
+        const int64_t l = t->leaf[vvo_find_node(t, px, py)];
+        double res1 = INFINITY, res2 = INFINITY, hh = INFINITY;
+        for (int64_t k = t->near_ptr[l]; k < t->near_ptr[l + 1]; k++) {
+            int64_t nn = t->leaf_node[t->near_idx[k]];
+            for (int64_t j = t->vfirst[nn]; j < t->vlast[nn]; j++) {
+                double dx = px - p->x[j], dy = py - p->y[j];
+                double d = dx * dx + dy * dy;
+                if (!d) continue;
+                else if (d < res1) { res2 = res1; res1 = d; }
+                else if (d < res2) res2 = d;
+            }
+            for (int64_t k2 = t->sfirst[nn]; k2 < t->slast[nn]; k2++) {
+                int64_t s = t->seg_perm[k2];
+                double dx = px - b->rx[s], dy = py - b->ry[s];
+                hh = dmin(hh, dx * dx + dy * dy);
+            }
+        }
+        out[2 * q] = isfinite(res2) ? res2 : (isfinite(res1) ? res1 : -DBL_MAX);
+        out[2 * q + 1] = hh;
+    }
+}
+
 /* ------------------------------------------------------------------ diffusive */
 
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)

@@ -75,6 +75,9 @@ void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double
 /* MConvectiveFast::velocity (MConvectiveFast.cpp:20-34) at npts points xy -> out (vx, vy pairs); needs ieps */
 void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double inf_vx, double inf_vy, double dt,
                      const double* sinks_xyg, int64_t nsink, const double* xy, int64_t npts, double* out);
+/* (MEpsilonFast::eps2h, MEpsilonFast::h2) of findNode(p), MEpsilonFast.cpp:66-107; out = npts pairs */
+void vvo_eps2h_h2_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, const double* xy, int64_t npts,
+                     double* out);
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
 /* advect, drop |g|<remove_eps, drop in-body (accumulating dead sums), zero v. Compacts p in place,
  * returns the new n; *cleaned = number removed by the in-body test */

@@ -56,6 +56,7 @@ def lib():
         L.vvo_convective.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double,
                                      C.c_double, C.c_double, C.c_void_p, C.c_int64]
         L.vvo_diffusive.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double]
+        L.vvo_eps2h_h2_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_velocity_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double,
                                       C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_move_and_clean.restype = C.c_int64
@@ -216,6 +217,12 @@ class Port:
         out = np.zeros_like(a)
         self.L.vvo_velocity_at(self.tree, C.byref(self.p), self._b(), inf_vx, inf_vy, dt, _ptr(s), s.shape[0],
                                _ptr(a), a.shape[0], _ptr(out))
+        return out
+
+    def eps2h_h2_at(self, xy):
+        a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros_like(a)
+        self.L.vvo_eps2h_h2_at(self.tree, C.byref(self.p), self._b(), _ptr(a), a.shape[0], _ptr(out))
         return out
 
     def diffusive(self, re):

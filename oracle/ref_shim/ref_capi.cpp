@@ -358,6 +358,16 @@ void vvr_velocity_at(void* h, const double* xy, size_t n, double* out) {
         out[2 * i] = v.x; out[2 * i + 1] = v.y;
     }
 }
+/* MEpsilonFast::eps2h / h2 (static, MEpsilonFast.cpp:66-107) with node = findNode(p): out = (eps2h, h2) pairs */
+void vvr_eps2h_h2_at(void* h, const double* xy, size_t n, double* out) {
+    Ctx* c = (Ctx*)h;
+    for (size_t i = 0; i < n; i++) {
+        TVec p(xy[2 * i], xy[2 * i + 1]);
+        const TSortedNode* node = c->tree->findNode(p);
+        out[2 * i] = MEpsilonFast::eps2h(*node, p);
+        out[2 * i + 1] = MEpsilonFast::h2(*node, p);
+    }
+}
 void vvr_diffusive(void* h, int vort, int heat) {
     Ctx* c = (Ctx*)h;
     if (vort) c->diff->process_vort_list();

@@ -258,6 +258,35 @@ def test_velocity_at_points(ctx, port, case):
         P.tree_destroy()
 
 
+@pytest.mark.parametrize("with_body", [False, True])
+def test_eps2h_h2_at_points(ctx, port, with_body):
+    """static MEpsilonFast::eps2h / h2 (MEpsilonFast.cpp:66-107) of findNode(p): order-free, so bit-exact"""
+    from vvflow_b200 import vvhd
+    rng = np.random.default_rng(41)
+    bodies = [cases.cylinder(0.5, 350)] if with_body else []
+    xyg = cases.around_cylinder(8000, sign="mixed", seed=23) if with_body else cases.cloud(30000, "gauss", "mixed", seed=22)
+    xyg[:40, :2] = xyg[40:80, :2]            # duplicates: zero distances are skipped, ties count twice
+    mn, mx = cases.tree_params(bodies)
+    P = port.Port(xyg=xyg, bodies=cases.port_bodies(port, bodies))
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    tr = vvhd.TSortedTree(S, 8, mn, mx)
+    eps = vvhd.MEpsilonFast(S, tr)
+    try:
+        P.tree_build(8, mn, mx); tr.build()
+        pts = _points_for(xyg, rng)
+        want = P.eps2h_h2_at(pts)
+        assert same(eps.eps2h(pts), want[:, 0]), "eps2h differs"
+        assert same(eps.h2(pts), want[:, 1]), "h2 differs"
+        assert with_body == bool(np.isfinite(want[:, 1]).any())
+        assert eps.eps2h(pts[3]) == want[3, 0]
+    finally:
+        if tr.built:
+            tr.destroy()
+        P.tree_destroy()
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

@@ -151,3 +151,24 @@ def test_velocity_at_matches_reference(port, ref):
         v2 = P.velocity_at(pts, 1.0, 0.25, 0.05)
         assert same(v1, v2), np.abs(v1 - v2).max()
         r.tree_destroy(); P.tree_destroy()
+
+
+def test_eps2h_h2_match_reference(port, ref):
+    """MEpsilonFast::eps2h / h2 (MEpsilonFast.cpp:66-107) of findNode(p): bit-exact against the compiled reference"""
+    rng = np.random.default_rng(6)
+    for with_body in (False, True):
+        xyg = cases.around_cylinder(4000, sign="mixed", seed=19) if with_body else cases.cloud(5000, "gauss", "mixed", seed=18)
+        r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+        if with_body:
+            r.add_cylinder(0.5, 350)
+        r.set_list(xyg)
+        mn, mx = r.tree_params(8)
+        r.tree_build()
+        pb = port.Bodies.from_ref(r) if with_body else None
+        P = port.Port(xyg=xyg, bodies=pb)
+        P.tree_build(8, mn, mx)
+        pts = _query_points(xyg, rng)
+        a, b = r.eps2h_h2_at(pts), P.eps2h_h2_at(pts)
+        assert same(a, b)
+        assert with_body == bool(np.isfinite(a[:, 1]).any())
+        r.tree_destroy(); P.tree_destroy()

@@ -990,6 +990,30 @@ int vvgpu_velocity_at(vvgpu_ctx* c, const double* xy, size_t npts, double inf_vx
     return 0;
 }
 
+int vvgpu_eps2h_h2_at(vvgpu_ctx* c, const double* xy, size_t npts, double* eps2h_h2_out) {
+    if (!c || (npts && (!xy || !eps2h_h2_out))) return fail(c, VVGPU_EINVAL, "eps2h_h2_at: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "TTree::findNode(): tree is not built");
+    if (npts == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* dxy = c->pt_xy.get<double>(2 * npts, &ok);
+    double* dout = c->pt_out.get<double>(2 * npts, &ok);
+    int* derr = c->d_err.get<int>(4, &ok);
+    NEED(ok);
+    CK(cudaMemcpyAsync(dxy, xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(derr, 0, 4 * sizeof(int), c->stream));
+    ScalarArgs A;
+    A.T = c->T(); A.P = c->ps[c->cur].view(); A.npts = (int)npts; A.xy = dxy; A.out = dout; A.farc = c->farc;
+    A.seg_perm = c->t_segperm[c->segcur].as<int>(); A.srx = c->s_rx.as<double>(); A.sry = c->s_ry.as<double>();
+    A.err = derr;
+    k_eps2h_h2_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
+    CK(cudaMemcpyAsync(eps2h_h2_out, dout, 2 * npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "eps2h_h2_at: traversal stack overflow");
+    return 0;
+}
+
 int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
     if (!c) return VVGPU_EINVAL;
     if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");

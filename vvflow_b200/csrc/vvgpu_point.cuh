@@ -129,4 +129,97 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_velocity_at(PointArgs A) {
     if (lane == 0) { A.out[2 * q] = vx + A.inf_vx; A.out[2 * q + 1] = vy + A.inf_vy; }
 }
 
+// MEpsilonFast::eps2h and ::h2 (static, libvvhd/src/MEpsilonFast.cpp:66-107) for node = findNode(p): the squared
+// distance from p to the second-nearest particle of the leaf's near leaves (zero distances skipped, g ignored) and to
+// the nearest body segment listed in them. Both are order-free (two smallest of a multiset / a minimum), so the
+// result is the reference's bit for bit; distances use the uncontracted VV_ operations.
+struct ScalarArgs {
+    TreeDev T;
+    Particles P;
+    int npts;
+    const double* xy;
+    double* out;          // npts x 2: eps2h, h2
+    double farc;
+    const int* seg_perm;
+    const double *srx, *sry;
+    int* err;
+};
+
+__device__ __forceinline__ void two_smallest(double d, double& r1, double& r2) {
+    if (d < r1) { r2 = r1; r1 = d; }
+    else if (d < r2) r2 = d;
+}
+
+__global__ void __launch_bounds__(kPtWarps * 32) k_eps2h_h2_at(ScalarArgs A) {
+    __shared__ int stack[kPtWarps][kPtStack];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * kPtWarps + warp;
+    if (q >= A.npts) return;
+    const TreeDev& T = A.T;
+    const double px = A.xy[2 * q], py = A.xy[2 * q + 1];
+    int leaf = 0;
+    while (T.ch1[leaf] >= 0) {
+        const int c = T.ch1[leaf];
+        leaf = T.axis[leaf] ? ((px < T.x[leaf]) ? c : c + 1) : ((py < T.y[leaf]) ? c : c + 1);
+    }
+    const double lcx = T.x[leaf], lcy = T.y[leaf], lh = T.h[leaf], lw = T.w[leaf];
+    int* st = stack[warp];
+    if (lane == 0) st[0] = 0;
+    int size = 1;
+    __syncwarp();
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double r1 = inf, r2 = inf, hh = inf;
+    while (size > 0) {
+        const int take = (size > kPtStack - 80) ? 1 : min(size, 32);
+        int n = -1;
+        if (lane < take) n = st[size - 1 - lane];
+        size -= take;
+        __syncwarp();
+        bool push = false, nearleaf = false;
+        int c1 = -1;
+        if (n >= 0) {
+            c1 = T.ch1[n];
+            if (!is_far(T.x[n], T.y[n], VV_ADD(T.h[n], T.w[n]), lcx, lcy, lh, lw, A.farc)) {
+                if (c1 >= 0) push = true; else nearleaf = true;
+            }
+        }
+        const u32 pb = __ballot_sync(0xffffffffu, push);
+        const int npush = 2 * __popc(pb);
+        if (size + npush > kPtStack) {
+            if (lane == 0) atomicOr(A.err, 2);
+            return;
+        }
+        if (push) {
+            const int off = size + 2 * __popc(pb & lanemask_lt());
+            st[off] = c1 + 1; st[off + 1] = c1;
+        }
+        size += npush;
+        for (u32 nb = __ballot_sync(0xffffffffu, nearleaf); nb; nb &= nb - 1) {
+            const int ln = __shfl_sync(0xffffffffu, n, __ffs(nb) - 1);
+            for (int j = T.first[ln] + lane; j < T.last[ln]; j += 32) {
+                const double dx = VV_SUB(px, A.P.x[j]), dy = VV_SUB(py, A.P.y[j]);
+                const double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
+                if (d != 0) two_smallest(d, r1, r2);
+            }
+            for (int k = T.sfirst[ln] + lane; k < T.slast[ln]; k += 32) {
+                const int s = A.seg_perm[k];
+                const double dx = VV_SUB(px, A.srx[s]), dy = VV_SUB(py, A.sry[s]);
+                hh = fmin(hh, VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy)));
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // merge the lanes' two smallest (multiset semantics: ties count twice)
+        const double a = __shfl_xor_sync(0xffffffffu, r1, o), b = __shfl_xor_sync(0xffffffffu, r2, o);
+        two_smallest(a, r1, r2);
+        two_smallest(b, r1, r2);
+        hh = fmin(hh, __shfl_xor_sync(0xffffffffu, hh, o));
+    }
+    if (lane == 0) {
+        A.out[2 * q] = isfinite(r2) ? r2 : (isfinite(r1) ? r1 : -DBL_MAX);   // numeric_limits<double>::lowest(), :91
+        A.out[2 * q + 1] = hh;
+    }
+}
+
 }  // namespace vv

@@ -226,6 +226,20 @@ class MEpsilonFast(_Module):
     def Merged(self):
         return self.merged_
 
+    def eps2h(self, p):
+        """static MEpsilonFast::eps2h(node, p) with node = findNode(p), MEpsilonFast.cpp:66-93; p is (x, y) or (n, 2)"""
+        self._need_tree("TTree::findNode()")
+        pts = np.asarray(p, dtype=np.float64)
+        r = self.S.ctx.eps2h_h2_at(pts.reshape(-1, 2))[:, 0]
+        return r[0] if pts.ndim == 1 else r
+
+    def h2(self, p):
+        """static MEpsilonFast::h2(node, p) with node = findNode(p), MEpsilonFast.cpp:95-107"""
+        self._need_tree("TTree::findNode()")
+        pts = np.asarray(p, dtype=np.float64)
+        r = self.S.ctx.eps2h_h2_at(pts.reshape(-1, 2))[:, 1]
+        return r[0] if pts.ndim == 1 else r
+
 
 class MConvectiveFast(_Module):
     def process_all_lists(self):

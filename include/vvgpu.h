@@ -120,6 +120,12 @@ int vvgpu_velocity_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double inf_
  * second-nearest particle and to the nearest body segment (+inf without bodies) of the leaf's near leaves.
  * eps2h_h2_out receives npts (eps2h, h2) pairs; bit-identical to the reference. ---------------------------- */
 int vvgpu_eps2h_h2_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double* eps2h_h2_out);
+/* ---- MConvectiveFast::NodeInfluence(*tree->findNode(seg.r), seg), MConvectiveFast.cpp:398-418:
+ * the free vortices' term of the slip equation's right-hand side (fillSlipEquationForSegment, :459-467), for every
+ * segment passed to vvgpu_set_bodies, in that order. Uses the _1_eps the particles carry (the reference solves the
+ * SLAE before CalcEpsilonFast, so these are last step's values that came in with the TObj records). With it
+ * calc_circulation needs no CPU tree: see INTEGRATION.md §2b. ------------------------------------------------ */
+int vvgpu_node_influence(vvgpu_ctx* ctx, double* out_nseg);
 /* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
  * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
 int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);

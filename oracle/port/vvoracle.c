@@ -535,6 +535,60 @@ void vvo_eps2h_h2_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b,
     }
 }
 
+/* MConvectiveFast::_2PI_Xi_g (MConvectiveFast.cpp:286-310) with _2PI_Xi_g_near (:275-279) and _2PI_Xi_g_dist
+ * (:281-284): 2 pi Xi_gamma of a vortex at (px, py) with core radius rd on segment s */
+static double xi_g_dist(double px, double py, double p1x, double p1y, double p2x, double p2y) {
+    return 0.5 * log((sqr(px - p2x) + sqr(py - p2y)) / (sqr(px - p1x) + sqr(py - p1y)));
+}
+static double xi_g_near(double px, double py, double pcx, double pcy, double dlx, double dly, double rd) {
+    return ((pcx - px) * dlx + (pcy - py) * dly) / sqr(rd);
+}
+static double xi_g(double px, double py, const vvo_bodies* b, int64_t s, double rd) {
+    const double cx = b->cx[s], cy = b->cy[s], dlx = b->dlx[s], dly = b->dly[s], rx = b->rx[s], ry = b->ry[s];
+    double rd_sqr = sqr(rd);
+    double dr1_sqr = sqr(px - cx) + sqr(py - cy);
+    double dr2_sqr = sqr(px - cx - dlx) + sqr(py - cy - dly);
+    if (dr1_sqr >= rd_sqr && dr2_sqr >= rd_sqr) return 0.5 * log(dr2_sqr / dr1_sqr);
+    else if (dr1_sqr <= rd_sqr && dr2_sqr <= rd_sqr) return xi_g_near(px, py, rx, ry, dlx, dly, rd);
+    else {
+        double a0 = dlx * dlx + dly * dly;
+        double b0 = (px - rx) * dlx + (py - ry) * dly;
+        double d = sqrt(b0 * b0 - a0 * ((sqr(px - rx) + sqr(py - ry)) - rd * rd));
+        double k = (b0 + d) / a0; if ((k <= -0.5) || (k >= 0.5)) k = (b0 - d) / a0;
+        double p3x = rx + k * dlx, p3y = ry + k * dly;
+        if (dr1_sqr < rd_sqr)
+            return xi_g_near(px, py, 0.5 * (p3x + cx), 0.5 * (p3y + cy), p3x - cx, p3y - cy, rd) +
+                   xi_g_dist(px, py, p3x, p3y, cx + dlx, cy + dly);
+        else
+            return xi_g_dist(px, py, cx, cy, p3x, p3y) +
+                   xi_g_near(px, py, 0.5 * (cx + dlx + p3x), 0.5 * (cy + dly + p3y), cx + dlx - p3x, cy + dly - p3y, rd);
+    }
+}
+
+/* MConvectiveFast::NodeInfluence(*findNode(seg.r), seg), MConvectiveFast.cpp:398-418, for every segment: the free
+ * vortices' term of the slip equation's right-hand side (fillSlipEquationForSegment, :459-467) */
+void vvo_node_influence(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double* out) {
+    for (int64_t s = 0; s < b->nseg; s++) {
+        const int64_t l = t->leaf[vvo_find_node(t, b->rx[s], b->ry[s])];
+        double res = 0;
+        for (int64_t k = t->near_ptr[l]; k < t->near_ptr[l + 1]; k++) {
+            int64_t nn = t->leaf_node[t->near_idx[k]];
+            for (int64_t j = t->vfirst[nn]; j < t->vlast[nn]; j++) {
+                if (!p->g[j]) continue;
+                res += xi_g(p->x[j], p->y[j], b, s, 1. / p->ieps[j]) * p->g[j];
+            }
+        }
+        const double c2x = b->cx[s] + b->dlx[s], c2y = b->cy[s] + b->dly[s];
+        for (int64_t k = t->far_ptr[l]; k < t->far_ptr[l + 1]; k++) {
+            const double* P = t->cmp + 3 * t->far_idx[k];
+            const double* M = t->cmm + 3 * t->far_idx[k];
+            res += xi_g_dist(P[0], P[1], b->cx[s], b->cy[s], c2x, c2y) * P[2];
+            res += xi_g_dist(M[0], M[1], b->cx[s], b->cy[s], c2x, c2y) * M[2];
+        }
+        out[s] = res * C_1_2PI;
+    }
+}
+
 /* ------------------------------------------------------------------ diffusive */
 
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)

@@ -78,6 +78,8 @@ void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b,
 /* (MEpsilonFast::eps2h, MEpsilonFast::h2) of findNode(p), MEpsilonFast.cpp:66-107; out = npts pairs */
 void vvo_eps2h_h2_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, const double* xy, int64_t npts,
                      double* out);
+/* MConvectiveFast::NodeInfluence(*findNode(seg.r), seg) of every segment, MConvectiveFast.cpp:398-418 -> out[nseg] */
+void vvo_node_influence(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double* out);
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
 /* advect, drop |g|<remove_eps, drop in-body (accumulating dead sums), zero v. Compacts p in place,
  * returns the new n; *cleaned = number removed by the in-body test */

@@ -57,6 +57,7 @@ def lib():
                                      C.c_double, C.c_double, C.c_void_p, C.c_int64]
         L.vvo_diffusive.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double]
         L.vvo_eps2h_h2_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p, C.c_int64, C.c_void_p]
+        L.vvo_node_influence.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p]
         L.vvo_velocity_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double,
                                       C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_move_and_clean.restype = C.c_int64
@@ -223,6 +224,12 @@ class Port:
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
         out = np.zeros_like(a)
         self.L.vvo_eps2h_h2_at(self.tree, C.byref(self.p), self._b(), _ptr(a), a.shape[0], _ptr(out))
+        return out
+
+    def node_influence(self):
+        out = np.zeros(int(self.bodies.nseg) if self.bodies is not None else 0)
+        if out.shape[0]:
+            self.L.vvo_node_influence(self.tree, C.byref(self.p), self._b(), _ptr(out))
         return out
 
     def diffusive(self, re):

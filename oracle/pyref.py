@@ -60,6 +60,7 @@ def _load():
         "vvr_convective": (None, [C.c_void_p]),
         "vvr_velocity_at": (None, [C.c_void_p, _dp, C.c_size_t, _dp]),
         "vvr_eps2h_h2_at": (None, [C.c_void_p, _dp, C.c_size_t, _dp]),
+        "vvr_node_influence": (None, [C.c_void_p, _dp]),
         "vvr_diffusive": (None, [C.c_void_p, C.c_int, C.c_int]),
         "vvr_move_and_clean": (C.c_size_t, [C.c_void_p, C.c_int]),
         "vvr_calc_circulation": (None, [C.c_void_p]),
@@ -238,6 +239,12 @@ class Ref:
         a = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
         out = np.zeros_like(a)
         self.L.vvr_eps2h_h2_at(self.h, a, a.shape[0], out)
+        return out
+
+    def node_influence(self):
+        """MConvectiveFast::NodeInfluence(findNode(seg.r), seg) of every segment (SLAE right-hand side, vortex term)"""
+        out = np.zeros(self.segments().shape[0])
+        self.L.vvr_node_influence(self.h, out)
         return out
 
     def diffusive(self, vort=True, heat=False):

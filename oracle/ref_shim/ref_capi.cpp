@@ -22,7 +22,9 @@
 #undef private
 #include "TSpace.hpp"
 #include "MEpsilonFast.hpp"
+#define private public   /* NodeInfluence (the vortex term of the SLAE right-hand side) is a private member */
 #include "MConvectiveFast.hpp"
+#undef private
 #include "MDiffusiveFast.hpp"
 #include "MFlowmove.hpp"
 
@@ -367,6 +369,15 @@ void vvr_eps2h_h2_at(void* h, const double* xy, size_t n, double* out) {
         out[2 * i] = MEpsilonFast::eps2h(*node, p);
         out[2 * i + 1] = MEpsilonFast::h2(*node, p);
     }
+}
+/* MConvectiveFast::NodeInfluence(*findNode(seg.r), seg) for every segment, in Space::BodyList order
+ * (the vortex term of fillSlipEquationForSegment, MConvectiveFast.cpp:459-467) */
+void vvr_node_influence(void* h, double* out) {
+    Ctx* c = (Ctx*)h;
+    size_t k = 0;
+    for (auto& lbody : c->S.BodyList)
+        for (auto& latt : lbody->alist)
+            out[k++] = c->conv->NodeInfluence(*c->tree->findNode(latt.r), latt);
 }
 void vvr_diffusive(void* h, int vort, int heat) {
     Ctx* c = (Ctx*)h;

@@ -287,6 +287,37 @@ def test_eps2h_h2_at_points(ctx, port, with_body):
         P.tree_destroy()
 
 
+@pytest.mark.parametrize("spread", [0.05, 0.3])
+def test_node_influence(ctx, port, spread):
+    """SURVEY 8(f) row 1: MConvectiveFast::NodeInfluence (MConvectiveFast.cpp:398-418) for every segment, the vortex
+    term of the SLAE right-hand side. Oracle pinned bit-exact to the compiled reference; 1e-10 norm-wise here
+    (log / sqrt of the device library, order of summation)."""
+    from vvflow_b200 import vvhd
+    bodies = [cases.cylinder(0.5, 350), cases.cylinder(0.3, 120, 1.6, 0.2)]
+    xyg = cases.around_cylinder(9000, sign="mixed", seed=37, spread=spread)
+    mn, mx = cases.tree_params(bodies)
+    P = port.Port(xyg=xyg, bodies=cases.port_bodies(port, bodies))
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    tr = vvhd.TSortedTree(S, 8, mn, mx)
+    eps, conv = vvhd.MEpsilonFast(S, tr), vvhd.MConvectiveFast(S, tr)
+    with pytest.raises(RuntimeError):
+        conv.NodeInfluence()
+    try:
+        P.tree_build(8, mn, mx); tr.build()
+        eps.CalcEpsilonFast(False); P.epsilon(False)          # core radii
+        want = P.node_influence()
+        got = conv.NodeInfluence()
+        assert got.shape == want.shape == (470,)
+        assert np.isfinite(want).all() and np.abs(want).max() > 0
+        assert relerr(got, want) <= VTOL, relerr(got, want)
+    finally:
+        if tr.built:
+            tr.destroy()
+        P.tree_destroy()
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

@@ -172,3 +172,23 @@ def test_eps2h_h2_match_reference(port, ref):
         assert same(a, b)
         assert with_body == bool(np.isfinite(a[:, 1]).any())
         r.tree_destroy(); P.tree_destroy()
+
+
+def test_node_influence_matches_reference(port, ref):
+    """MConvectiveFast::NodeInfluence (MConvectiveFast.cpp:398-418, the free vortices' term of the SLAE right-hand
+    side) for every segment of a cylinder: the port against the compiled reference. Particles close to the wall make
+    every branch of _2PI_Xi_g (:286-310) run."""
+    xyg = cases.around_cylinder(6000, sign="mixed", seed=29, spread=0.05)
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    r.add_cylinder(0.5, 350)
+    r.set_list(xyg)
+    mn, mx = r.tree_params(8)
+    r.tree_build()
+    pb = port.Bodies.from_ref(r)
+    P = port.Port(xyg=xyg, bodies=pb)
+    P.tree_build(8, mn, mx)
+    assert r.epsilon(True) == P.epsilon(True)      # core radii rd = 1 / _1_eps
+    a, b = r.node_influence(), P.node_influence()
+    assert a.shape == (350,) and np.isfinite(a).all() and np.abs(a).max() > 0
+    assert same(a, b), np.abs(a - b).max()
+    r.tree_destroy(); P.tree_destroy()

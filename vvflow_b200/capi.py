@@ -18,7 +18,7 @@ SYMBOLS = [
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
-    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_diffusive", "vvgpu_move_and_clean",
+    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_diffusive", "vvgpu_move_and_clean",
     "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_shard_bounds", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
 ]
@@ -72,6 +72,7 @@ def load():
         "vvgpu_convective": [vp, C.c_double, C.c_double, C.c_double, dp, sz],
         "vvgpu_velocity_at": [vp, dp, sz, C.c_double, C.c_double, C.c_double, dp, sz, dp],
         "vvgpu_eps2h_h2_at": [vp, dp, sz, dp],
+        "vvgpu_node_influence": [vp, dp],
         "vvgpu_diffusive": [vp, C.c_double, dp],
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
         "vvgpu_set_shard": [vp, C.c_int, C.c_int],
@@ -242,6 +243,12 @@ class Context:
         out = np.zeros_like(a)
         self._ck(self.L.vvgpu_eps2h_h2_at(self.h, _p(a), a.shape[0], _p(out)))
         return out
+
+    def node_influence(self):
+        """MConvectiveFast::NodeInfluence(findNode(seg.r), seg) for every segment set with set_bodies"""
+        out = np.zeros(max(1, getattr(self, "nseg", 0)))
+        self._ck(self.L.vvgpu_node_influence(self.h, _p(out)))
+        return out[: getattr(self, "nseg", 0)]
 
     def diffusive(self, re, want_fric=True):
         fric = np.zeros(max(1, getattr(self, "nseg", 0))) if want_fric and getattr(self, "nseg", 0) else None

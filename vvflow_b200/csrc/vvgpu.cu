@@ -1014,6 +1014,26 @@ int vvgpu_eps2h_h2_at(vvgpu_ctx* c, const double* xy, size_t npts, double* eps2h
     return 0;
 }
 
+int vvgpu_node_influence(vvgpu_ctx* c, double* out_nseg) {
+    if (!c || (c->nseg && !out_nseg)) return fail(c, VVGPU_EINVAL, "node_influence: bad argument");
+    if (!c->built) return fail(c, VVGPU_ESTATE, "TTree::findNode(): tree is not built");
+    if (c->nseg == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* dout = c->pt_out.get<double>(c->nseg, &ok);
+    int* derr = c->d_err.get<int>(4, &ok);
+    NEED(ok);
+    CK(cudaMemsetAsync(derr, 0, 4 * sizeof(int), c->stream));
+    SegInflArgs A{c->T(), c->ps[c->cur].view(), c->nseg, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(),
+                  c->s_cy.as<double>(), c->s_dlx.as<double>(), c->s_dly.as<double>(), dout, c->farc, derr};
+    k_node_influence<<<cdiv(c->nseg, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
+    CK(cudaMemcpyAsync(out_nseg, dout, c->nseg * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "node_influence: traversal stack overflow");
+    return 0;
+}
+
 int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
     if (!c) return VVGPU_EINVAL;
     if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");

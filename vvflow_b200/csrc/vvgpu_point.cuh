@@ -222,4 +222,112 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_eps2h_h2_at(ScalarArgs A) {
     }
 }
 
+// SURVEY §8(f) row 1 — MConvectiveFast::NodeInfluence(*findNode(seg.r), seg) (libvvhd/src/MConvectiveFast.cpp:398-418),
+// the free vortices' term of the slip equation's right-hand side (fillSlipEquationForSegment, :459-467): near
+// vortices through 2 pi Xi_gamma (_2PI_Xi_g, :286-310, three branches on the core radius rd = 1 / _1_eps), far nodes
+// as two monopoles through the logarithmic far form (_2PI_Xi_g_dist, :281-284). One warp per segment; with it the
+// SLAE stage needs the DEVICE tree only (the reference rebuilds its CPU tree every step just for this, vvflow.cpp:218).
+struct SegInflArgs {
+    TreeDev T;
+    Particles P;
+    int nseg;
+    const double *srx, *sry, *scx, *scy, *sdlx, *sdly;
+    double* out;
+    double farc;
+    int* err;
+};
+
+__device__ __forceinline__ double xi_g_dist(double px, double py, double p1x, double p1y, double p2x, double p2y) {
+    const double ax = px - p2x, ay = py - p2y, bx = px - p1x, by = py - p1y;
+    return 0.5 * log((ax * ax + ay * ay) / (bx * bx + by * by));
+}
+__device__ __forceinline__ double xi_g_near(double px, double py, double pcx, double pcy, double dlx, double dly, double rd) {
+    return ((pcx - px) * dlx + (pcy - py) * dly) / (rd * rd);
+}
+__device__ __forceinline__ double xi_g(double px, double py, double cx, double cy, double dlx, double dly, double rx, double ry,
+                                       double rd) {
+    // the branch decisions compare exactly what the reference compares (uncontracted)
+    const double rd_sqr = VV_MUL(rd, rd);
+    const double d1x = VV_SUB(px, cx), d1y = VV_SUB(py, cy);
+    const double dr1_sqr = VV_ADD(VV_MUL(d1x, d1x), VV_MUL(d1y, d1y));
+    const double d2x = VV_SUB(VV_SUB(px, cx), dlx), d2y = VV_SUB(VV_SUB(py, cy), dly);
+    const double dr2_sqr = VV_ADD(VV_MUL(d2x, d2x), VV_MUL(d2y, d2y));
+    if (dr1_sqr >= rd_sqr && dr2_sqr >= rd_sqr) return 0.5 * log(dr2_sqr / dr1_sqr);
+    if (dr1_sqr <= rd_sqr && dr2_sqr <= rd_sqr) return xi_g_near(px, py, rx, ry, dlx, dly, rd);
+    const double a0 = dlx * dlx + dly * dly;
+    const double ex = px - rx, ey = py - ry;
+    const double b0 = ex * dlx + ey * dly;
+    const double d = sqrt(b0 * b0 - a0 * ((ex * ex + ey * ey) - rd * rd));
+    double k = (b0 + d) / a0;
+    if ((k <= -0.5) || (k >= 0.5)) k = (b0 - d) / a0;
+    const double p3x = rx + k * dlx, p3y = ry + k * dly;
+    if (dr1_sqr < rd_sqr)
+        return xi_g_near(px, py, 0.5 * (p3x + cx), 0.5 * (p3y + cy), p3x - cx, p3y - cy, rd) +
+               xi_g_dist(px, py, p3x, p3y, cx + dlx, cy + dly);
+    return xi_g_dist(px, py, cx, cy, p3x, p3y) +
+           xi_g_near(px, py, 0.5 * (cx + dlx + p3x), 0.5 * (cy + dly + p3y), cx + dlx - p3x, cy + dly - p3y, rd);
+}
+
+__global__ void __launch_bounds__(kPtWarps * 32) k_node_influence(SegInflArgs A) {
+    __shared__ int stack[kPtWarps][kPtStack];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * kPtWarps + warp;
+    if (s >= A.nseg) return;
+    const TreeDev& T = A.T;
+    const double rx = A.srx[s], ry = A.sry[s], cx = A.scx[s], cy = A.scy[s], dlx = A.sdlx[s], dly = A.sdly[s];
+    int leaf = 0;
+    while (T.ch1[leaf] >= 0) {   // stree::findNode(seg.r)
+        const int c = T.ch1[leaf];
+        leaf = T.axis[leaf] ? ((rx < T.x[leaf]) ? c : c + 1) : ((ry < T.y[leaf]) ? c : c + 1);
+    }
+    const double lcx = T.x[leaf], lcy = T.y[leaf], lh = T.h[leaf], lw = T.w[leaf];
+    int* st = stack[warp];
+    if (lane == 0) st[0] = 0;
+    int size = 1;
+    __syncwarp();
+    double res = 0;
+    while (size > 0) {
+        const int take = (size > kPtStack - 80) ? 1 : min(size, 32);
+        int n = -1;
+        if (lane < take) n = st[size - 1 - lane];
+        size -= take;
+        __syncwarp();
+        bool push = false, nearleaf = false;
+        int c1 = -1;
+        if (n >= 0) {
+            c1 = T.ch1[n];
+            if (is_far(T.x[n], T.y[n], VV_ADD(T.h[n], T.w[n]), lcx, lcy, lh, lw, A.farc)) {
+                const double* Pm = T.cmp + 3ll * n;
+                const double* Mm = T.cmm + 3ll * n;
+                res += xi_g_dist(Pm[0], Pm[1], cx, cy, cx + dlx, cy + dly) * Pm[2];
+                res += xi_g_dist(Mm[0], Mm[1], cx, cy, cx + dlx, cy + dly) * Mm[2];
+            } else if (c1 >= 0) push = true;
+            else nearleaf = true;
+        }
+        const u32 pb = __ballot_sync(0xffffffffu, push);
+        const int npush = 2 * __popc(pb);
+        if (size + npush > kPtStack) {
+            if (lane == 0) atomicOr(A.err, 2);
+            return;
+        }
+        if (push) {
+            const int off = size + 2 * __popc(pb & lanemask_lt());
+            st[off] = c1 + 1; st[off + 1] = c1;
+        }
+        size += npush;
+        for (u32 nb = __ballot_sync(0xffffffffu, nearleaf); nb; nb &= nb - 1) {
+            const int ln = __shfl_sync(0xffffffffu, n, __ffs(nb) - 1);
+            for (int j = T.first[ln] + lane; j < T.last[ln]; j += 32) {
+                const double g = A.P.g[j];
+                if (g == 0) continue;   // `if (!lobj->g) {continue;}`, :406
+                res += xi_g(A.P.x[j], A.P.y[j], cx, cy, dlx, dly, rx, ry, 1. / A.P.ie[j]) * g;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+    if (lane == 0) A.out[s] = res * k1_2Pi;
+}
+
 }  // namespace vv

@@ -224,6 +224,17 @@ class MConvectiveFast {
                     "vvgpu_convective");
         }
 
+        // MConvectiveFast::NodeInfluence(*tree->findNode(seg.r), seg) (MConvectiveFast.cpp:398-418) for every segment
+        // in BodyList order: the term fillSlipEquationForSegment (:459-467) subtracts from the right-hand side.
+        // With it the SLAE stage runs on the device tree; INTEGRATION.md §2b shows the three-line patch.
+        std::vector<double> NodeInfluence() const {
+            if (!tree->isBuilt()) throw std::invalid_argument("TTree::findNode(): tree is not built");
+            Device& D = *Device::of(S);
+            std::vector<double> rhs(S->total_segment_count());
+            D.check(vvgpu_node_influence(D.ctx, rhs.empty() ? nullptr : rhs.data()), "vvgpu_node_influence");
+            return rhs;
+        }
+
         TVec velocity(TVec p) const {   // MConvectiveFast.cpp:20-34 (sensors, X* rasters)
             TVec v = TVec(0, 0);
             velocity(&p, 1, &v);

@@ -248,6 +248,13 @@ class MConvectiveFast(_Module):
         S.ctx.convective(S.inf_vx, S.inf_vy, S.dt, S.SourceList if len(S.SourceList) else None)
         S._dev_newer = True
 
+    def NodeInfluence(self):
+        """double MConvectiveFast::NodeInfluence(const TSortedNode&, const TAtt&) const (MConvectiveFast.cpp:398-418)
+        evaluated for Node = findNode(seg.r) of EVERY segment in BodyList order: the free vortices' term that
+        fillSlipEquationForSegment (:459-467) subtracts from the right-hand side."""
+        self._need_tree("TTree::findNode()")
+        return self.S.ctx.node_influence()
+
     def velocity(self, p):
         """TVec MConvectiveFast::velocity(TVec p) const, MConvectiveFast.cpp:20-34; `p` is (x, y) or an (n, 2)
         array of points (the X* evaluators call it per raster point). Raises like stree::findNode when the tree

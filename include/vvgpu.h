@@ -68,6 +68,10 @@ const char* vvgpu_last_error(const vvgpu_ctx* ctx);
 int vvgpu_set_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t n);
 /* 24-byte (x,y,g) records as Space::load_list_bin reads them (TSpace.cpp:161-175); v,_1_eps = 0 */
 int vvgpu_set_particles_xyg(vvgpu_ctx* ctx, int list, const double* xyg, size_t n);
+/* append n records behind the particles that are resident on the device (what
+ * MFlowmove::vortex_shed adds per step, MFlowmove.cpp:217-235, without re-uploading the whole list). The caller-order
+ * index (vvgpu_get_permutation) of the appended particles continues after the last one handed over so far. */
+int vvgpu_append_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t n);
 int vvgpu_particle_count(vvgpu_ctx* ctx, int list, size_t* n);
 /* current device order (after tree_build: the reference's in-place permuted order) */
 int vvgpu_get_particles(vvgpu_ctx* ctx, int list, vvgpu_obj* out, size_t cap, size_t* n);

@@ -318,6 +318,45 @@ def test_node_influence(ctx, port, spread):
         P.tree_destroy()
 
 
+def _gpu_step(ctx, dt=0.05, re=600.0):
+    ctx.tree_build(8, 0.0)
+    ctx.epsilon(True)
+    ctx.convective(1.0, 0.0, dt)
+    ctx.diffusive(re, want_fric=False)
+    ctx.tree_destroy()
+    ctx.move_and_clean(dt)
+
+
+def test_append_particles_resident_loop(ctx):
+    from vvflow_b200 import capi
+    """SURVEY 8(f) row 2: the list stays on the device between steps and newly shed vortices are appended
+    (vvgpu_append_particles) instead of re-uploading everything. The step on (resident survivors + appended) must be
+    bit-identical to the step on the same list uploaded afresh, and the caller-order indices must continue."""
+    a = np.zeros((20000, 6)); a[:, :3] = cases.cloud(20000, "gauss", "mixed", seed=51)
+    b = np.zeros((3000, 6)); b[:, :3] = cases.cloud(3000, "uniform", "mixed", seed=52); b[:, 5] = 7.5   # carries an _1_eps
+    ctx.set_particles(a)
+    _gpu_step(ctx)
+    surv = ctx.get_particles()
+    ctx.append_particles(b)
+    both = ctx.get_particles()
+    assert both.shape[0] == surv.shape[0] + 3000
+    assert same(both[: surv.shape[0]], surv) and same(both[surv.shape[0]:], b)
+    perm = ctx.get_permutation()
+    assert np.array_equal(perm[surv.shape[0]:], 20000 + np.arange(3000))
+    ctx.append_particles(np.zeros((0, 6)))              # appending nothing is a no-op
+    assert ctx.n == both.shape[0]
+    _gpu_step(ctx)
+    resident = ctx.get_particles()
+    ctx.set_particles(both)
+    _gpu_step(ctx)
+    fresh = ctx.get_particles()
+    assert resident.shape == fresh.shape and same(resident, fresh)
+    ctx.tree_build(8, 0.0)
+    with pytest.raises(capi.VVGpuError):
+        ctx.append_particles(b)                         # the tree holds positions into the list
+    ctx.tree_destroy()
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

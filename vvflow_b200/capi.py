@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libvvgpu.so")
 # every symbol include/vvgpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vvgpu_create", "vvgpu_destroy", "vvgpu_strerror", "vvgpu_last_error",
-    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_particle_count", "vvgpu_get_particles",
+    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_append_particles", "vvgpu_particle_count", "vvgpu_get_particles",
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
@@ -56,6 +56,7 @@ def load():
         "vvgpu_create": [C.c_int, C.POINTER(vp)],
         "vvgpu_set_particles": [vp, C.c_int, dp, sz],
         "vvgpu_set_particles_xyg": [vp, C.c_int, dp, sz],
+        "vvgpu_append_particles": [vp, C.c_int, dp, sz],
         "vvgpu_particle_count": [vp, C.c_int, C.POINTER(sz)],
         "vvgpu_get_particles": [vp, C.c_int, dp, sz, C.POINTER(sz)],
         "vvgpu_get_permutation": [vp, C.c_int, ip, sz],
@@ -134,6 +135,11 @@ class Context:
     def set_particles(self, rec48):
         a = np.ascontiguousarray(rec48, dtype=np.float64).reshape(-1, 6)
         self._ck(self.L.vvgpu_set_particles(self.h, 0, _p(a), a.shape[0]))
+
+    def append_particles(self, rec48):
+        """append (n, 6) TObj records behind the resident particles (newly shed vortices)"""
+        a = np.ascontiguousarray(rec48, dtype=np.float64).reshape(-1, 6)
+        self._ck(self.L.vvgpu_append_particles(self.h, 0, _p(a), a.shape[0]))
 
     def set_particles_xyg(self, xyg):
         a = np.ascontiguousarray(xyg, dtype=np.float64).reshape(-1, 3)

@@ -62,6 +62,13 @@ struct PSet {  // one SoA particle set
         vx.get<double>(n, &ok); vy.get<double>(n, &ok); ie.get<double>(n, &ok); orig.get<int>(n, &ok);
         return ok;
     }
+    bool ensure_keep(size_t n, cudaStream_t st) {   // grow, keeping the resident particles
+        bool ok = true;
+        x.get_keep<double>(n, &ok, st); y.get_keep<double>(n, &ok, st); g.get_keep<double>(n, &ok, st);
+        vx.get_keep<double>(n, &ok, st); vy.get_keep<double>(n, &ok, st); ie.get_keep<double>(n, &ok, st);
+        orig.get_keep<int>(n, &ok, st);
+        return ok;
+    }
     void release() { x.release(); y.release(); g.release(); vx.release(); vy.release(); ie.release(); orig.release(); }
 };
 
@@ -78,6 +85,7 @@ struct vvgpu_ctx {
 
     // particles (vortex list)
     size_t n = 0;
+    size_t orig_next = 0;   // caller-order index of the next appended particle
     PSet ps[2];
     int cur = 0;
     Buf stage;  // AoS staging
@@ -573,6 +581,7 @@ static int set_particles_common(vvgpu_ctx* c, int list, const void* src, size_t 
     double* st = c->stage.get<double>(n * rec_doubles, &ok);
     if (!ok || !c->ps[c->cur].ensure(n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
     c->n = n;
+    c->orig_next = n;
     if (n) {
         CK(cudaMemcpyAsync(st, src, n * rec_doubles * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         if (rec_doubles == 6) k_unpack48<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
@@ -587,6 +596,25 @@ int vvgpu_set_particles(vvgpu_ctx* c, int list, const vvgpu_obj* objs, size_t n)
 }
 int vvgpu_set_particles_xyg(vvgpu_ctx* c, int list, const double* xyg, size_t n) {
     return set_particles_common(c, list, xyg, n, 3);
+}
+int vvgpu_append_particles(vvgpu_ctx* c, int list, const vvgpu_obj* objs, size_t n) {
+    if (!c || list != VVGPU_LIST_VORTEX || (!objs && n)) return fail(c, VVGPU_EINVAL, "append_particles: bad argument");
+    if (c->built) return fail(c, VVGPU_ESTATE, "append_particles while the tree is built (the tree holds positions into the list)");
+    if (n == 0) return 0;
+    if (c->n + n > (size_t)std::numeric_limits<int>::max() / 4) return fail(c, VVGPU_EINVAL, "append_particles: too many particles");
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* st = c->stage.get<double>(n * 6, &ok);
+    // grow with headroom: a shedding body appends a few hundred vortices every step
+    const size_t want = c->n + n;
+    if (!ok || !c->ps[c->cur].ensure_keep(want + want / 8, c->stream)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(st, objs, n * 48, cudaMemcpyHostToDevice, c->stream));
+    k_unpack48_at<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>(), (int)c->n,
+                                                       (int)c->orig_next); CKLAUNCH();
+    CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `objs`
+    c->n += n;
+    c->orig_next += n;
+    return 0;
 }
 int vvgpu_particle_count(vvgpu_ctx* c, int list, size_t* n) {
     if (!c || !n || list != VVGPU_LIST_VORTEX) return fail(c, VVGPU_EINVAL, "particle_count: bad argument");

@@ -93,6 +93,15 @@ __global__ void k_unpack48(int n, const double* __restrict__ rec, Particles P, i
     P.x[i] = r[0]; P.y[i] = r[1]; P.g[i] = r[2]; P.vx[i] = r[3]; P.vy[i] = r[4]; P.ie[i] = r[5];
     orig[i] = i;
 }
+// records appended behind the `at` resident ones (vvgpu_append_particles)
+__global__ void k_unpack48_at(int n, const double* __restrict__ rec, Particles P, int* orig, int at, int orig_base) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = rec + 6ll * i;
+    const int d = at + i;
+    P.x[d] = r[0]; P.y[d] = r[1]; P.g[d] = r[2]; P.vx[d] = r[3]; P.vy[d] = r[4]; P.ie[d] = r[5];
+    orig[d] = orig_base + i;
+}
 __global__ void k_unpack24(int n, const double* __restrict__ rec, Particles P, int* orig) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

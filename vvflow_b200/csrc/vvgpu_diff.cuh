@@ -24,9 +24,12 @@
 namespace vv {
 
 #ifndef VV_DF_MINB
-#define VV_DF_MINB 4
+#define VV_DF_MINB 2
 #endif
-constexpr int kDfWarps = 4;
+#ifndef VV_DF_WARPS
+#define VV_DF_WARPS 8
+#endif
+constexpr int kDfWarps = VV_DF_WARPS;
 constexpr int kDfThreads = kDfWarps * 32;
 constexpr int kDfFlush = 512;                  // examine once the candidate list holds this many
 constexpr int kDfPiece = 16;

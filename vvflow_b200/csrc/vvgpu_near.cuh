@@ -19,7 +19,13 @@
 
 namespace vv {
 
-constexpr int kLwWarps = 4;
+#ifndef VV_LW_WARPS
+#define VV_LW_WARPS 8
+#endif
+#ifndef VV_EPS_MINB
+#define VV_EPS_MINB 3
+#endif
+constexpr int kLwWarps = VV_LW_WARPS;
 constexpr int kLwThreads = kLwWarps * 32;
 constexpr int kMaxT = 15;           // targets per pass of a warp
 constexpr int kIdxCap = 1024;       // flat source indices buffered per warp
@@ -475,7 +481,7 @@ struct EpsOp {
     // a source leaf whose box is farther from the leaf's targets than the largest seeded second-neighbour
     // distance cannot hold a closer neighbour of any of them: exact pruning
     static constexpr bool kFilter = true;
-    static constexpr int kMinBlocks = 6;
+    static constexpr int kMinBlocks = VV_EPS_MINB;
     MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
     MergeState B_;      // recomputed solution (decision mode only)
     const double* lcrit;   // per leaf merge_criteria_sq (NaN: never merge)

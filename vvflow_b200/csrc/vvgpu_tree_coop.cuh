@@ -23,7 +23,13 @@
 namespace vv {
 namespace cg = cooperative_groups;
 
-constexpr int kCoopThreads = 1024;
+#ifndef VV_COOP_THREADS
+#define VV_COOP_THREADS 1024
+#endif
+#ifndef VV_COOP_BATCH
+#define VV_COOP_BATCH 4
+#endif
+constexpr int kCoopThreads = VV_COOP_THREADS;
 constexpr int kCoopItems = 4;
 constexpr int kCoopTile = kCoopThreads * kCoopItems;
 constexpr int kCoopMaxDepth = 4096;
@@ -99,7 +105,7 @@ __device__ __forceinline__ void coop_scan_apply(F f, long long n, const u32* par
 // four DEPENDENT gathers (pnode -> node record -> scan values), ~700 cycles each from L2: done one item at
 // a time that chain was the whole cost of a phase (ncu: 11.7 % issue-active, 2.7 ms for 22 levels at N = 1M).
 // Items are therefore processed in batches of kCoopBatch with the loads of a stage issued back to back.
-constexpr int kCoopBatch = 4;
+constexpr int kCoopBatch = VV_COOP_BATCH;
 
 // Stretch of freshly created nodes: fold every object into the box of its (pending) node.
 // Objects of one node are contiguous, so a warp first reduces every RUN of equal node ids among its 32
@@ -166,7 +172,8 @@ __device__ __forceinline__ void coop_bbox(const TreeDev& T, const int* snode, co
         }
         __syncthreads();
         if (warp < kCoopBatch) {   // warp k folds the uniform warps' results of batch item k
-            const BoxSlot sl = slots[warp][lane];
+            BoxSlot sl; sl.node = -1; sl.mnx = sl.mny = sl.mxx = sl.mxy = 0;
+            if (lane < kCoopThreads / 32) sl = slots[warp][lane];   // one slot per warp of the CTA
             int nd = sl.node;
             u64 mnx = sl.mnx, mny = sl.mny, mxx = sl.mxx, mxy = sl.mxy;
             seg_minmax(nd, mnx, mny, mxx, mxy, lane);

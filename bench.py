@@ -357,7 +357,7 @@ def ours(args):
                          "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None,
                          # ncu dram__bytes_read + dram__bytes_write of this kernel at N=1M, per launch
-                         # (profiles/r1_ncu_kernels_v6.txt: 97.2 MB + 13.2 MB)
+                         # (profiles/r1_ncu_kernels_v7.txt: 97.2 MB + 13.2 MB)
                          "traffic": 1.10e8 if n == 1_000_000 and world == 1 else None,
                          "ncu_fp64_pipe_pct": 58.9 if n == 1_000_000 and world == 1 else None,
                          "note": "FP64-pipe bound (no tensor cores: N-body gather). achieved = 11 flop x near pairs / "

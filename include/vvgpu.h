@@ -65,6 +65,7 @@ const char* vvgpu_strerror(int code);
 const char* vvgpu_last_error(const vvgpu_ctx* ctx);
 
 /* ---- state in / out (Space::VortexList, Space::BodyList; libvvhd/headers/TSpace.hpp:38-44) */
+/* (set_particles / get_particles accept a host OR a device address: the copy uses cudaMemcpyDefault) */
 int vvgpu_set_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t n);
 /* 24-byte (x,y,g) records as Space::load_list_bin reads them (TSpace.cpp:161-175); v,_1_eps = 0 */
 int vvgpu_set_particles_xyg(vvgpu_ctx* ctx, int list, const double* xyg, size_t n);

@@ -583,7 +583,9 @@ static int set_particles_common(vvgpu_ctx* c, int list, const void* src, size_t 
     c->n = n;
     c->orig_next = n;
     if (n) {
-        CK(cudaMemcpyAsync(st, src, n * rec_doubles * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        // cudaMemcpyDefault: the records may also sit in device memory (a multi-GPU host layer that uploads one slice
+        // per rank and all-gathers over NVLink hands over a device buffer)
+        CK(cudaMemcpyAsync(st, src, n * rec_doubles * sizeof(double), cudaMemcpyDefault, c->stream));
         if (rec_doubles == 6) k_unpack48<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
         else k_unpack24<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
         CKLAUNCH();
@@ -632,7 +634,7 @@ int vvgpu_get_particles(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t cap, size
     double* st = c->stage.get<double>(c->n * 6, &ok);
     NEED(ok);
     k_pack48<<<cdiv(c->n, 256), 256, 0, c->stream>>>((int)c->n, c->ps[c->cur].view(), st); CKLAUNCH();
-    CK(cudaMemcpyAsync(out, st, c->n * 48, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, st, c->n * 48, cudaMemcpyDefault, c->stream));   // host or device destination
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -325,9 +325,7 @@ int lists_impl(vvgpu_ctx* c, bool all) {
     NEED(ok);
     TreeDev T = c->T();
     LeafDev L = c->Lv();
-    CK(cudaFuncSetAttribute(k_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
     CK(cudaFuncSetAttribute(k_traverse<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
-    CK(cudaFuncSetAttribute(k_traverse<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem()));
     // heavy groups are cut at the first tree level that is at least 256 nodes wide
     int cut = c->depth;
     for (int d = 0; d <= c->depth; d++)

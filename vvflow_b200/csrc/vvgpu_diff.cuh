@@ -17,7 +17,7 @@
 // exp(x) for x in [-8, 0]: n = rint(x log2 e), r = x - n ln 2 (two-term), degree-11 Taylor polynomial
 // (truncation 6e-15 relative), exponent patched in — 19 instructions, no special cases; the library exp
 // spent a quarter of the kernel's instructions on loading its constants into uniform registers.
-// The cut-off decision itself is replayed exactly as in DiffOp::hit (vvgpu_near.cuh).
+// The cut-off decision itself is replayed exactly (df_hit below).
 #pragma once
 #include "vvgpu_near.cuh"
 

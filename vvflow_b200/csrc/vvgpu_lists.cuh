@@ -1,20 +1,25 @@
 // K2 — near/far classification (snode::FindNearNodes, libvvhd/src/TSortedTree.cpp:199-217).
 //
-// The reference walks the tree once per leaf and stores two pointer vectors per leaf. Here one
-// warp walks the tree ONCE for a GROUP of 32 consecutive leaves (consecutive in DFS order =
-// contiguous in the permuted particle array): lanes hold up to 32 frontier nodes, each lane
-// tests its node against the group's leaves with the reference's exact criterion and produces a
-// 32-bit mask of leaves for which the node is far / still near. Outputs of the single walk:
+// The reference walks the tree once per leaf and stores two pointer vectors per leaf. Here the tree is
+// walked ONCE for a GROUP of 32 consecutive leaves (consecutive in DFS order = contiguous in the
+// permuted particle array): lanes hold frontier nodes, each lane tests its node against the group's
+// leaves with the reference's exact criterion and produces a 32-bit mask of leaves for which the
+// node is far / still near. Outputs of the single walk:
 //   * the near list of the group: (source leaf, mask of target leaves that see it) entries, appended
-//     to an entry pool in chunks of kUnitEntries. A chunk IS a work unit of the near-field kernels,
-//     so no counting pass is needed; chunks are claimed with one atomic add each (their placement in
-//     the pool is arbitrary, their content and their order within the group are deterministic);
+//     to an entry pool in chunks (TravOut::unit entries). A chunk IS a work unit of the near-field
+//     kernels, so no counting pass is needed; chunks are claimed with one atomic add each (their
+//     placement in the pool is arbitrary, their content and their order within the group are
+//     deterministic);
 //   * per leaf, the four far-field Taylor coefficients of MConvectiveFast.cpp:48-69, accumulated on
 //     the fly, so far lists are never stored.
-// A few fringe groups see (almost) the whole tree. A warp that exceeds its iteration budget gives
-// up and the group is redone in two steps: one warp walks the top kTopDepth.. levels and turns every
-// still-near node of the cut level into an ITEM (node, mask); then one warp per item walks that
+// Who walks: k_traverse_cta<0> — one CTA of kTcWarps warps per group over a shared frontier in
+// lock-step (a one-warp walk is ~150 dependent iterations and the kernel ended with its longest one).
+// A few fringe groups see (almost) the whole tree; a walk that exceeds its node budget gives up and
+// the group is redone in two steps: k_traverse<1> (one warp) walks the top levels and turns every
+// still-near node of the cut level into an ITEM (node, mask); k_traverse_cta<2> walks each item's
 // subtree. Items own their chunks and Taylor partials, which are combined in item order.
+// k_traverse<0> / <2> are the one-warp forms of the same walks; they are not launched any more and
+// stay as the plain statement of the algorithm that the CTA form parallelises.
 // k_lists_dfs is the literal per-leaf walk, used only to export the reference's own lists
 // (vvgpu_tree_lists) to host code and tests.
 #pragma once

@@ -321,28 +321,8 @@ struct ConvOp {
         double e = 1. / P.ie[j];
         return (g == 0) ? make_double4(P.x[j], P.y[j], 0., 1.) : make_double4(P.x[j], P.y[j], g, e * e);
     }
-    // rotl(dr) * g / (|dr|^2 + eps^2). Reciprocal = rcp.approx.ftz.f64 (MUFU.RCP64H, relative error
-    // e0 <= 2^-19.9 measured on B200, tools/microbench2.cu) + one Newton step: 1/den = r0 (1 + e) up to
-    // e0^2 <= 2^-39.8 ~ 1e-12 per pair, two orders below the 1e-10 bar on velocities. 9 FP64 ops / pair.
-    static __device__ __forceinline__ double4 dummy() { return make_double4(0., 0., 0., 1.); }
-    __device__ __forceinline__ void pair(const double2 p, const double4 s, double& ax, double& ay) const {
-        const double dx = p.x - s.x, dy = p.y - s.y;
-        const double den = fma(dx, dx, fma(dy, dy, s.w));
-        double r0;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
-        const double e = fma(-den, r0, 1.0);
-        const double gr = s.z * r0;
-        const double w = fma(gr, e, gr);
-        ax = fma(-dy, w, ax);
-        ay = fma(dx, w, ay);
-    }
+    // (the pair sum itself lives in vvgpu_conv.cuh)
     __device__ __forceinline__ void take(Tgt& t, double vx, double vy) const { t.rx = vx; t.ry = vy; }
-    typedef double4 Src;
-    static __device__ __forceinline__ Src none() { return dummy(); }
-    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return A.src4[j]; }
-    __device__ __forceinline__ void use(Tgt& t, const NearArgs&, const Src& v, int) const {
-        pair(make_double2(t.x, t.y), v, t.rx, t.ry);
-    }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
         double vx = inf_vx + t.rx * k1_2Pi, vy = inf_vy + t.ry * k1_2Pi;
@@ -370,7 +350,6 @@ struct DiffOp {
     // only sources within 8 eps of a target contribute (:101): leaves farther than that from the whole
     // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
     static constexpr bool kFilter = true;
-    static constexpr int kMinBlocks = 5;
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, lim, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
@@ -390,44 +369,9 @@ struct DiffOp {
         t.x = A.P.x[i]; t.y = A.P.y[i]; t.g = g; t.ie = A.P.ie[i]; t.ie2 = t.ie * t.ie; t.pos = g > 0;
         return true;
     }
-    // a g == 0 source is parked at x = +inf: its distance is inf and the pre-test below drops it
-    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*) {
-        double g = P.g[j];
-        return make_double4(g == 0 ? __longlong_as_double(0x7ff0000000000000ll) : P.x[j], P.y[j], g, 0.);
-    }
-    // vortex_influence, :93-105. The cut-off decision `-|dr|*_1_eps < -8` is replayed exactly in
-    // hit(); a squared-distance pre-test with a 1e-6 safety margin rejects the ~98 % of pairs that
-    // are far outside it, so the common path is 7 FP64 instructions and one rarely-taken branch.
-    __device__ __forceinline__ void hit(Tgt& t, double dx, double dy, double d2, double sg) const {
-        if (sg == 0 || ((sg > 0) != t.pos)) return;        // same sign only (:95)
-        if (VV_ADD(fabs(dx), fabs(dy)) < 1E-10) return;    // TVec::iszero
-        // |dr| and 1/|dr| from one rsqrt; the exact sqrt of the reference decides only when the
-        // cut-off test is within 1e-9 of the boundary
-        double rinv = rsqrt(d2);
-        double drabs = d2 * rinv;
-        double exparg = -VV_MUL(drabs, t.ie);
-        if (fabs(exparg + 8.) < 1e-9) {
-            drabs = sqrt(d2);
-            exparg = -VV_MUL(drabs, t.ie);
-            rinv = 1. / drabs;
-        }
-        if (exparg < -8.) return;
-        double i1tmp = sg * exp(exparg);
-        double q = i1tmp * rinv;
-        t.S2x = fma(dx, q, t.S2x);
-        t.S2y = fma(dy, q, t.S2y);
-        t.S1 += i1tmp;
-    }
+    // (source views, the examine / evaluate loop and vortex_influence itself live in vvgpu_diff.cuh)
     // squared reach of a target: sources farther than 8 eps never contribute (:101)
     __device__ __forceinline__ double reach2(const Tgt& t) const { double r = 8.000008 / t.ie; return r * r; }
-    typedef double4 Src;
-    static __device__ __forceinline__ Src none() { return make_double4(__longlong_as_double(0x7ff0000000000000ll), 0., 0., 0.); }
-    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return A.src4[j]; }
-    __device__ __forceinline__ void use(Tgt& t, const NearArgs&, const Src& v, int) const {
-        double dx = VV_SUB(t.x, v.x), dy = VV_SUB(t.y, v.y);
-        double d2 = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-        if (!(d2 * t.ie2 > t.lim)) hit(t, dx, dy, d2, v.z);
-    }
     // segment_influence, :107-123
     __device__ __forceinline__ void segments(Tgt& t, const NearArgs& A, int sf, int sl) const {
         for (int k = sf; k < sl; k++) {

@@ -32,26 +32,12 @@ def check_tiling(bounds, n):
         raise RuntimeError(f"shard slices do not tile [0,{n}): {b.tolist()}")
 
 
-def allgather_slices(full, bounds, rank, group=None):
-    """`full` is a length-n tensor of which this rank owns [bounds[rank,0], bounds[rank,1]);
-    on return every rank holds every slice. Uneven slices: one broadcast per rank, coalesced on NCCL."""
-    world = bounds.shape[0]
-    ops = []
-    for r in range(world):
-        a, b = int(bounds[r, 0]), int(bounds[r, 1])
-        if b > a:
-            ops.append(dist.broadcast(full[a:b], src=dist.get_global_rank(group, r) if group is not None else r,
-                                      group=group, async_op=True))
-    for w in ops:
-        w.wait()
-    return full
-
-
 def allgather_padded(fulls, bounds, rank, group=None):
-    """Same result as allgather_slices for every tensor in `fulls`, with ONE collective for all of them: the
-    slices are padded to the longest one, gathered with all_gather (equal sizes), and written back with one
-    concatenation per tensor. One broadcast per rank and array (allgather_slices) costs world x len(fulls)
-    collectives per phase boundary, which dominated the step at 8 GPUs."""
+    """Every tensor in `fulls` is a length-n tensor of which this rank owns [bounds[rank,0], bounds[rank,1]); on
+    return every rank holds every slice of every tensor. ONE collective for all of them: the (uneven) slices are
+    padded to the longest one, gathered with all_gather (equal sizes), and written back with one concatenation
+    per tensor. One broadcast per rank and array cost world x len(fulls) collectives per phase boundary, which
+    dominated the step at 8 GPUs."""
     world = bounds.shape[0]
     lens = [int(bounds[r, 1] - bounds[r, 0]) for r in range(world)]
     L = max(max(lens), 1)

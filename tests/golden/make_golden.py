@@ -3,7 +3,8 @@ oracle/Makefile from /root/reference). Run in the build container: python tests/
 
 Each fixture holds the inputs and the reference's state after every phase of the hot path
 (vvflow.cpp:246-257): tree (pre-order node table, interaction lists), epsilon(+merge), convective,
-diffusive, move_and_clean. The oracle port and the CUDA path are both tested against them.
+diffusive, move_and_clean — plus, on the state after epsilon, the point evaluators (velocity(p), eps2h, h2) and
+the SLAE right-hand-side term NodeInfluence. The oracle port and the CUDA path are both tested against them.
 """
 import os
 import sys
@@ -38,6 +39,18 @@ def snapshot(r, with_body):
     d["interactions"] = np.array(r.count_interactions())
     d["merged"] = np.array([r.epsilon(True)])
     d["after_eps"] = r.get_list48()
+    # SURVEY 8(f) rows 1 and 4, evaluated on this state (tree built, _1_eps fresh): MConvectiveFast::velocity(p),
+    # static MEpsilonFast::eps2h / h2 of findNode(p), MConvectiveFast::NodeInfluence of every segment
+    rng = np.random.default_rng(7)
+    xy = d["after_eps"][:, :2]
+    lo, hi = xy.min(0), xy.max(0)
+    pts = np.concatenate([rng.uniform(lo, hi, (400, 2)), xy[rng.integers(0, xy.shape[0], 30)],
+                          rng.uniform(lo - 2 * (hi - lo), hi + 2 * (hi - lo), (70, 2))])
+    d["pts"] = pts
+    d["vel_at_pts"] = r.velocity_at(pts)
+    d["eps2h_h2_at_pts"] = r.eps2h_h2_at(pts)
+    if with_body:
+        d["node_influence"] = r.node_influence()
     r.convective()
     d["after_conv"] = r.get_list48()
     r.diffusive()

@@ -471,6 +471,13 @@ def test_golden_fixtures(ctx, name):
         e = vvhd.MEpsilonFast(S, tr); e.CalcEpsilonFast(True)
         assert e.Merged() == d["merged"][0]
         assert same(S.VortexList, d["after_eps"])
+        # SURVEY 8(f) rows 1, 4 against the reference's own values
+        conv = vvhd.MConvectiveFast(S, tr)
+        ok = np.isfinite(d["vel_at_pts"]).all(axis=1)
+        assert relerr(conv.velocity(d["pts"])[ok], d["vel_at_pts"][ok]) <= VTOL
+        assert same(e.eps2h(d["pts"]), d["eps2h_h2_at_pts"][:, 0]) and same(e.h2(d["pts"]), d["eps2h_h2_at_pts"][:, 1])
+        if bodies:
+            assert relerr(conv.NodeInfluence(), d["node_influence"]) <= VTOL
         vvhd.MConvectiveFast(S, tr).process_all_lists()
         assert relerr(S.VortexList[:, 3:5], d["after_conv"][:, 3:5]) <= VTOL
         vvhd.MDiffusiveFast(S, tr).process_vort_list()

@@ -34,6 +34,11 @@ def run_port_on_golden(port, d):
     assert npairs == d["interactions"][0] and nfar == d["interactions"][1]
     assert P.epsilon(True) == d["merged"][0]
     assert same(P.rec48(), d["after_eps"])
+    # SURVEY 8(f) rows 1, 4 on this state: bit-exact against the reference's values stored in the fixture
+    assert same(P.velocity_at(d["pts"], ivx, ivy, dt), d["vel_at_pts"])
+    assert same(P.eps2h_h2_at(d["pts"]), d["eps2h_h2_at_pts"])
+    if pb is not None:
+        assert same(P.node_influence(), d["node_influence"])
     P.convective(ivx, ivy, dt)
     assert same(P.rec48(), d["after_conv"])
     P.diffusive(re)

@@ -8,6 +8,8 @@
 // Modes:
 //   free N      run the gpu arm alone for N steps and print time + force_hydro (x y o) + particle
 //               count per step, exactly what stepdata would record (README.md:115-120 rows)
+//   points N    N lock-step steps, then on the next step's tree (after epsilon) compare the adapter's
+//               velocity(p) on a raster and NodeInfluence() of every segment with the reference classes
 //   lockstep N  per step: clone the reference Space into the gpu Space, run the hot path on both,
 //               compare order / merge decisions bit-exactly and every floating output to 1e-10
 // Built by oracle/Makefile into oracle/_ref/ (needs the reference headers; nothing is copied),
@@ -16,7 +18,9 @@
 
 #include "TSortedTree.hpp"
 #include "MEpsilonFast.hpp"
+#define private public   /* `points` mode calls the reference's private NodeInfluence (test infrastructure only) */
 #include "MConvectiveFast.hpp"
+#undef private
 #include "MDiffusiveFast.hpp"
 #include "MFlowmove.hpp"
 
@@ -135,6 +139,7 @@ int main(int argc, char** argv) {
         RefArm A(SA, mn, mx);
         GpuArm B(SB, mn, mx);
         double worst = 0;
+        const bool points = !strcmp(mode, "points");
         for (int k = 0; k < nsteps; k++) {
             A.pre();
             SA.zero_forces();
@@ -177,6 +182,42 @@ int main(int argc, char** argv) {
             worst = fmax(worst, e);
             printf("step %d N=%zu merged=%d cleaned=%zu relerr=%.3e\n", k, SA.VortexList.size(), ma, ca, e);
             SA.time = TTime::add(SA.time, SA.dt);
+        }
+        if (points) {
+            // SURVEY 8(f) rows 1 and 4 through the C++ adapter: same state in both Spaces, trees built, epsilon done
+            A.pre();
+            SA.zero_forces();
+            SB.VortexList = SA.VortexList;
+            *SB.BodyList[0] = *SA.BodyList[0];
+            SB.time = SA.time;
+            A.tr.build(); B.tr.build();
+            A.epsilon.CalcEpsilonFast(true); B.epsilon.CalcEpsilonFast(true);
+            std::vector<TVec> pts, vb;
+            for (int j = 0; j < 40; j++)
+                for (int i = 0; i < 60; i++) pts.push_back(TVec(-1.0 + 0.07 * i, -1.2 + 0.06 * j));
+            vb.resize(pts.size());
+            B.convective.velocity(pts.data(), pts.size(), vb.data());
+            double vs = 0, ve = 0;
+            for (size_t k = 0; k < pts.size(); k++) {
+                TVec va = A.convective.velocity(pts[k]);
+                vs = fmax(vs, fmax(fabs(va.x), fabs(va.y)));
+                ve = fmax(ve, fmax(fabs(va.x - vb[k].x), fabs(va.y - vb[k].y)));
+            }
+            TVec one = B.convective.velocity(pts[7]);
+            if (one.x != vb[7].x || one.y != vb[7].y) { printf("FAIL velocity(p) one-point form differs from the batched form\n"); return 1; }
+            std::vector<double> nb = B.convective.NodeInfluence();
+            double ns = 0, ne = 0;
+            size_t k = 0;
+            for (auto& lbody : SA.BodyList)
+                for (auto& latt : lbody->alist) {
+                    double na = A.convective.NodeInfluence(*A.tr.findNode(latt.r), latt);
+                    ns = fmax(ns, fabs(na));
+                    ne = fmax(ne, fabs(na - nb[k++]));
+                }
+            A.tr.destroy(); B.tr.destroy();
+            printf("points: velocity(p) on %zu points relerr=%.3e; NodeInfluence on %zu segments relerr=%.3e\n", pts.size(),
+                   ve / vs, nb.size(), ne / ns);
+            worst = fmax(worst, fmax(ve / vs, ne / ns));
         }
         printf("%s worst=%.3e\n", worst <= 1e-10 ? "OK" : "FAIL", worst);
         return worst <= 1e-10 ? 0 : 1;

@@ -60,3 +60,15 @@ def test_lockstep_against_reference_classes():
     p = subprocess.run([BIN, "lockstep", "40"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.strip().splitlines()[-1].startswith("OK"), p.stdout[-500:]
+
+
+@pytest.mark.gpu
+def test_points_and_slae_rhs_against_reference_classes():
+    """SURVEY 8(f) rows 1 and 4 through the C++ adapter: after 12 lock-step steps of cyl_re600, velocity(p) on a
+    60 x 40 raster and NodeInfluence() of all 350 segments against the reference's own classes in the same
+    process (1e-10, checked inside the binary)"""
+    _need_bin()
+    p = subprocess.run([BIN, "points", "12"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    lines = p.stdout.strip().splitlines()
+    assert lines[-1].startswith("OK") and lines[-2].startswith("points:"), p.stdout[-500:]

@@ -131,6 +131,13 @@ int vvgpu_eps2h_h2_at(vvgpu_ctx* ctx, const double* xy, size_t npts, double* eps
  * SLAE before CalcEpsilonFast, so these are last step's values that came in with the TObj records). With it
  * calc_circulation needs no CPU tree: see INTEGRATION.md §2b. ------------------------------------------------ */
 int vvgpu_node_influence(vvgpu_ctx* ctx, double* out_nseg);
+/* ---- XVorticity::evaluate, XVorticity.cpp:26-97 (the vorticity raster of vvplot) on the resident
+ * vortex list, which must already hold what MFlowmove::vortex_shed adds (XVorticity.cpp:36; append them with
+ * vvgpu_append_particles). Builds its own tree (far criteria 8, minNodeSize 20 dl, :38) on a copy, so the resident
+ * list keeps its order, like the reference's Space copy. xmin, ymin, dxdy are floats as in XField; dl =
+ * Space::average_segment_length(). out[yj * xres + xi] in double: XField::map stores the same value as float. ---- */
+int vvgpu_vorticity_raster(vvgpu_ctx* ctx, float xmin, float ymin, float dxdy, int xres, int yres, double eps_mult,
+                           double dl, double* out);
 /* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
  * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
 int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);

@@ -589,6 +589,70 @@ void vvo_node_influence(const vvo_tree* t, const vvo_plist* p, const vvo_bodies*
     }
 }
 
+/* XVorticity::evaluate + XVorticity::vorticity (libvvhd/src/XVorticity.cpp:26-97), the vorticity raster of vvplot.
+ * `p` is the vortex list AFTER MFlowmove::vortex_shed (:36, the caller appends the attached vortices); it is permuted
+ * by the tree this function builds for itself (far criteria 8, minNodeSize 20 dl, :38). Per particle (:46-52):
+ * v.x = 1 / (eps_mult^2 max(eps2h(leaf, r), (0.6 dl)^2)), v.y = v.x g. Per raster point (:58-69, 76-97): 0 inside a
+ * body, else sum over the near leaves' particles of v.y exp(-|p - r|^2 v.x) where that exponent > -6, times 1/pi,
+ * plus 0.5 (1 - erf(h2 / (dl eps_mult)^2)) where that argument < 3. xmin, ymin, dxdy are floats as in XField.
+ * out[yj * xres + xi] in double (the reference stores the same value rounded to float). */
+void vvo_vorticity_raster(vvo_plist* p, const vvo_bodies* b, float xmin, float ymin, float dxdy, int xres, int yres,
+                          double eps_mult, double dl, double* out) {
+    static const vvo_bodies nobody;
+    if (!b) b = &nobody;
+    vvo_tree* t = vvo_tree_build(p, b, 8, dl * 20, DBL_MAX);
+    double* vx = (double*)malloc(sizeof(double) * (size_t)(p->n > 0 ? p->n : 1));
+    double* vy = (double*)malloc(sizeof(double) * (size_t)(p->n > 0 ? p->n : 1));
+    for (int64_t l = 0; l < t->n_leaves; l++) {
+        const int64_t node = t->leaf_node[l];
+        for (int64_t i = t->vfirst[node]; i < t->vlast[node]; i++) {
+            double res1 = INFINITY, res2 = INFINITY;   /* MEpsilonFast::eps2h(leaf, r_i), MEpsilonFast.cpp:66-93 */
+            for (int64_t k = t->near_ptr[l]; k < t->near_ptr[l + 1]; k++) {
+                int64_t nn = t->leaf_node[t->near_idx[k]];
+                for (int64_t j = t->vfirst[nn]; j < t->vlast[nn]; j++) {
+                    double dx = p->x[i] - p->x[j], dy = p->y[i] - p->y[j];
+                    double d = dx * dx + dy * dy;
+                    if (!d) continue;
+                    else if (d < res1) { res2 = res1; res1 = d; }
+                    else if (d < res2) res2 = d;
+                }
+            }
+            double e2 = isfinite(res2) ? res2 : (isfinite(res1) ? res1 : -DBL_MAX);
+            vx[i] = 1. / (sqr(eps_mult) * dmax(e2, sqr(0.6 * dl)));
+            vy[i] = vx[i] * p->g[i];
+        }
+    }
+    for (int yj = 0; yj < yres; yj++) {
+        for (int xi = 0; xi < xres; xi++) {
+            const double px = (double)xmin + (double)dxdy * (double)xi, py = (double)ymin + (double)dxdy * (double)yj;
+            int inbody = 0;
+            for (int64_t ib = 0; ib < b->nbody && !inbody; ib++) inbody = vvo_point_invalid(b, ib, px, py) >= 0;
+            if (inbody) { out[(size_t)yj * xres + xi] = 0; continue; }
+            const int64_t l = t->leaf[vvo_find_node(t, px, py)];
+            double res = 0, hh = INFINITY;
+            for (int64_t k = t->near_ptr[l]; k < t->near_ptr[l + 1]; k++) {
+                int64_t nn = t->leaf_node[t->near_idx[k]];
+                for (int64_t j = t->vfirst[nn]; j < t->vlast[nn]; j++) {
+                    double dx = px - p->x[j], dy = py - p->y[j];
+                    double exparg = -(dx * dx + dy * dy) * vx[j];
+                    res += (exparg > -6) ? vy[j] * exp(exparg) : 0;
+                }
+                for (int64_t k2 = t->sfirst[nn]; k2 < t->slast[nn]; k2++) {
+                    int64_t s = t->seg_perm[k2];
+                    double dx = px - b->rx[s], dy = py - b->ry[s];
+                    hh = dmin(hh, dx * dx + dy * dy);
+                }
+            }
+            res *= C_1_PI;
+            double erfarg = hh / sqr(dl * eps_mult);
+            res += (erfarg < 3) ? 0.5 * (1 - erf(erfarg)) : 0;
+            out[(size_t)yj * xres + xi] = res;
+        }
+    }
+    free(vx); free(vy);
+    vvo_tree_free(t);
+}
+
 /* ------------------------------------------------------------------ diffusive */
 
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)

@@ -80,6 +80,9 @@ void vvo_eps2h_h2_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b,
                      double* out);
 /* MConvectiveFast::NodeInfluence(*findNode(seg.r), seg) of every segment, MConvectiveFast.cpp:398-418 -> out[nseg] */
 void vvo_node_influence(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b, double* out);
+/* XVorticity::evaluate (XVorticity.cpp:26-97) on the post-shed list p (permuted by the tree built inside) */
+void vvo_vorticity_raster(vvo_plist* p, const vvo_bodies* b, float xmin, float ymin, float dxdy, int xres, int yres,
+                          double eps_mult, double dl, double* out);
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
 /* advect, drop |g|<remove_eps, drop in-body (accumulating dead sums), zero v. Compacts p in place,
  * returns the new n; *cleaned = number removed by the in-body test */

@@ -58,6 +58,8 @@ def lib():
         L.vvo_diffusive.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double]
         L.vvo_eps2h_h2_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_node_influence.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p]
+        L.vvo_vorticity_raster.argtypes = [C.POINTER(_PList), C.POINTER(_Bodies), C.c_float, C.c_float, C.c_float, C.c_int,
+                                           C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.vvo_velocity_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double,
                                       C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_move_and_clean.restype = C.c_int64
@@ -230,6 +232,14 @@ class Port:
         out = np.zeros(int(self.bodies.nseg) if self.bodies is not None else 0)
         if out.shape[0]:
             self.L.vvo_node_influence(self.tree, C.byref(self.p), self._b(), _ptr(out))
+        return out
+
+    def vorticity_raster(self, xmin, ymin, dxdy, xres, yres, eps_mult, dl):
+        """XVorticity::evaluate on this (post-shed) list; the list is permuted by the tree built inside.
+        (yres, xres) float64 — the reference stores float32 of the same values."""
+        assert self.tree is None or not self.tree, "destroy the tree first"
+        out = np.zeros((yres, xres))
+        self.L.vvo_vorticity_raster(C.byref(self.p), self._b(), xmin, ymin, dxdy, xres, yres, eps_mult, dl, _ptr(out))
         return out
 
     def diffusive(self, re):

@@ -61,6 +61,8 @@ def _load():
         "vvr_velocity_at": (None, [C.c_void_p, _dp, C.c_size_t, _dp]),
         "vvr_eps2h_h2_at": (None, [C.c_void_p, _dp, C.c_size_t, _dp]),
         "vvr_node_influence": (None, [C.c_void_p, _dp]),
+        "vvr_vorticity_raster": (None, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double,
+                                        np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]),
         "vvr_diffusive": (None, [C.c_void_p, C.c_int, C.c_int]),
         "vvr_move_and_clean": (C.c_size_t, [C.c_void_p, C.c_int]),
         "vvr_calc_circulation": (None, [C.c_void_p]),
@@ -245,6 +247,12 @@ class Ref:
         """MConvectiveFast::NodeInfluence(findNode(seg.r), seg) of every segment (SLAE right-hand side, vortex term)"""
         out = np.zeros(self.segments().shape[0])
         self.L.vvr_node_influence(self.h, out)
+        return out
+
+    def vorticity_raster(self, xmin, ymin, dxdy, xres, yres, eps_mult):
+        """XVorticity(S, ...).evaluate(): (yres, xres) float32 map"""
+        out = np.zeros((yres, xres), dtype=np.float32)
+        self.L.vvr_vorticity_raster(self.h, xmin, ymin, dxdy, xres, yres, eps_mult, out)
         return out
 
     def diffusive(self, vort=True, heat=False):

@@ -27,6 +27,7 @@
 #undef private
 #include "MDiffusiveFast.hpp"
 #include "MFlowmove.hpp"
+#include "XVorticity.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -378,6 +379,24 @@ void vvr_node_influence(void* h, double* out) {
     for (auto& lbody : c->S.BodyList)
         for (auto& latt : lbody->alist)
             out[k++] = c->conv->NodeInfluence(*c->tree->findNode(latt.r), latt);
+}
+/* XVorticity(S, xmin, ymin, dxdy, xres, yres).evaluate() (libvvhd/src/XVorticity.cpp:26-97): the vorticity raster of
+ * vvplot. It works on a COPY of the Space (sheds the attached vortices into it, builds its own tree with
+ * minNodeSize = 20 dl), so the context's lists are untouched — except TAtt::gsum, which vortex_shed increments through
+ * the shared TBody pointers; it is restored here. out[yj * xres + xi], float like XField::map. */
+void vvr_vorticity_raster(void* h, float xmin, float ymin, float dxdy, int xres, int yres, double eps_mult, float* out) {
+    Ctx* c = (Ctx*)h;
+    std::vector<double> gsum;
+    for (auto& lbody : c->S.BodyList) for (auto& latt : lbody->alist) gsum.push_back(latt.gsum);
+    {
+        XVorticity f(c->S, xmin, ymin, dxdy, xres, yres);
+        f.eps_mult = eps_mult;
+        f.evaluate();
+        for (int yj = 0; yj < yres; yj++)
+            for (int xi = 0; xi < xres; xi++) out[yj * xres + xi] = f.at(xi, yj);
+    }
+    size_t k = 0;
+    for (auto& lbody : c->S.BodyList) for (auto& latt : lbody->alist) latt.gsum = gsum[k++];
 }
 void vvr_diffusive(void* h, int vort, int heat) {
     Ctx* c = (Ctx*)h;

@@ -357,6 +357,50 @@ def test_append_particles_resident_loop(ctx):
     ctx.tree_destroy()
 
 
+@pytest.mark.parametrize("with_body", [False, True])
+def test_vorticity_raster(ctx, port, with_body):
+    """SURVEY 8(f) row 4: XVorticity::evaluate (XVorticity.cpp:26-97). The oracle's raster is pinned to the compiled
+    reference (bit-exact after the float rounding of XField::map); here 1e-10 norm-wise in double, and the resident
+    list must come back untouched (the reference works on a copy of the Space)."""
+    from vvflow_b200 import vvhd
+    if with_body:
+        bodies = [cases.cylinder(0.5, 350)]
+        bodies[0].g[:] = np.random.default_rng(81).uniform(-1, 1, 350) * 1e-3     # attached vortices to shed
+        xyg = cases.around_cylinder(8000, sign="mixed", seed=82)
+        grid = (-1.0, -1.0, 0.02, 100, 100, 1.5)
+    else:
+        bodies = []
+        xyg = cases.cloud(20000, "gauss", "mixed", seed=83)
+        grid = (-2.5, -2.5, 0.05, 100, 100, 2.0)
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    f = vvhd.XVorticity(S, *grid[:5])
+    with pytest.raises(ValueError):
+        f.evaluate()                                   # eps_mult must be positive
+    f.eps_mult = grid[5]
+    f.evaluate()
+    assert same(ctx.get_particles()[:, :3], xyg)       # the Space's list is back on the device, in its own order
+    # oracle on the same post-shed list
+    shed = []
+    for b in bodies:
+        keep = (np.abs(b.g) >= 1e-10) & (b.slip == 0)
+        shed.append(np.stack([b.corner[keep, 0] - b.dl[keep, 1] * 1e-4, b.corner[keep, 1] + b.dl[keep, 0] * 1e-4, b.g[keep]], 1))
+    P = port.Port(xyg=np.concatenate([xyg] + shed), bodies=cases.port_bodies(port, bodies))
+    want = P.vorticity_raster(*[np.float32(v) for v in grid[:3]], grid[3], grid[4], grid[5], S.average_segment_length())
+    got = ctx_raster = f.map
+    assert got.shape == want.shape == (100, 100)
+    assert np.abs(want).max() > 0 and (not with_body or (want == 0).sum() > 100)
+    assert np.array_equal(got == 0, want.astype(np.float32) == 0)                 # the same points are inside the body
+    assert relerr(got.astype(np.float64), want) <= 2e-7                            # float32 map
+    # the double values behind the map
+    S.ctx.set_particles(np.concatenate([np.concatenate([xyg, np.zeros((xyg.shape[0], 3))], 1)] +
+                                       [np.concatenate([s_, np.zeros((s_.shape[0], 3))], 1) for s_ in shed]))
+    dbl = ctx.vorticity_raster(float(np.float32(grid[0])), float(np.float32(grid[1])), float(np.float32(grid[2])), grid[3], grid[4],
+                               grid[5], S.average_segment_length())
+    assert relerr(dbl, want) <= VTOL, relerr(dbl, want)
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

@@ -197,3 +197,45 @@ def test_node_influence_matches_reference(port, ref):
     assert a.shape == (350,) and np.isfinite(a).all() and np.abs(a).max() > 0
     assert same(a, b), np.abs(a - b).max()
     r.tree_destroy(); P.tree_destroy()
+
+
+def shed_vortices(seg, remove_eps=1e-10):
+    """MFlowmove::vortex_shed (MFlowmove.cpp:217-235): one vortex per segment with |g| >= remove_eps and no slip,
+    at corner + rotl(dl) * 1e-4. `seg` rows as pyref.Ref.segments(): r(2) corner(2) dl(2) g gsum fric ieps slip body"""
+    keep = (np.abs(seg[:, 6]) >= remove_eps) & (seg[:, 10] == 0)
+    s = seg[keep]
+    out = np.zeros((s.shape[0], 3))
+    out[:, 0] = s[:, 2] + (-s[:, 5]) * 1e-4       # rotl(dl) = (-dl.y, dl.x)
+    out[:, 1] = s[:, 3] + s[:, 4] * 1e-4
+    out[:, 2] = s[:, 6]
+    return out
+
+
+def test_vorticity_raster_matches_reference(port, ref):
+    """XVorticity::evaluate (XVorticity.cpp:26-97, SURVEY 8(f) row 4): the port's raster, rounded to float like
+    XField::map, equals the compiled reference's bit for bit — body-free cloud and a cylinder whose segments carry
+    circulation (so that vortex_shed adds particles and the erf wall term is live)."""
+    # body-free: dl = 0
+    xyg = cases.cloud(4000, "gauss", "mixed", seed=71)
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    r.set_list(xyg)
+    want = r.vorticity_raster(-2.5, -2.5, 0.1, 50, 50, 2.0)
+    got = port.Port(xyg=xyg).vorticity_raster(-2.5, -2.5, 0.1, 50, 50, 2.0, 0.0)
+    assert same(got.astype(np.float32), want)
+    assert np.abs(want).max() > 0
+    # cylinder with circulation on its segments
+    xyg = cases.around_cylinder(5000, sign="mixed", seed=72)
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    r.add_cylinder(0.5, 350)
+    rng = np.random.default_rng(73)
+    r.set_segments(g=rng.uniform(-1, 1, 350) * 1e-3)
+    r.set_list(xyg)
+    seg = r.segments()
+    want = r.vorticity_raster(-1.0, -1.0, 0.04, 50, 50, 1.5)
+    assert same(r.segments()[:, 7], seg[:, 7])                      # the shim restores gsum
+    pb = port.Bodies.from_ref(r)
+    dl = float(np.hypot(seg[:, 4], seg[:, 5]).sum() / (350 - 1))    # Space::average_segment_length, TSpace.hpp:119-129
+    P = port.Port(xyg=np.concatenate([xyg, shed_vortices(seg)]), bodies=pb)
+    got = P.vorticity_raster(-1.0, -1.0, 0.04, 50, 50, 1.5, dl)
+    assert (want == 0).sum() > 100 and np.abs(want).max() > 0
+    assert same(got.astype(np.float32), want), np.abs(got.astype(np.float32) - want).max()

@@ -18,7 +18,7 @@ SYMBOLS = [
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
-    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_diffusive", "vvgpu_move_and_clean",
+    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
     "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_shard_bounds", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
 ]
@@ -74,6 +74,7 @@ def load():
         "vvgpu_velocity_at": [vp, dp, sz, C.c_double, C.c_double, C.c_double, dp, sz, dp],
         "vvgpu_eps2h_h2_at": [vp, dp, sz, dp],
         "vvgpu_node_influence": [vp, dp],
+        "vvgpu_vorticity_raster": [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double, C.c_double, dp],
         "vvgpu_diffusive": [vp, C.c_double, dp],
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
         "vvgpu_set_shard": [vp, C.c_int, C.c_int],
@@ -255,6 +256,12 @@ class Context:
         out = np.zeros(max(1, getattr(self, "nseg", 0)))
         self._ck(self.L.vvgpu_node_influence(self.h, _p(out)))
         return out[: getattr(self, "nseg", 0)]
+
+    def vorticity_raster(self, xmin, ymin, dxdy, xres, yres, eps_mult, dl):
+        """XVorticity::evaluate on the resident (post-shed) list: (yres, xres) float64"""
+        out = np.zeros((yres, xres))
+        self._ck(self.L.vvgpu_vorticity_raster(self.h, xmin, ymin, dxdy, xres, yres, eps_mult, dl, _p(out)))
+        return out
 
     def diffusive(self, re, want_fric=True):
         fric = np.zeros(max(1, getattr(self, "nseg", 0))) if want_fric and getattr(self, "nseg", 0) else None

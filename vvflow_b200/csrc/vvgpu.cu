@@ -119,7 +119,8 @@ struct vvgpu_ctx {
     // epsilon
     Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged;
     Buf mA[6], mB[6];
-    Buf d_sinks, d_pairs, pt_xy, pt_out;
+    Buf d_sinks, d_pairs, pt_xy, pt_out, pt_v;
+    PSet ps_backup;   // the resident list while a raster evaluator works on its own tree
 
     // shard
     int rank = 0, nranks = 1;
@@ -563,7 +564,8 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
-    c->ps[0].release(); c->ps[1].release();
+    c->ps[0].release(); c->ps[1].release(); c->ps_backup.release();
+    c->pt_xy.release(); c->pt_out.release(); c->pt_v.release();
     for (int k = 0; k < VVGPU_T_COUNT; k++) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     cudaStreamDestroy(c->stream);
@@ -1060,6 +1062,69 @@ int vvgpu_node_influence(vvgpu_ctx* c, double* out_nseg) {
     CK(cudaStreamSynchronize(c->stream));
     if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "node_influence: traversal stack overflow");
     return 0;
+}
+
+int vvgpu_vorticity_raster(vvgpu_ctx* c, float xmin, float ymin, float dxdy, int xres, int yres, double eps_mult, double dl,
+                           double* out) {
+    if (!c || xres <= 0 || yres <= 0 || !out) return fail(c, VVGPU_EINVAL, "vorticity_raster: bad argument");
+    if (!(eps_mult > 0)) return fail(c, VVGPU_EINVAL, "XVorticity(): eps_mult must be positive");   // XVorticity.cpp:28-29
+    if (c->built) return fail(c, VVGPU_ESTATE, "vorticity_raster builds its own tree: destroy the step's tree first");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = c->n, npts = (size_t)xres * yres;
+    bool ok = true;
+    // the reference works on a COPY of the Space (:33-38): the resident list must come back in its own order
+    PSet& P = c->ps[c->cur];
+    if (n && !c->ps_backup.ensure(n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    auto copy7 = [&](PSet& dst, PSet& src) {
+        if (!n) return;
+        Buf* d[6] = {&dst.x, &dst.y, &dst.g, &dst.vx, &dst.vy, &dst.ie};
+        Buf* s7[6] = {&src.x, &src.y, &src.g, &src.vx, &src.vy, &src.ie};
+        for (int k = 0; k < 6; k++) cudaMemcpyAsync(d[k]->p, s7[k]->p, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dst.orig.p, src.orig.p, n * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    };
+    copy7(c->ps_backup, P);
+    int rc = tree_build_impl(c, 8, dl * 20, std::numeric_limits<double>::max(), 3u);   // TSortedTree tree(&S, 8, dl*20), :38
+    if (!rc) {
+        double* dxy = c->pt_xy.get<double>(2 * std::max<size_t>(n, 1), &ok);
+        double* de2 = c->pt_out.get<double>(2 * std::max<size_t>(std::max(n, npts), 1), &ok);
+        double* dv = c->pt_v.get<double>(2 * std::max<size_t>(n, 1), &ok);
+        int* derr = c->d_err.get<int>(4, &ok);
+        if (!ok) rc = fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+        if (!rc) {
+            cudaMemsetAsync(derr, 0, 4 * sizeof(int), st);
+            PSet& PP = c->ps[c->cur];
+            if (n) {
+                k_interleave_xy<<<cdiv(n, 256), 256, 0, st>>>((int)n, PP.view(), dxy);
+                ScalarArgs SA;
+                SA.T = c->T(); SA.P = PP.view(); SA.npts = (int)n; SA.xy = dxy; SA.out = de2; SA.farc = c->farc;
+                SA.seg_perm = c->t_segperm[c->segcur].as<int>(); SA.srx = c->s_rx.as<double>(); SA.sry = c->s_ry.as<double>();
+                SA.err = derr;
+                k_eps2h_h2_at<<<cdiv(n, kPtWarps), kPtWarps * 32, 0, st>>>(SA);
+                k_vort_prepare<<<cdiv(n, 256), 256, 0, st>>>((int)n, PP.view(), de2, eps_mult, dl, dv, dv + n);
+                c->launches += 3;
+            }
+            RasterArgs RA;
+            RA.T = c->T(); RA.P = PP.view(); RA.vx = dv; RA.vy = dv + n;
+            RA.seg_perm = c->t_segperm[c->segcur].as<int>(); RA.srx = c->s_rx.as<double>(); RA.sry = c->s_ry.as<double>();
+            RA.B = BodyGeom{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                            c->b_first.as<int>(), c->b_prop.as<double>()};
+            RA.xmin = xmin; RA.ymin = ymin; RA.dxdy = dxdy; RA.xres = xres; RA.yres = yres;
+            RA.eps_mult = eps_mult; RA.dl = dl; RA.farc = c->farc; RA.out = de2; RA.err = derr;
+            k_vorticity_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, st>>>(RA); c->launches++;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(c, VVGPU_ECUDA, "vorticity_raster: launch failed");
+            cudaMemcpyAsync(out, de2, npts * sizeof(double), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, VVGPU_ECUDA, "vorticity_raster: kernel failed");
+            if (!rc && (c->h_pinned[64] & 2)) rc = fail(c, VVGPU_ELIMIT, "vorticity_raster: traversal stack overflow");
+        }
+    }
+    // destroy the raster's tree and put the resident list back
+    c->built = false; c->lists_ready = false;
+    c->nnodes = c->nleaves = c->ngroups = 0;
+    copy7(c->ps[c->cur], c->ps_backup);
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail(c, VVGPU_ECUDA, "vorticity_raster: restore failed");
+    return rc;
 }
 
 int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {

@@ -11,7 +11,7 @@
 // its children, a near leaf is streamed particle by particle. Sums are reduced across lanes at the end, so the
 // result agrees with the reference to rounding (order of summation), not bit for bit.
 #pragma once
-#include "vvgpu_near.cuh"
+#include "vvgpu_move.cuh"
 
 namespace vv {
 
@@ -328,6 +328,121 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_node_influence(SegInflArgs A)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
     if (lane == 0) A.out[s] = res * k1_2Pi;
+}
+
+// SURVEY §8(f) row 4 — XVorticity::evaluate / ::vorticity (libvvhd/src/XVorticity.cpp:26-97), the vorticity raster of
+// vvplot, on the tree the host built for it (far criteria 8, minNodeSize 20 dl, :38):
+//   per particle (:46-52)   v.x = 1 / (eps_mult^2 max(eps2h(leaf, r), (0.6 dl)^2)),  v.y = v.x g
+//   per raster point (:58-69, :76-97)   0 inside a body, else  (1/pi) sum over the near leaves' particles of
+//       v.y exp(-|p - r|^2 v.x)  where the exponent > -6,  + 0.5 (1 - erf(h2 / (dl eps_mult)^2)) where that is < 3.
+__global__ void k_interleave_xy(int n, Particles P, double* xy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { xy[2ll * i] = P.x[i]; xy[2ll * i + 1] = P.y[i]; }
+}
+__global__ void k_vort_prepare(int n, Particles P, const double* __restrict__ e2h2, double eps_mult, double dl, double* vx,
+                               double* vy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double floor2 = VV_MUL(VV_MUL(0.6, dl), VV_MUL(0.6, dl));
+    const double v = 1. / VV_MUL(VV_MUL(eps_mult, eps_mult), std_max(e2h2[2ll * i], floor2));
+    vx[i] = v;
+    vy[i] = VV_MUL(v, P.g[i]);
+}
+
+struct RasterArgs {
+    TreeDev T;
+    Particles P;
+    const double *vx, *vy;     // per particle, k_vort_prepare
+    const int* seg_perm;
+    const double *srx, *sry;
+    BodyGeom B;
+    float xmin, ymin, dxdy;    // floats, as XField keeps them
+    int xres, yres;
+    double eps_mult, dl, farc;
+    double* out;               // yres x xres
+    int* err;
+};
+
+__global__ void __launch_bounds__(kPtWarps * 32) k_vorticity_at(RasterArgs A) {
+    __shared__ int stack[kPtWarps][kPtStack];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * kPtWarps + warp;
+    if (q >= (long long)A.xres * A.yres) return;
+    const int xi = (int)(q % A.xres), yj = (int)(q / A.xres);
+    // TVec(xmin, ymin) + dxdy * TVec(xi, yj), :65
+    const double px = VV_ADD((double)A.xmin, VV_MUL((double)A.dxdy, (double)xi));
+    const double py = VV_ADD((double)A.ymin, VV_MUL((double)A.dxdy, (double)yj));
+    int inbody = 0;
+    if (lane == 0)
+        for (int ib = 0; ib < A.B.nbody && !inbody; ib++) inbody = point_invalid(A.B, ib, px, py) >= 0;   // Space::point_is_in_body
+    if (__shfl_sync(0xffffffffu, inbody, 0)) {
+        if (lane == 0) A.out[q] = 0;
+        return;
+    }
+    const TreeDev& T = A.T;
+    int leaf = 0;
+    while (T.ch1[leaf] >= 0) {
+        const int c = T.ch1[leaf];
+        leaf = T.axis[leaf] ? ((px < T.x[leaf]) ? c : c + 1) : ((py < T.y[leaf]) ? c : c + 1);
+    }
+    const double lcx = T.x[leaf], lcy = T.y[leaf], lh = T.h[leaf], lw = T.w[leaf];
+    int* st = stack[warp];
+    if (lane == 0) st[0] = 0;
+    int size = 1;
+    __syncwarp();
+    double res = 0, hh = __longlong_as_double(0x7ff0000000000000ll);
+    while (size > 0) {
+        const int take = (size > kPtStack - 80) ? 1 : min(size, 32);
+        int n = -1;
+        if (lane < take) n = st[size - 1 - lane];
+        size -= take;
+        __syncwarp();
+        bool push = false, nearleaf = false;
+        int c1 = -1;
+        if (n >= 0) {
+            c1 = T.ch1[n];
+            if (!is_far(T.x[n], T.y[n], VV_ADD(T.h[n], T.w[n]), lcx, lcy, lh, lw, A.farc)) {
+                if (c1 >= 0) push = true; else nearleaf = true;
+            }
+        }
+        const u32 pb = __ballot_sync(0xffffffffu, push);
+        const int npush = 2 * __popc(pb);
+        if (size + npush > kPtStack) {
+            if (lane == 0) atomicOr(A.err, 2);
+            return;
+        }
+        if (push) {
+            const int off = size + 2 * __popc(pb & lanemask_lt());
+            st[off] = c1 + 1; st[off + 1] = c1;
+        }
+        size += npush;
+        for (u32 nb = __ballot_sync(0xffffffffu, nearleaf); nb; nb &= nb - 1) {
+            const int ln = __shfl_sync(0xffffffffu, n, __ffs(nb) - 1);
+            for (int j = T.first[ln] + lane; j < T.last[ln]; j += 32) {
+                const double dx = VV_SUB(px, A.P.x[j]), dy = VV_SUB(py, A.P.y[j]);
+                const double exparg = -VV_MUL(VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy)), A.vx[j]);
+                if (exparg > -6) res += A.vy[j] * exp(exparg);
+            }
+            for (int k = T.sfirst[ln] + lane; k < T.slast[ln]; k += 32) {
+                const int s = A.seg_perm[k];
+                const double dx = VV_SUB(px, A.srx[s]), dy = VV_SUB(py, A.sry[s]);
+                hh = fmin(hh, VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy)));
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        res += __shfl_xor_sync(0xffffffffu, res, o);
+        hh = fmin(hh, __shfl_xor_sync(0xffffffffu, hh, o));
+    }
+    if (lane == 0) {
+        res *= k1_Pi;
+        const double de = VV_MUL(A.dl, A.eps_mult);
+        const double erfarg = hh / VV_MUL(de, de);
+        if (erfarg < 3) res += 0.5 * (1 - erf(erfarg));   // a NaN (no bodies: inf / 0) fails the test like in the reference
+        A.out[q] = res;
+    }
 }
 
 }  // namespace vv

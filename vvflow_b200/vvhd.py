@@ -300,3 +300,43 @@ class MFlowmove:
             k += b.size()
         S._dev_newer = True
         return out["cleaned"]
+
+
+class XVorticity:
+    """XVorticity (libvvhd/headers/XVorticity.hpp, src/XVorticity.cpp): the vorticity raster of vvplot. Like the
+    reference it works on a copy of the Space: the attached vortices are shed into the copy (MFlowmove::vortex_shed,
+    MFlowmove.cpp:217-235), a tree with minNodeSize = 20 dl is built for it, and the Space itself is left untouched."""
+
+    def __init__(self, S, xmin, ymin, dxdy, xres, yres):
+        self.S = S
+        self.xmin, self.ymin, self.dxdy = np.float32(xmin), np.float32(ymin), np.float32(dxdy)   # XField keeps floats
+        self.xres, self.yres = int(xres), int(yres)
+        self.eps_mult = 0.0
+        self.map = None
+
+    def evaluate(self, remove_eps=1e-10):
+        if self.eps_mult <= 0:
+            raise ValueError("XVorticity(): eps_mult must be positive")   # XVorticity.cpp:28-29
+        if self.map is not None:
+            return
+        S = self.S
+        own = S.VortexList.copy()                  # pulls the device copy if it is newer
+        shed = []
+        for b in S.BodyList:                       # vortex_shed on the copy (gsum is not touched here)
+            keep = (np.abs(b.g) >= remove_eps) & (b.slip == 0)
+            rec = np.zeros((int(keep.sum()), 6))
+            rec[:, 0] = b.corner[keep, 0] - b.dl[keep, 1] * 1e-4   # corner + rotl(dl) * 1e-4
+            rec[:, 1] = b.corner[keep, 1] + b.dl[keep, 0] * 1e-4
+            rec[:, 2] = b.g[keep]
+            shed.append(rec)
+        S.ctx.set_particles(np.concatenate([own] + shed) if shed else own)
+        segs, bodies = S._pack_bodies()
+        S.ctx.set_bodies(segs, bodies)
+        m = S.ctx.vorticity_raster(float(self.xmin), float(self.ymin), float(self.dxdy), self.xres, self.yres,
+                                   float(self.eps_mult), S.average_segment_length())
+        S.ctx.set_particles(own)                   # the Space's own list goes back to the device
+        S._dev_newer = False
+        self.map = m.astype(np.float32)
+
+    def at(self, xi, yj):
+        return self.map[yj, xi]

@@ -31,7 +31,10 @@ namespace vv {
 #endif
 constexpr int kDfWarps = VV_DF_WARPS;
 constexpr int kDfThreads = kDfWarps * 32;
-constexpr int kDfFlush = 512;                  // examine once the candidate list holds this many
+#ifndef VV_DF_FLUSH
+#define VV_DF_FLUSH 768
+#endif
+constexpr int kDfFlush = VV_DF_FLUSH;                  // examine once the candidate list holds this many
 constexpr int kDfPiece = 16;
 constexpr int kDfCap = kDfFlush + 32 * kDfPiece + 64;
 constexpr int kDfQueue = 96;                   // < 32 carried + 64 pushed per step

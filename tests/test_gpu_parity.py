@@ -401,6 +401,33 @@ def test_vorticity_raster(ctx, port, with_body):
     assert relerr(dbl, want) <= VTOL, relerr(dbl, want)
 
 
+def test_awkward_small_inputs(ctx, port):
+    """the sweep of tests/test_oracle_port.py::test_port_matches_reference_on_random_small_inputs on the CUDA path:
+    one or two particles, exact duplicates, points on a line, a lattice (ties in every comparison), zero
+    circulations, particles inside a body"""
+    rng = np.random.default_rng(2024)
+    for trial in range(30):
+        n = int(rng.choice([1, 2, 3, 15, 16, 17, 31, 64, 200, 400]))
+        kind = trial % 5
+        if kind == 0:
+            xy = rng.standard_normal((n, 2))
+        elif kind == 1:
+            xy = rng.uniform(-1, 1, (n, 2)); xy[n // 2:] = xy[: n - n // 2]
+        elif kind == 2:
+            xy = np.stack([np.linspace(-1, 1, n), np.zeros(n)], 1)
+        elif kind == 3:
+            k = int(np.ceil(np.sqrt(n)))
+            xy = np.stack(np.meshgrid(np.arange(k), np.arange(k)), -1).reshape(-1, 2)[:n] * 0.125 - 0.3
+        else:
+            rad = 0.5 + np.abs(rng.standard_normal(n)) * 0.2; th = rng.uniform(0, 2 * np.pi, n)
+            xy = np.stack([rad * np.cos(th), rad * np.sin(th)], 1); xy[: n // 8] *= 0.3
+        g = rng.uniform(-1, 1, n) / n
+        g[rng.uniform(size=n) < 0.1] = 0.0
+        xyg = np.concatenate([xy.astype(np.float64), g[:, None]], 1)
+        bodies = [cases.cylinder(0.5, 60)] if (kind == 4 or trial % 7 == 0) else []
+        run_pair(ctx, port, xyg, bodies=bodies, merge=(trial % 3 != 0))
+
+
 def test_against_reference_build(ctx, ref):
     """same comparison directly against the reference's own compiled code, where it travelled"""
     xyg = cases.cloud(20000, "gauss", "mixed", seed=21)

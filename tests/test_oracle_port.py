@@ -239,3 +239,61 @@ def test_vorticity_raster_matches_reference(port, ref):
     got = P.vorticity_raster(-1.0, -1.0, 0.04, 50, 50, 1.5, dl)
     assert (want == 0).sum() > 100 and np.abs(want).max() > 0
     assert same(got.astype(np.float32), want), np.abs(got.astype(np.float32) - want).max()
+
+
+def _pipeline_pair(port, ref, xyg, with_body, merge=True):
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    if with_body:
+        r.add_cylinder(0.5, 60)
+    r.set_list(xyg)
+    mn, mx = r.tree_params(8)
+    r.tree_build()
+    pb = port.Bodies.from_ref(r) if with_body else None
+    P = port.Port(xyg=xyg, bodies=pb)
+    P.tree_build(8, mn, mx)
+    d1, i1, nl1 = r.tree_export()
+    d2, i2, nl2 = P.tree_export()
+    assert nl1 == nl2 and same(d1, d2) and same(i1[:, [0, 1, 6, 7, 8, 9]], i2[:, [0, 1, 6, 7, 8, 9]])
+    for a, b in zip(r.tree_lists(nl1), P.tree_lists()):
+        assert same(a, b)
+    assert r.epsilon(merge) == P.epsilon(merge)
+    assert same(P.rec48(), r.get_list48())
+    pts = np.concatenate([xyg[: min(8, xyg.shape[0]), :2], np.array([[0.0, 0.0], [3.0, -2.0], [0.51, 0.0]])])
+    assert same(r.velocity_at(pts), P.velocity_at(pts, 1.0, 0.0, 0.05))
+    assert same(r.eps2h_h2_at(pts), P.eps2h_h2_at(pts))
+    if with_body:
+        assert same(r.node_influence(), P.node_influence())
+    r.convective(); P.convective(1.0, 0.0, 0.05)
+    r.diffusive(); P.diffusive(600.0)
+    assert same(P.rec48(), r.get_list48())
+    r.tree_destroy(); P.tree_destroy()
+    c1 = r.move_and_clean(True)
+    n2, c2 = P.move_and_clean(0.05)
+    assert c1 == c2 and same(P.rec48()[:, :5], r.get_list48()[:, :5])
+
+
+def test_port_matches_reference_on_random_small_inputs(port, ref):
+    """property-style sweep (fixed seeds): tiny and awkward inputs — one or two particles, exact duplicates, points on
+    a line, a lattice (ties in every comparison), zero circulations, particles inside the body — through the whole
+    pipeline and the 8(f) evaluators, port vs the compiled reference, bit for bit"""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.choice([1, 2, 3, 15, 16, 17, 31, 64, 200, 400]))
+        kind = trial % 5
+        if kind == 0:
+            xy = rng.standard_normal((n, 2))
+        elif kind == 1:
+            xy = rng.uniform(-1, 1, (n, 2)); xy[n // 2:] = xy[: n - n // 2]          # exact duplicates
+        elif kind == 2:
+            xy = np.stack([np.linspace(-1, 1, n), np.zeros(n)], 1)                    # on a line (h == 0 boxes)
+        elif kind == 3:
+            k = int(np.ceil(np.sqrt(n)))
+            g2 = np.stack(np.meshgrid(np.arange(k), np.arange(k)), -1).reshape(-1, 2)[:n] * 0.125   # lattice: ties
+            xy = g2.astype(np.float64) - 0.3
+        else:
+            rad = 0.5 + np.abs(rng.standard_normal(n)) * 0.2; th = rng.uniform(0, 2 * np.pi, n)
+            xy = np.stack([rad * np.cos(th), rad * np.sin(th)], 1); xy[: n // 8] *= 0.3  # some inside the body
+        g = rng.uniform(-1, 1, n) / n
+        g[rng.uniform(size=n) < 0.1] = 0.0
+        xyg = np.concatenate([xy, g[:, None]], 1)
+        _pipeline_pair(port, ref, xyg, with_body=(kind == 4 or trial % 7 == 0), merge=(trial % 3 != 0))

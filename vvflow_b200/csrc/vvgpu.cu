@@ -6,7 +6,7 @@
 #include "vvgpu_diff.cuh"
 #include "vvgpu_point.cuh"
 #include "vvgpu_move.cuh"
-#include "vvgpu_tree_coop.cuh"
+#include "vvgpu_tree_build.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -101,15 +101,17 @@ struct vvgpu_ctx {
     int tn = 0, tnseg = 0;  // objects included in the built tree
     int nnodes = 0, nleaves = 0, depth = 0, ngroups = 0;
     double farc = 8;
-    Buf t_x, t_y, t_h, t_w, t_bb, t_first, t_last, t_sfirst, t_slast, t_ch1, t_parent, t_depth, t_status, t_axis,
-        t_nl, t_nn, t_lstart, t_pre, t_cmp, t_cmm, t_leafnode, t_pnode, t_snode[2], t_segperm[2], t_perm, t_tmpR;
-    int segcur = 0;
-    Buf scan_part, scan_out, flags, scan_seg, part_n, part_p, part_s, build_state;
-    int coop_grid = 0;
+    Buf t_x, t_y, t_h, t_w, t_bb, t_first, t_last, t_sfirst, t_slast, t_ch1, t_depth, t_status, t_axis,
+        t_nl, t_nn, t_lstart, t_pre, t_cmp, t_cmm, t_leafnode, t_segperm[2], t_perm, t_tmpR;
+    const int segcur = 0;   // the final segment order is always in t_segperm[0] (t_segperm[1] is the build's scratch)
+    Buf scan_part, scan_out, flags, build_state;
+    // tree build (vvgpu_tree_build.cuh)
+    Buf b_enc, b_tilepre, b_chunktot, b_actm, b_sublist, b_scratch, b_arena, b_aux, b_subinfo;
+    int coop_grid = 0, sub_grid = 0;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
     Buf g_leaf, g_mask, g_cursor, slot_base, slot_count, taylor, farcount, d_err;
     long long pool_cap = 0;
-    std::vector<int> h_lvl;
+    std::vector<int> h_hist;   // nodes per tree depth
     int lists_g0 = 0, lists_g1 = 0;
     Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, src2, lbox, wall_d, wall_key, hv_list,
         hv_inode, hv_imask, hv_icount, hv_tpart, hv_off;
@@ -131,12 +133,11 @@ struct vvgpu_ctx {
         t.x = t_x.as<double>(); t.y = t_y.as<double>(); t.h = t_h.as<double>(); t.w = t_w.as<double>();
         t.bb = t_bb.as<u64>();
         t.first = t_first.as<int>(); t.last = t_last.as<int>(); t.sfirst = t_sfirst.as<int>(); t.slast = t_slast.as<int>();
-        t.ch1 = t_ch1.as<int>(); t.parent = t_parent.as<int>(); t.depth = t_depth.as<int>();
+        t.ch1 = t_ch1.as<int>(); t.depth = t_depth.as<int>();
         t.status = t_status.as<unsigned char>(); t.axis = t_axis.as<unsigned char>();
         t.nl = t_nl.as<int>(); t.nn = t_nn.as<int>(); t.lstart = t_lstart.as<int>(); t.pre = t_pre.as<int>();
         t.cmp = t_cmp.as<double>(); t.cmm = t_cmm.as<double>();
         t.leaf_node = t_leafnode.as<int>();
-        t.pnode = t_pnode.as<int>(); t.snode = t_snode[segcur].as<int>();
         return t;
     }
     LeafDev Lv() {
@@ -212,23 +213,22 @@ int read_u32(vvgpu_ctx* c, const u32* d, u32* h) {
     return 0;
 }
 
-constexpr int kMaxDepth = 4096;
-
 int alloc_tree(vvgpu_ctx* c, size_t cap, size_t n, size_t nseg) {
     bool ok = true;
     c->t_x.get<double>(cap, &ok); c->t_y.get<double>(cap, &ok); c->t_h.get<double>(cap, &ok); c->t_w.get<double>(cap, &ok);
     c->t_bb.get<u64>(4 * cap, &ok);
     c->t_first.get<int>(cap, &ok); c->t_last.get<int>(cap, &ok); c->t_sfirst.get<int>(cap, &ok); c->t_slast.get<int>(cap, &ok);
-    c->t_ch1.get<int>(cap, &ok); c->t_parent.get<int>(cap, &ok); c->t_depth.get<int>(cap, &ok);
+    c->t_ch1.get<int>(cap, &ok); c->t_depth.get<int>(cap, &ok);
     c->t_status.get<unsigned char>(cap, &ok); c->t_axis.get<unsigned char>(cap, &ok);
-    c->t_pnode.get<int>(n, &ok); c->t_perm.get<int>(n, &ok); c->t_tmpR.get<int>(n, &ok);
-    for (int k = 0; k < 2; k++) { c->t_snode[k].get<int>(nseg, &ok); c->t_segperm[k].get<int>(nseg, &ok); }
+    c->t_perm.get<int>(n, &ok); c->t_tmpR.get<int>(n, &ok);
+    for (int k = 0; k < 2; k++) c->t_segperm[k].get<int>(nseg, &ok);
     c->scan_out.get<u32>(std::max(std::max(n, nseg), cap) + 2, &ok);
     c->flags.get<u32>(std::max(n, cap) + 2, &ok);
     NEED(ok);
     return 0;
 }
 
+// K1 (vvgpu_tree_build.cuh): top phase (cooperative) -> CTA-built subtrees -> top sweeps -> relocation; one read-back
 int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_node, unsigned mask) {
     const int n = (mask & 1u) ? (int)c->n : 0;
     const int nseg = (mask & 2u) ? c->nseg : 0;
@@ -241,46 +241,61 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     c->t_nl.get<int>(cap, &ok); c->t_nn.get<int>(cap, &ok); c->t_lstart.get<int>(cap, &ok); c->t_pre.get<int>(cap, &ok);
     c->t_cmp.get<double>(3 * cap, &ok); c->t_cmm.get<double>(3 * cap, &ok);
     c->t_leafnode.get<int>(cap, &ok);
-    u32* Gs = c->scan_seg.get<u32>((size_t)nseg + 2, &ok);
-    u32* partN = c->part_n.get<u32>(cap / kCoopTile + 2, &ok);
-    u32* partP = c->part_p.get<u32>((size_t)n / kCoopTile + 2, &ok);
-    u32* partS = c->part_s.get<u32>((size_t)nseg / kCoopTile + 2, &ok);
     BuildState* bs = c->build_state.get<BuildState>(1, &ok);
     NEED(ok);
-    c->segcur = 0;
     c->tn = n; c->tnseg = nseg; c->farc = (double)far_criteria;
     if (c->coop_grid == 0) {
-        int sms = 0, occ = 0;
+        int sms = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tree_build_coop, kCoopThreads, 0));
-        if (occ < 1) return fail(c, VVGPU_ECUDA, "k_tree_build_coop does not fit on an SM");
-        c->coop_grid = sms;
+        CK(cudaFuncSetAttribute(k_tree_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SubSmem)));
+        c->coop_grid = std::min(sms, kTopThreads);   // the top phase scans one total per CTA with one block scan
+        c->sub_grid = sms;
     }
-    CoopArgs A;
+    // splitting top-phase nodes of one level are disjoint and hold > kSubCap particles or > kSubSegCap segments
+    const int maxact = n / kSubCap + nseg / kSubSegCap + 2;
+    const size_t top_smem = top_smem_bytes(maxact);
+    if (top_smem > 160 * 1024) return fail(c, VVGPU_ELIMIT, "tree build: too many particles for the top-phase tables");
+    if (top_smem > 40 * 1024) CK(cudaFuncSetAttribute(k_tree_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
+    const size_t ntile_max = (size_t)n / kTopThreads + maxact + 2;
+    TopArgs A;
     A.T = c->T();
     A.bp = BuildParams{min_node, max_node};
     A.px = P.x.as<double>(); A.py = P.y.as<double>(); A.pg = P.g.as<double>();
+    A.perm = c->t_perm.as<int>();
     A.sx = c->s_rx.as<double>(); A.sy = c->s_ry.as<double>();
+    A.segperm = c->t_segperm[0].as<int>(); A.segtmp = c->t_segperm[1].as<int>();
     A.n = n; A.nseg = nseg;
-    A.perm = c->t_perm.as<int>(); A.tmpR = c->t_tmpR.as<int>();
-    for (int k = 0; k < 2; k++) { A.segperm[k] = c->t_segperm[k].as<int>(); A.snode[k] = c->t_snode[k].as<int>(); }
-    A.G = c->scan_out.as<u32>(); A.Gs = Gs; A.splitflag = c->flags.as<u32>();
-    A.partN = partN; A.partP = partP; A.partS = partS;
-    A.st = bs; A.cap = (long long)cap;
+    A.enc = c->b_enc.get<u32>((size_t)n + 1, &ok);
+    A.tmpR = c->t_tmpR.as<int>();
+    A.tilepre = c->b_tilepre.get<int>(ntile_max, &ok);
+    A.chunktot = c->b_chunktot.get<int>(c->coop_grid, &ok);
+    A.act_m = c->b_actm.get<int>(maxact, &ok);
+    A.sublist = c->b_sublist.get<int>(((size_t)n + nseg) / 2 + 2, &ok);
+    A.st = bs; A.cap = (long long)cap; A.maxact = maxact;
+    SubNode* scratch = c->b_scratch.get<SubNode>(cap, &ok);
+    unsigned char* arena = c->b_arena.get<unsigned char>((size_t)c->sub_grid * sub_arena_bytes(), &ok);
+    int* aux = c->b_aux.get<int>(3 * cap, &ok);
+    int* subinfo = c->b_subinfo.get<int>(3 * (((size_t)n + nseg) / 2 + 2), &ok);
+    NEED(ok);
     void* args[] = {&A};
-    CK(cudaLaunchCooperativeKernel((void*)k_tree_build_coop, dim3(c->coop_grid), dim3(kCoopThreads), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((void*)k_tree_top, dim3(c->coop_grid), dim3(kTopThreads), args, top_smem, st));
     c->launches++;
-    CK(cudaMemcpyAsync(c->h_pinned + 32, bs, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SubArgs SA{A.T, A.bp, A.px, A.py, A.pg, A.perm, A.sx, A.sy, A.segperm, scratch, A.sublist, bs, arena};
+    k_tree_sub<<<c->sub_grid, kSubThreads, sizeof(SubSmem), st>>>(SA); CKLAUNCH();
+    const size_t nsubmax = ((size_t)n + nseg) / 2 + 2;
+    SweepArgs WA{A.T, A.px, A.py, A.pg, scratch, A.sublist, aux, aux + cap, aux + 2 * cap, subinfo, subinfo + nsubmax, subinfo + 2 * nsubmax, bs};
+    k_tree_topsweep<<<1, 1024, 0, st>>>(WA); CKLAUNCH();
+    k_tree_relocate<<<c->sub_grid * 8, 256, 0, st>>>(A.T, scratch, A.sublist, subinfo, subinfo + nsubmax, subinfo + 2 * nsubmax, bs); CKLAUNCH();
+    CK(cudaMemcpyAsync(c->h_pinned + 32, bs, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int* hb = c->h_pinned + 32;
+    if (hb[3] == 2) return fail(c, VVGPU_ELIMIT, "tree build: a top level is wider than its tables");
     if (hb[3]) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
     c->nnodes = hb[0]; c->depth = hb[1];
     const u32 nl = (u32)hb[2];
-    c->h_lvl.resize(c->depth + 2);
-    CK(cudaMemcpyAsync(c->h_lvl.data(), (const int*)bs + 4, sizeof(int) * (c->depth + 2), cudaMemcpyDeviceToHost, st));
+    c->h_hist.resize(c->depth + 2);
+    CK(cudaMemcpyAsync(c->h_hist.data(), bs->hist, sizeof(int) * (c->depth + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // the stable segment split ping-pongs between two buffers: one flip per level that split
-    c->segcur = (nseg > 0) ? (c->depth & 1) : 0;
     c->nleaves = (int)nl;
     c->ngroups = cdiv(c->nleaves, kGroupLeaves);
     TreeDev T = c->T();
@@ -330,8 +345,8 @@ int lists_impl(vvgpu_ctx* c, bool all) {
     // heavy groups are cut at the first tree level that is at least 256 nodes wide
     int cut = c->depth;
     for (int d = 0; d <= c->depth; d++)
-        if (c->h_lvl[d + 1] - c->h_lvl[d] >= 256) { cut = d; break; }
-    const int item_cap = std::max(2, c->h_lvl[cut + 1] - c->h_lvl[cut]);
+        if (c->h_hist[d] >= 256) { cut = d; break; }
+    const int item_cap = std::max(2, c->h_hist[cut]);
     const long long nreg_slots = (long long)ng * kGroupSlots;
     for (int attempt = 0;; attempt++) {
         if (attempt > 6) return fail(c, VVGPU_ELIMIT, "interaction lists do not fit the entry pool");
@@ -555,9 +570,9 @@ void vvgpu_destroy(vvgpu_ctx* c) {
     Buf* all[] = {&c->stage, &c->s_rx, &c->s_ry, &c->s_cx, &c->s_cy, &c->s_dlx, &c->s_dly, &c->s_g, &c->s_ie, &c->s_slip,
                   &c->s_body, &c->b_first, &c->b_prop, &c->d_fric, &c->d_gsum, &c->d_fdt, &c->d_gdead, &c->d_cleaned,
                   &c->t_x, &c->t_y, &c->t_h, &c->t_w, &c->t_bb, &c->t_first, &c->t_last, &c->t_sfirst, &c->t_slast,
-                  &c->t_ch1, &c->t_parent, &c->t_depth, &c->t_status, &c->t_axis, &c->t_nl, &c->t_nn, &c->t_lstart,
-                  &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode, &c->t_pnode, &c->t_snode[0], &c->t_snode[1],
-                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->scan_seg, &c->part_n, &c->part_p, &c->part_s, &c->build_state,
+                  &c->t_ch1, &c->t_depth, &c->t_status, &c->t_axis, &c->t_nl, &c->t_nn, &c->t_lstart,
+                  &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode,
+                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_actm, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,

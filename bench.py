@@ -289,16 +289,13 @@ def ours(args):
               + f" sum={sum(phase_sum.values()) / args.steps:.2f} wall/step={wall_ms / args.steps:.2f}", file=sys.stderr)
     # interaction counts of the final state's tree (work done per step)
     ctx.tree_build(FAR, 0.0, DBL_MAX)
-    local_pairs, local_far = ctx.count_interactions()   # of this rank's slice of the leaf groups
+    near_pairs, far_nodes = ctx.count_interactions()   # totals over the ranks (summed inside the library)
+    local_pairs = near_pairs / world                    # the groups are dealt round-robin: every rank has ~1/world of them
     nn, nl, depth = ctx.tree_counts()
     ctx.tree_destroy()
     ctx.phase_times()
-    near_pairs, far_nodes = local_pairs, local_far
     conv_ms_max = phase_sum["conv"] / args.steps
     if world > 1:
-        t = torch.tensor([local_pairs, local_far], dtype=torch.float64, device=device)
-        dist.all_reduce(t)
-        near_pairs, far_nodes = float(t[0].item()), float(t[1].item())
         t = torch.tensor([conv_ms_max], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         conv_ms_max = float(t[0].item())
@@ -308,30 +305,20 @@ def ours(args):
     # all-gathered over NVLink into a device buffer that is handed to the library; pushing the full list through
     # every rank's PCIe link cost 6 ms per step at 8 GPUs.
     lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-    if world > 1:
-        per = (n + world - 1) // world
-        dev_slice = torch.zeros((per, 6), dtype=torch.float64, device=device)
-        dev_all = torch.empty((world * per, 6), dtype=torch.float64, device=device)
-        dev_in = torch.empty((n, 6), dtype=torch.float64, device=device)
-        dev_out = torch.empty((n, 6), dtype=torch.float64, device=device)
+    rec_bytes = 48
 
     def e2e_in():
         if world == 1:
             ctx.set_particles_ptr(host_in.data_ptr(), n)
-            return
-        dev_slice[: hi - lo].copy_(host_in[lo:hi], non_blocking=True)
-        dist.all_gather_into_tensor(dev_all, dev_slice)
-        torch.cat([dev_all[r * per: r * per + ((n * (r + 1)) // world - (n * r) // world)] for r in range(world)], out=dev_in)
-        torch.cuda.synchronize()
-        ctx.set_particles_ptr(dev_in.data_ptr(), n)
+        else:   # one slice per rank over PCIe, gathered over NVLink inside the library
+            ctx.set_particles_slice_ptr(host_in.data_ptr() + lo * rec_bytes, lo, hi - lo, n)
 
     def e2e_out():
         if world == 1:
             return ctx.get_particles_ptr(host_out.data_ptr(), n), n
-        k = ctx.get_particles_ptr(dev_out.data_ptr(), n)          # every rank holds the whole (replicated) result
+        k = ctx.n                                                   # every rank holds the whole (replicated) result
         a, b = (k * rank) // world, (k * (rank + 1)) // world       # ... and brings its share back to the host
-        host_out[a:b].copy_(dev_out[a:b], non_blocking=True)
-        torch.cuda.synchronize()
+        ctx.get_particles_range_ptr(host_out.data_ptr() + a * rec_bytes, a, b - a)
         return k, b - a
 
     for _ in range(min(args.warmup, 2)):

@@ -76,6 +76,8 @@ int vvgpu_append_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size
 int vvgpu_particle_count(vvgpu_ctx* ctx, int list, size_t* n);
 /* current device order (after tree_build: the reference's in-place permuted order) */
 int vvgpu_get_particles(vvgpu_ctx* ctx, int list, vvgpu_obj* out, size_t cap, size_t* n);
+/* records [first, first + count) of the current device order (a rank of a multi-GPU job brings back its share only) */
+int vvgpu_get_particles_range(vvgpu_ctx* ctx, int list, vvgpu_obj* out, size_t first, size_t count);
 /* orig[i] = index, in the order of the last set_particles call, of the particle now at i */
 int vvgpu_get_permutation(vvgpu_ctx* ctx, int list, int32_t* orig, size_t cap);
 int vvgpu_set_bodies(vvgpu_ctx* ctx, const vvgpu_seg* segs, size_t nseg, const vvgpu_body* bodies, size_t nbody);
@@ -105,11 +107,8 @@ int vvgpu_count_interactions(vvgpu_ctx* ctx, double* near_pairs, double* far_nod
 
 /* ---- MEpsilonFast::CalcEpsilonFast(merge), MEpsilonFast.cpp:11-63; Merged() -> *merged ---- */
 int vvgpu_epsilon(vvgpu_ctx* ctx, int merge, int* merged);
-/* multi-GPU helper: the first round of CalcEpsilonFast(merge=true) on this rank's slice only;
- * *ncandidates = particles of the slice that want to merge. If the sum over ranks is 0 no merge can
- * happen and the slice's _1_eps are final; otherwise every rank calls vvgpu_epsilon(merge=1), which
- * replays the merges replicated. */
-int vvgpu_epsilon_probe(vvgpu_ctx* ctx, int* ncandidates);
+/* rounds the merge fixed point of the last vvgpu_epsilon(merge=1) took (one host read-back each) */
+int vvgpu_merge_rounds(vvgpu_ctx* ctx, int* rounds);
 /* ---- MConvectiveFast::process_all_lists, MConvectiveFast.cpp:36-114. inf_* = S->inf_speed(),
  * dt = S->dt (sink epsilon, :160), sinks = Space::SourceList as (x,y,g) triples -------------- */
 int vvgpu_convective(vvgpu_ctx* ctx, double inf_vx, double inf_vy, double dt, const double* sinks_xyg,
@@ -147,19 +146,30 @@ int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);
 int vvgpu_move_and_clean(vvgpu_ctx* ctx, double dt_eff, double remove_eps, int remove_in_body,
                          double* fdt_dead_xyo, double* g_dead, double* gsum_delta, size_t* cleaned);
 
-/* ---- multi-GPU (target-sharded, source-replicated) -------------------------- */
-/* This context computes epsilon/convective/diffusive only for its slice of the leaf groups
- * (balanced by near-pair count); the caller all-gathers the slices between phases. */
-int vvgpu_set_shard(vvgpu_ctx* ctx, int rank, int nranks);
-/* particle range [*first, *last) this rank owns after tree_build */
-int vvgpu_shard_range(vvgpu_ctx* ctx, size_t* first, size_t* last);
-/* every rank's range, [first_last[2r], first_last[2r+1]): the tree and the cut are replicated, so no
- * communication is needed to learn the other ranks' slices */
-int vvgpu_shard_bounds(vvgpu_ctx* ctx, size_t* first_last, size_t nranks);
-/* device pointers of the SoA arrays (x y g vx vy ieps), for NCCL all-gathers by the host layer */
+/* ---- multi-GPU (target-sharded, source-replicated) ----------------------------
+ * Every rank holds all particles and rebuilds the (deterministic) tree; the leaf groups are dealt block-cyclically
+ * over the ranks and each rank computes epsilon / convective / diffusive for the particles of ITS groups. The
+ * exchanges happen inside the calls, on the context's stream: _1_eps (and the merge columns, once per round of the
+ * merge fixed point) at the end of vvgpu_epsilon, v before vvgpu_tree_destroy / vvgpu_get_particles, TAtt::fric
+ * summed over the ranks in vvgpu_diffusive (MDiffusiveFast.cpp:121-122). All ranks make the same calls in the same
+ * order with the same arguments; the results are bit-identical on every rank and to the single-GPU results, except
+ * fric (a sum over ranks: 1e-10). Two transports:
+ *   one process per GPU (torchrun):  rank 0 calls vvgpu_comm_unique_id, the host layer carries the 128 bytes to the
+ *     other ranks, every rank calls vvgpu_comm_init (NCCL all-gathers over NVLink; libnccl.so.2 is dlopen'ed);
+ *   one process, several GPUs:       vvgpu_group_create makes one context per entry of `devices` (entries may
+ *     repeat: several ranks on one device, for tests); each context is then driven from its own host thread and
+ *     the ranks exchange by peer-to-peer copies. */
+int vvgpu_comm_unique_id(void* id128, size_t cap);
+int vvgpu_comm_init(vvgpu_ctx* ctx, int rank, int nranks, const void* id128);
+int vvgpu_group_create(const int* devices, int n, vvgpu_ctx** ctxs_out);
+int vvgpu_comm_info(vvgpu_ctx* ctx, int* rank, int* nranks, int* kind /* 0 none, 1 NCCL, 2 in-process */);
+/* rank that owns leaf group `group` (groups of 32 consecutive leaves, in pieces of 4, round-robin); no device needed */
+int vvgpu_shard_owner(int group, int nranks);
+/* e2e upload with one slice per rank: rank r passes records [n r / P, n (r + 1) / P) of a list of n_total (host or
+ * device address); the slices are gathered over the transport */
+int vvgpu_set_particles_slice(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t first, size_t count, size_t n_total);
+/* device pointers of the SoA arrays (x y g vx vy ieps) */
 int vvgpu_particle_arrays_dev(vvgpu_ctx* ctx, int list, double** arrays6, size_t* n);
-/* tell the context that ieps / (x,y,g) of non-owned particles were filled in by the caller */
-int vvgpu_after_exchange(vvgpu_ctx* ctx, int phase);
 int vvgpu_stream(vvgpu_ctx* ctx, void** cuda_stream);
 int vvgpu_synchronize(vvgpu_ctx* ctx);
 

@@ -23,6 +23,10 @@ static double sqr(double v) { return v * v; }
 static int sgn(double v) { return (v > 0) ? 1 : ((v < 0) ? -1 : 0); } /* TObj.hpp:8 */
 static double dmax(double a, double b) { return (a < b) ? b : a; }     /* std::max */
 static double dmin(double a, double b) { return (b < a) ? b : a; }     /* std::min */
+/* MConvectiveFast.cpp:165 writes a bare `abs(src.g)`: with the reference's includes and -std=c++11 that is ::abs(int),
+ * so the strength is truncated to an integer first (no regularisation at all for |g| < 1). Pinned against the
+ * compiled reference by tests/test_oracle_port.py::test_sinks_match_reference. */
+static double sink_abs(double g) { int t = (int)g; return (double)(t < 0 ? -t : t); }
 
 /* bench.py's bounded CPU sample: epsilon / convective / diffusive visit every stride-th leaf only */
 static int64_t g_stride = 1, g_phase = 0;
@@ -440,7 +444,7 @@ void vvo_convective(const vvo_tree* t, vvo_plist* p, const vvo_bodies* b, double
             double eps2_div_srcg = dt * C_1_PI;
             for (int64_t k = 0; k < nsink; k++) {
                 double dx = px - sinks[3 * k], dy = py - sinks[3 * k + 1], sg = sinks[3 * k + 2];
-                double q = sg / (dx * dx + dy * dy + eps2_div_srcg * fabs(sg));
+                double q = sg / (dx * dx + dy * dy + eps2_div_srcg * sink_abs(sg));
                 sx += dx * q; sy += dy * q;
             }
             p->vx[i] += sx * C_1_2PI; p->vy[i] += sy * C_1_2PI;
@@ -494,7 +498,7 @@ void vvo_velocity_at(const vvo_tree* t, const vvo_plist* p, const vvo_bodies* b,
         double eps2_div_srcg = dt * C_1_PI;
         for (int64_t k = 0; k < nsink; k++) {
             double dx = px - sinks[3 * k], dy = py - sinks[3 * k + 1], sg = sinks[3 * k + 2];
-            double w = sg / (dx * dx + dy * dy + eps2_div_srcg * fabs(sg));
+            double w = sg / (dx * dx + dy * dy + eps2_div_srcg * sink_abs(sg));
             sx += dx * w; sy += dy * w;
         }
         resx += sx * C_1_2PI; resy += sy * C_1_2PI;

@@ -85,11 +85,41 @@ def relerr(a, b):
     return float(np.max(np.abs(a[ok] - b[ok]))) / scale
 
 
+def relerr_elem(a, b, floor=1e-4):
+    """element-wise relative error with a floor: max_i |a_i - b_i| / max(|b_i|, floor * ||b||_inf). For (n, 2) arrays an
+    element is a ROW (a particle's velocity vector). Returns (error, index of the worst element)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0, -1
+    na, nb = np.isnan(a), np.isnan(b)
+    if np.any(na != nb):
+        return float("inf"), int(np.argmax((na != nb).reshape(a.shape[0], -1).any(axis=1)))
+    a, b = np.where(na, 0.0, a), np.where(nb, 0.0, b)
+    if a.ndim == 2:
+        diff, mag = np.hypot.reduce(a - b, axis=1), np.hypot.reduce(b, axis=1)
+    else:
+        diff, mag = np.abs(a - b), np.abs(b)
+    scale = np.maximum(mag, floor * max(float(mag.max()), 1e-300))
+    e = diff / scale
+    k = int(np.argmax(e))
+    return float(e[k]), k
+
+
+def check_close(a, b, tol, what):
+    """the velocity / integral-sum bar of north_star (1e-10 relative): norm-wise AND element-wise (with a floor of
+    1e-4 of the field maximum, so that exact zeros and cancellation residues do not divide by nothing)"""
+    nw = relerr(a, b)
+    ew, k = relerr_elem(a, b)
+    assert nw <= tol and ew <= tol, (f"{what}: norm-wise {nw:.3e}, element-wise {ew:.3e} at element {k}: "
+                                     f"got {np.asarray(a)[k] if k >= 0 else None}, want {np.asarray(b)[k] if k >= 0 else None}")
+    return max(nw, ew)
+
+
 # ---- golden fixtures (tests/golden/*.npz, generated from the compiled reference) ------------------
 import os
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN = ("cloud_mixed_3000", "blob_same_4000", "cyl_re600_step30")
+GOLDEN = ("cloud_mixed_3000", "blob_same_4000", "cyl_re600_step30")   # + sinks_1500 (convective only)
 
 
 def golden(name):

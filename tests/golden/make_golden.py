@@ -104,6 +104,24 @@ def main():
     for k in range(4):
         print("  force_hydro t=%.2f: %+.6e %+.6e %+.6e" % (0.05 * k, *rows[k]))
 
+    # 4. point sinks / sources (Space::SourceList) through process_all_lists and velocity(p): strengths below and above 1
+    #    (MConvectiveFast.cpp:165 truncates the strength to an integer in the reference build)
+    xyg = cases.cloud(1500, "gauss", "mixed", seed=33)
+    sinks = np.array([[0.3, 0.2, 0.2], [-0.5, 0.1, -1.5], [0.0, -0.4, 2.7], [1.1, 0.9, -0.99]])
+    r = pyref.Ref(re=600, dt=0.05, inf_vx=1.0, inf_vy=0.25)
+    r.set_list(xyg)
+    r.set_list(sinks, pyref.SOURCE)
+    r.tree_build()
+    r.epsilon(False)
+    d = {"xyg": xyg, "sinks": sinks, "params": np.array([600, 0.05, 1.0, 0.25])}
+    rng = np.random.default_rng(5)
+    d["pts"] = np.concatenate([rng.standard_normal((60, 2)), sinks[:, :2] + 1e-3])
+    d["vel_at_pts"] = r.velocity_at(d["pts"])
+    r.convective()
+    d["after_conv"] = r.get_list48()
+    np.savez_compressed(os.path.join(HERE, "sinks_1500.npz"), **d)
+    print("sinks_1500: |v|max", np.abs(d["after_conv"][:, 3:5]).max())
+
 
 if __name__ == "__main__":
     main()

@@ -1,12 +1,12 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic in vvflow_b200/multigpu.py: slice
-bookkeeping, tiling check, uneven all-gather, and the probe -> replay decision for merging. The CUDA
-context is replaced by a numpy double with the same method names; the exchange code is the real one."""
+"""world_size-2 gloo test (CPU) of the multi-GPU HOST logic that is left in vvflow_b200/multigpu.py now that the data
+plane lives in the library: the NCCL unique id travels from rank 0 to every rank, every rank hands the SAME id and its
+own (rank, world) to vvgpu_comm_init, and the ranks then make identical call sequences. The CUDA context is replaced by
+a recording double; the ownership rule is the library's own (vvgpu_shard_owner needs no device)."""
 import os
 import sys
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -14,85 +14,64 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class FakeCtx:
-    """stands in for capi.Context: particle i 'computes' f(i) for the targets of its slice only"""
+    def __init__(self):
+        self.calls, self.comm = [], None
 
-    def __init__(self, n, rank, world, candidates_on=None):
-        self.nn, self.rank, self.world = n, rank, world
-        self.arr = [np.zeros(n) for _ in range(6)]
-        self.candidates_on = candidates_on
-        self.calls = []
-        cuts = [0, n // 3, n] if world == 2 else np.linspace(0, n, world + 1).astype(int).tolist()
-        self.first, self.last = cuts[rank], cuts[rank + 1]
+    def comm_info(self):
+        return (0, 1, 0) if self.comm is None else (self.comm[0], self.comm[1], 1)
 
-    n = property(lambda self: self.nn)
+    def comm_init(self, rank, nranks, ident):
+        self.comm = (rank, nranks, bytes(ident))
 
-    def set_shard(self, rank, world): pass
-    def tree_build(self, *a): self.calls.append("build")
-    def tree_destroy(self): self.calls.append("destroy")
-    def shard_range(self): return self.first, self.last
-    def synchronize(self): pass
-    def tensors(self): return [torch.from_numpy(a) for a in self.arr]
-
-    def epsilon_probe(self):
-        self.calls.append("probe")
-        self.arr[5][self.first:self.last] = 1.0 + np.arange(self.first, self.last)
-        return 3 if self.candidates_on == self.rank else 0
-
-    def epsilon(self, merge):
-        self.calls.append("eps_replicated" if merge else "eps")
-        if merge:  # replicated replay: every rank computes everything
-            self.arr[5][:] = 100.0 + np.arange(self.nn)
-            return 7
-        self.arr[5][self.first:self.last] = 1.0 + np.arange(self.first, self.last)
-        return 0
-
-    def convective(self, *a):
-        self.arr[3][self.first:self.last] = 2.0 * np.arange(self.first, self.last)
-        self.arr[4][self.first:self.last] = -1.0 * np.arange(self.first, self.last)
-
-    def diffusive(self, re, want_fric=False):
-        self.arr[3][self.first:self.last] += 0.5
-
-    def move_and_clean(self, dt):
-        return {"cleaned": 0}
+    def tree_build(self, *a): self.calls.append(("build",) + a)
+    def epsilon(self, merge): self.calls.append(("eps", merge)); return 5
+    def convective(self, *a): self.calls.append(("conv",) + a)
+    def diffusive(self, re, want_fric=False): self.calls.append(("diff", re)); return None
+    def tree_destroy(self): self.calls.append(("destroy",))
+    def move_and_clean(self, dt): self.calls.append(("move", dt)); return {"cleaned": 0}
 
 
-def _worker(rank, world, port, n, candidates_on, q):
+def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT)
+    from vvflow_b200 import capi, multigpu
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from vvflow_b200 import multigpu
-    ctx = FakeCtx(n, rank, world, candidates_on)
-    step = multigpu.ShardedStep(ctx, rank, world, "cpu")
-    out = step.step(8, 0.0, 1e300, True, 1.0, 0.0, 0.005, 1000.0)
-    ok = True
-    i = np.arange(n)
-    if candidates_on is None:
-        ok &= bool(np.array_equal(ctx.arr[5], 1.0 + i)) and "eps_replicated" not in ctx.calls
-    else:
-        ok &= bool(np.array_equal(ctx.arr[5], 100.0 + i)) and "eps_replicated" in ctx.calls and out["merged"] == 7
-    ok &= bool(np.array_equal(ctx.arr[3], 2.0 * i + 0.5)) and bool(np.array_equal(ctx.arr[4], -1.0 * i))
-    # a broken tiling must be detected
-    try:
-        multigpu.check_tiling(np.array([[0, 5], [6, n]]), n)
-        ok = False
-    except RuntimeError:
-        pass
-    q.put((rank, ok, step.bounds.tolist()))
+    capi.comm_unique_id = lambda: bytes(range(128))       # no NCCL needed on the CPU box: the id is opaque bytes
+    ctx = FakeCtx()
+    st = multigpu.ShardedStep(ctx, rank, world)
+    out = st.step(8, 0.0, 1e300, True, 1.0, 0.0, 0.05, 600.0)
+    q.put((rank, ctx.comm, ctx.calls, out["merged"]))
+    dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("candidates_on", [None, 1])
-def test_sharded_step_two_ranks(candidates_on):
+def test_unique_id_reaches_every_rank_and_calls_are_identical():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (0 if candidates_on is None else 1)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1000, candidates_on, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
-    assert all(ok for _, ok, _ in res), res
-    assert res[0][2] == res[1][2] == [[0, 333], [333, 1000]]
+    assert [r[1][:2] for r in res] == [(0, 2), (1, 2)]
+    assert res[0][1][2] == res[1][1][2] == bytes(range(128))
+    assert res[0][2] == res[1][2] and [c[0] for c in res[0][2]] == ["build", "eps", "conv", "diff", "destroy", "move"]
+    assert res[0][3] == res[1][3] == 5
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_ownership_tiles_the_groups(world):
+    """every leaf group has exactly one owner, pieces of 4 consecutive groups go round the ranks"""
+    sys.path.insert(0, ROOT)
+    from vvflow_b200 import multigpu
+    ng = 1003
+    owned = [multigpu.owned_groups(ng, r, world) for r in range(world)]
+    allg = sorted(g for o in owned for g in o)
+    assert allg == list(range(ng))
+    sizes = [len(o) for o in owned]
+    assert max(sizes) - min(sizes) <= 4
+    for r, o in enumerate(owned):
+        assert all((g // 4) % world == r for g in o)

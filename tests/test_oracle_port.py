@@ -58,6 +58,31 @@ def test_port_matches_golden(port, name):
     run_port_on_golden(port, cases.golden(name))
 
 
+def test_sinks_match_golden(port):
+    """sink_list_influence (MConvectiveFast.cpp:153-170) through process_all_lists and velocity(p), against the
+    compiled reference's values: its bare abs(src.g) truncates the strength to an integer"""
+    d = cases.golden("sinks_1500")
+    re, dt, ivx, ivy = d["params"]
+    P = port.Port(xyg=d["xyg"])
+    P.tree_build(8, 0.0)
+    P.epsilon(False)
+    assert same(P.velocity_at(d["pts"], ivx, ivy, dt, sinks=d["sinks"]), d["vel_at_pts"])
+    P.convective(ivx, ivy, dt, sinks=d["sinks"])
+    assert same(P.rec48(), d["after_conv"])
+
+
+def test_sinks_match_reference(port, ref):
+    xyg = cases.cloud(2000, "gauss", "mixed", seed=3)
+    sinks = np.array([[0.3, 0.2, 0.2], [-0.5, 0.1, -1.5], [0.0, -0.4, 2.7]])
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+    r.set_list(xyg)
+    r.set_list(sinks, ref.SOURCE)
+    r.tree_build(); r.epsilon(False); r.convective()
+    P = port.Port(xyg=xyg)
+    P.tree_build(8, 0.0); P.epsilon(False); P.convective(1.0, 0.0, 0.05, sinks=sinks)
+    assert same(P.rec48(), r.get_list48())
+
+
 def test_readme_force_hydro_rows():
     """README.md:117-120 (float32-stored, 7 printed digits) — recorded in the cylinder fixture by the
     reference build that generated it"""

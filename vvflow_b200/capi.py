@@ -9,17 +9,18 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvvgpu.so")
+LIB_PATH = os.environ.get("VVGPU_LIB") or os.path.join(HERE, "lib", "libvvgpu.so")   # VVGPU_LIB: an experimental build
 
 # every symbol include/vvgpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vvgpu_create", "vvgpu_destroy", "vvgpu_strerror", "vvgpu_last_error",
-    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_append_particles", "vvgpu_particle_count", "vvgpu_get_particles",
+    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_append_particles", "vvgpu_particle_count", "vvgpu_get_particles", "vvgpu_get_particles_range",
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
-    "vvgpu_epsilon", "vvgpu_epsilon_probe", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
-    "vvgpu_set_shard", "vvgpu_shard_range", "vvgpu_shard_bounds", "vvgpu_particle_arrays_dev", "vvgpu_after_exchange", "vvgpu_stream",
+    "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
+    "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner",
+    "vvgpu_set_particles_slice", "vvgpu_particle_arrays_dev", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
 ]
 
@@ -59,6 +60,7 @@ def load():
         "vvgpu_append_particles": [vp, C.c_int, dp, sz],
         "vvgpu_particle_count": [vp, C.c_int, C.POINTER(sz)],
         "vvgpu_get_particles": [vp, C.c_int, dp, sz, C.POINTER(sz)],
+        "vvgpu_get_particles_range": [vp, C.c_int, dp, sz, sz],
         "vvgpu_get_permutation": [vp, C.c_int, ip, sz],
         "vvgpu_set_bodies": [vp, vp, sz, vp, sz],
         "vvgpu_tree_build": [vp, C.c_int, C.c_double, C.c_double, C.c_uint],
@@ -69,7 +71,7 @@ def load():
         "vvgpu_tree_leaf_segments": [vp, ip, ip, sz],
         "vvgpu_count_interactions": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "vvgpu_epsilon": [vp, C.c_int, C.POINTER(C.c_int)],
-        "vvgpu_epsilon_probe": [vp, C.POINTER(C.c_int)],
+        "vvgpu_merge_rounds": [vp, C.POINTER(C.c_int)],
         "vvgpu_convective": [vp, C.c_double, C.c_double, C.c_double, dp, sz],
         "vvgpu_velocity_at": [vp, dp, sz, C.c_double, C.c_double, C.c_double, dp, sz, dp],
         "vvgpu_eps2h_h2_at": [vp, dp, sz, dp],
@@ -77,11 +79,13 @@ def load():
         "vvgpu_vorticity_raster": [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double, C.c_double, dp],
         "vvgpu_diffusive": [vp, C.c_double, dp],
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
-        "vvgpu_set_shard": [vp, C.c_int, C.c_int],
-        "vvgpu_shard_range": [vp, C.POINTER(sz), C.POINTER(sz)],
-        "vvgpu_shard_bounds": [vp, C.POINTER(sz), sz],
+        "vvgpu_comm_unique_id": [vp, sz],
+        "vvgpu_comm_init": [vp, C.c_int, C.c_int, vp],
+        "vvgpu_group_create": [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)],
+        "vvgpu_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "vvgpu_shard_owner": [C.c_int, C.c_int],
+        "vvgpu_set_particles_slice": [vp, C.c_int, dp, sz, sz, sz],
         "vvgpu_particle_arrays_dev": [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)],
-        "vvgpu_after_exchange": [vp, C.c_int],
         "vvgpu_stream": [vp, C.POINTER(vp)],
         "vvgpu_synchronize": [vp],
         "vvgpu_phase_times": [vp, dp, C.POINTER(C.c_uint64)],
@@ -108,8 +112,11 @@ def _p(a):
 class Context:
     """One vvgpu context = one CUDA device."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.L = load()
+        if handle is not None:      # a context made by vvgpu_group_create
+            self.h = handle
+            return
         h = C.c_void_p()
         rc = self.L.vvgpu_create(device, C.byref(h))
         if rc:
@@ -154,6 +161,9 @@ class Context:
         n = C.c_size_t()
         self._ck(self.L.vvgpu_get_particles(self.h, 0, C.c_void_p(ptr), cap, C.byref(n)))
         return n.value
+
+    def get_particles_range_ptr(self, ptr, first, count):
+        self._ck(self.L.vvgpu_get_particles_range(self.h, 0, C.c_void_p(ptr), first, count))
 
     @property
     def n(self):
@@ -226,9 +236,9 @@ class Context:
         self._ck(self.L.vvgpu_epsilon(self.h, int(merge), C.byref(m)))
         return m.value
 
-    def epsilon_probe(self):
+    def merge_rounds(self):
         m = C.c_int()
-        self._ck(self.L.vvgpu_epsilon_probe(self.h, C.byref(m)))
+        self._ck(self.L.vvgpu_merge_rounds(self.h, C.byref(m)))
         return m.value
 
     def convective(self, inf_vx=0.0, inf_vy=0.0, dt=0.0, sinks=None):
@@ -275,20 +285,23 @@ class Context:
         self._ck(self.L.vvgpu_move_and_clean(self.h, dt, remove_eps, int(remove), _p(fdt), _p(gd), _p(gs), C.byref(cl)))
         return dict(fdt_dead=fdt[: 3 * nb].reshape(-1, 3), g_dead=gd[:nb], gsum=gs[:ns], cleaned=cl.value)
 
-    # ---- sharding / interop
-    def set_shard(self, rank, nranks):
-        self._ck(self.L.vvgpu_set_shard(self.h, rank, nranks))
+    # ---- multi-GPU / interop
+    def comm_init(self, rank, nranks, unique_id):
+        """one process per GPU: `unique_id` = the 128 bytes rank 0 got from comm_unique_id()"""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id)) if nranks > 1 else None
+        self._ck(self.L.vvgpu_comm_init(self.h, rank, nranks, buf))
 
-    def shard_bounds(self, nranks):
-        """all ranks' [first, last) particle ranges as a (nranks, 2) int64 array (computed locally)"""
-        buf = (C.c_size_t * (2 * nranks))()
-        self._ck(self.L.vvgpu_shard_bounds(self.h, buf, nranks))
-        return np.array(list(buf), dtype=np.int64).reshape(nranks, 2)
+    def comm_info(self):
+        r, n, k = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.L.vvgpu_comm_info(self.h, C.byref(r), C.byref(n), C.byref(k)))
+        return r.value, n.value, k.value
 
-    def shard_range(self):
-        a, b = C.c_size_t(), C.c_size_t()
-        self._ck(self.L.vvgpu_shard_range(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    def set_particles_slice_ptr(self, ptr, first, count, n_total):
+        self._ck(self.L.vvgpu_set_particles_slice(self.h, 0, C.c_void_p(ptr), first, count, n_total))
+
+    def set_particles_slice(self, rec48, first, n_total):
+        a = np.ascontiguousarray(rec48, dtype=np.float64).reshape(-1, 6)
+        self._ck(self.L.vvgpu_set_particles_slice(self.h, 0, _p(a), first, a.shape[0], n_total))
 
     def arrays_dev(self):
         arr = (C.c_void_p * 6)()
@@ -314,3 +327,29 @@ class Context:
         t = C.c_double()
         self._ck(self.L.vvgpu_fp64_peak(self.h, C.byref(t)))
         return t.value
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); carry the bytes to the other ranks with any host transport"""
+    L = load()
+    buf = (C.c_char * 128)()
+    rc = L.vvgpu_comm_unique_id(buf, 128)
+    if rc:
+        raise VVGpuError(rc, "vvgpu_comm_unique_id: libnccl.so.2 is not usable")
+    return bytes(buf)
+
+
+def shard_owner(group, nranks):
+    return load().vvgpu_shard_owner(group, nranks)
+
+
+def group_create(devices):
+    """one process, several ranks (devices may repeat): a list of Contexts, each to be driven from its own thread"""
+    L = load()
+    n = len(devices)
+    dev = (C.c_int * n)(*devices)
+    hs = (C.c_void_p * n)()
+    rc = L.vvgpu_group_create(dev, n, hs)
+    if rc:
+        raise VVGpuError(rc, f"vvgpu_group_create({list(devices)}): {L.vvgpu_strerror(rc).decode()}")
+    return [Context(handle=C.c_void_p(hs[k])) for k in range(n)]

@@ -7,6 +7,8 @@
 #include "vvgpu_point.cuh"
 #include "vvgpu_move.cuh"
 #include "vvgpu_tree_build.cuh"
+#include "vvgpu_shard.cuh"
+#include "vvgpu_comm.h"
 
 #include <algorithm>
 #include <cmath>
@@ -112,7 +114,6 @@ struct vvgpu_ctx {
     Buf g_leaf, g_mask, g_cursor, slot_base, slot_count, taylor, farcount, d_err;
     long long pool_cap = 0;
     std::vector<int> h_hist;   // nodes per tree depth
-    int lists_g0 = 0, lists_g1 = 0;
     Buf u_group, u_base, u_count, u_first, u_num, u_sbase, u_tmp, near_scratch, src4, src2, lbox, wall_d, wall_key, hv_list,
         hv_inode, hv_imask, hv_icount, hv_tpart, hv_off;
     int nunits = 0;
@@ -124,9 +125,16 @@ struct vvgpu_ctx {
     Buf d_sinks, d_pairs, pt_xy, pt_out, pt_v;
     PSet ps_backup;   // the resident list while a raster evaluator works on its own tree
 
-    // shard
-    int rank = 0, nranks = 1;
-    int shard_g0 = 0, shard_g1 = 0;
+    // multi-GPU: target sharding + the transport (vvgpu_shard.cuh, vvgpu_comm.h)
+    Comm comm;
+    int ngmine = 0;            // leaf groups this rank owns
+    int npieces = 0;           // pieces of kShardBlock groups
+    long long xL = 1;          // particles of the rank that owns most
+    bool v_dirty = false;      // v of the other ranks' targets not yet gathered
+    int merge_rounds = 0;      // rounds of the last merge fixed point
+    Buf sh_first, sh_cnt, sh_off, sh_rankcnt, xsend, xrecv;
+    Shard shard() const { return Shard{comm.rank, comm.nranks}; }
+    ShardTable shard_table() { return ShardTable{sh_first.as<int>(), sh_cnt.as<int>(), sh_off.as<int>()}; }
 
     TreeDev T() {
         TreeDev t;
@@ -282,15 +290,42 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     c->launches++;
     SubArgs SA{A.T, A.bp, A.px, A.py, A.pg, A.perm, A.sx, A.sy, A.segperm, scratch, A.sublist, bs, arena};
     k_tree_sub<<<c->sub_grid, kSubThreads, sizeof(SubSmem), st>>>(SA); CKLAUNCH();
+    // the rest of each TObj follows the permutation (g included: the build moved only x, y and the caller index)
+    PSet& Q = c->ps[c->cur ^ 1];
+    if (n) {
+        if (!Q.ensure(c->n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+        k_tree_gather_rest<<<cdiv(n, 256), 256, 0, st>>>(n, c->t_perm.as<int>(), P.g.as<double>(), P.vx.as<double>(), P.vy.as<double>(),
+                                                        P.ie.as<double>(), P.orig.as<int>(), Q.g.as<double>(), Q.vx.as<double>(),
+                                                        Q.vy.as<double>(), Q.ie.as<double>(), Q.orig.as<int>()); CKLAUNCH();
+    }
     const size_t nsubmax = ((size_t)n + nseg) / 2 + 2;
-    SweepArgs WA{A.T, A.px, A.py, A.pg, scratch, A.sublist, aux, aux + cap, aux + 2 * cap, subinfo, subinfo + nsubmax, subinfo + 2 * nsubmax, bs};
+    SweepArgs WA{A.T, A.px, A.py, n ? Q.g.as<double>() : nullptr, scratch, A.sublist, aux, aux + cap, aux + 2 * cap, subinfo,
+                 subinfo + nsubmax, subinfo + 2 * nsubmax, bs};
     k_tree_topsweep<<<1, 1024, 0, st>>>(WA); CKLAUNCH();
     k_tree_relocate<<<c->sub_grid * 8, 256, 0, st>>>(A.T, scratch, A.sublist, subinfo, subinfo + nsubmax, subinfo + 2 * nsubmax, bs); CKLAUNCH();
+    const int nranks = c->comm.nranks;
+    if (nranks > 1) {
+        const size_t pmax = ((size_t)n + nseg) / kGroupLeaves + 8;
+        c->sh_first.get<int>(pmax, &ok); c->sh_cnt.get<int>(pmax, &ok); c->sh_off.get<int>(pmax, &ok);
+        int* rc_dev = c->sh_rankcnt.get<int>(kMaxRanks, &ok);
+        NEED(ok);
+        k_shard_table<<<1, 1024, 0, st>>>(A.T, bs, nranks, c->shard_table(), rc_dev); CKLAUNCH();
+        CK(cudaMemcpyAsync(c->h_pinned + 128, rc_dev, nranks * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaMemcpyAsync(c->h_pinned + 32, bs, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int* hb = c->h_pinned + 32;
-    if (hb[3] == 2) return fail(c, VVGPU_ELIMIT, "tree build: a top level is wider than its tables");
-    if (hb[3]) return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
+    if (hb[3]) {
+        // the build moved (x, y) in place: put them back in the caller's order so that the resident list stays valid
+        if (n) {
+            k_tree_unpermute<<<cdiv(n, 256), 256, 0, st>>>(n, c->t_perm.as<int>(), P.x.as<double>(), P.y.as<double>(), Q.x.as<double>(),
+                                                          Q.y.as<double>()); CKLAUNCH();
+            std::swap(P.x, Q.x); std::swap(P.y, Q.y);
+            CK(cudaStreamSynchronize(st));
+        }
+        if (hb[3] == 2) return fail(c, VVGPU_ELIMIT, "tree build: a top level is wider than its tables");
+        return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
+    }
     c->nnodes = hb[0]; c->depth = hb[1];
     const u32 nl = (u32)hb[2];
     c->h_hist.resize(c->depth + 2);
@@ -298,16 +333,13 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     CK(cudaStreamSynchronize(st));
     c->nleaves = (int)nl;
     c->ngroups = cdiv(c->nleaves, kGroupLeaves);
+    c->npieces = cdiv(c->ngroups, kShardBlock);
+    c->ngmine = shard_count(c->ngroups, c->comm.rank, nranks);
+    c->xL = 1;
+    for (int r = 0; r < nranks && nranks > 1; r++) c->xL = std::max<long long>(c->xL, c->h_pinned[128 + r]);
+    c->v_dirty = false;
     TreeDev T = c->T();
-    // the rest of each TObj follows the permutation
-    if (n) {
-        PSet& Q = c->ps[c->cur ^ 1];
-        if (!Q.ensure(c->n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
-        k_tree_gather_rest<<<cdiv(n, 256), 256, 0, st>>>(n, c->t_perm.as<int>(), P.vx.as<double>(), P.vy.as<double>(), P.ie.as<double>(),
-                                                        P.orig.as<int>(), Q.vx.as<double>(), Q.vy.as<double>(),
-                                                        Q.ie.as<double>(), Q.orig.as<int>()); CKLAUNCH();
-        std::swap(P.vx, Q.vx); std::swap(P.vy, Q.vy); std::swap(P.ie, Q.ie); std::swap(P.orig, Q.orig);
-    }
+    if (n) { std::swap(P.g, Q.g); std::swap(P.vx, Q.vx); std::swap(P.vy, Q.vy); std::swap(P.ie, Q.ie); std::swap(P.orig, Q.orig); }
     // leaf records
     c->l_first.get<int>(nl, &ok); c->l_last.get<int>(nl, &ok); c->l_sfirst.get<int>(nl, &ok); c->l_slast.get<int>(nl, &ok);
     c->l_cx.get<double>(nl, &ok); c->l_cy.get<double>(nl, &ok); c->l_h.get<double>(nl, &ok); c->l_w.get<double>(nl, &ok);
@@ -321,17 +353,11 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
 
 size_t trav_smem() { return (size_t)kTravWarps * ((size_t)kTravStack * sizeof(int2) + (4 * 32 + 32 * 6) * sizeof(double)); }
 
-// Interaction lists + Taylor coefficients for the groups [g0, g1) in ONE tree walk per group, then the
-// work-unit table (vvgpu_lists.cuh). `all` = every group (single GPU, or the replicated merge replay);
-// otherwise only this rank's slice.
-int lists_impl(vvgpu_ctx* c, bool all) {
+// Interaction lists + Taylor coefficients for the groups this rank owns in ONE tree walk per group, then the
+// work-unit table (vvgpu_lists.cuh)
+int lists_impl(vvgpu_ctx* c) {
     const int ng = c->ngroups, nl = c->nleaves;
-    int g0 = 0, g1 = ng;
-    if (!all && c->nranks > 1) {   // contiguous slices of groups: uniform clouds balance by themselves
-        g0 = (int)((long long)ng * c->rank / c->nranks);
-        g1 = (int)((long long)ng * (c->rank + 1) / c->nranks);
-    }
-    if (c->lists_ready && c->lists_g0 == g0 && c->lists_g1 == g1) return 0;
+    if (c->lists_ready) return 0;
     cudaStream_t st = c->stream;
     bool ok = true;
     double* taylor = c->taylor.get<double>(4 * (size_t)nl, &ok);
@@ -365,9 +391,9 @@ int lists_impl(vvgpu_ctx* c, bool all) {
         const int unit = ng >= 2000 ? kUnitEntries : (ng >= 600 ? std::min(512, kUnitEntries) : 256);
         TravOut O{GroupLists{pleaf, pmask}, cursor, c->pool_cap, sbase, scount, derr, unit};
         TravItems I0{nullptr, nullptr, nullptr, item_cap, cut};
-        if (g1 > g0) {
-            k_traverse_cta<0><<<g1 - g0, kTcWarps * 32, 0, st>>>(T, L, nl, g0, g1, c->farc, O, taylor, farcount, hvlist, derr + 1,
-                                                                  nullptr, nullptr, 0, I0); CKLAUNCH();
+        if (c->ngmine > 0) {
+            k_traverse_cta<0><<<c->ngmine, kTcWarps * 32, 0, st>>>(T, L, nl, c->shard(), c->ngmine, c->farc, O, taylor, farcount, hvlist,
+                                                                   derr + 1, nullptr, nullptr, 0, I0); CKLAUNCH();
         }
         CK(cudaMemcpyAsync(c->h_pinned + 64, derr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -390,7 +416,7 @@ int lists_impl(vvgpu_ctx* c, bool all) {
             TravItems I{inode, imask, icount, item_cap, cut};
             k_traverse<1><<<cdiv(nheavy, kTravWarps), kTravWarps * 32, trav_smem(), st>>>(
                 T, L, nl, 0, 0, c->farc, OH, taylor, farcount, tpart, hvlist, nheavy, nullptr, nullptr, I); CKLAUNCH();
-            k_traverse_cta<2><<<nheavy * item_cap, kTcWarps * 32, 0, st>>>(T, L, nl, 0, 0, c->farc, OH, taylor, farcount, nullptr, nullptr,
+            k_traverse_cta<2><<<nheavy * item_cap, kTcWarps * 32, 0, st>>>(T, L, nl, c->shard(), 0, c->farc, OH, taylor, farcount, nullptr, nullptr,
                                                                           tpart, hvlist, nheavy, I); CKLAUNCH();
             k_heavy_taylor<<<nheavy, 256, 0, st>>>(hvlist, nheavy, nl, tpart, icount, item_cap, taylor, farcount); CKLAUNCH();
             {
@@ -439,8 +465,6 @@ int lists_impl(vvgpu_ctx* c, bool all) {
         break;
     }
     c->lists_ready = true;
-    c->lists_g0 = g0; c->lists_g1 = g1;
-    c->shard_g0 = g0; c->shard_g1 = g1;
     return 0;
 }
 
@@ -457,7 +481,7 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
     CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
     k_near<Op><<<c->nunits, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
-        k_near_finalize<Op><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
+        k_near_finalize<Op><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
     return 0;
 }
@@ -472,7 +496,7 @@ int launch_conv(vvgpu_ctx* c, ConvOp op) {
     CK(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvShared)));
     k_conv<<<c->nunits, kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
-        k_near_finalize<ConvOp><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
+        k_near_finalize<ConvOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
     return 0;
 }
@@ -490,8 +514,59 @@ int launch_diff(vvgpu_ctx* c, DiffOp op) {
     CK(cudaFuncSetAttribute(k_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)));
     k_diff<<<c->nunits, kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
-        k_near_finalize<DiffOp><<<c->lists_g1 - c->lists_g0, 256, 0, c->stream>>>(c->near_args(), op, c->lists_g0, c->lists_g1); CKLAUNCH();
+        k_near_finalize<DiffOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
+    return 0;
+}
+
+// ---- multi-GPU exchange (vvgpu_shard.cuh, vvgpu_comm.h) ------------------------------------------------------
+int comm_gather(vvgpu_ctx* c, const void* send, void* recv, size_t bytes) {
+    const std::string e = comm_allgather(c->comm, c->device, c->stream, send, recv, bytes);
+    if (!e.empty()) return fail(c, VVGPU_ECUDA, e);
+    return 0;
+}
+// Every array of X holds, for the particles this rank owns, the result of the phase that just ran; on return it
+// holds every rank's. ONE all-gather: owned pieces packed densely, blocks padded to the largest rank's count.
+// `scalar` (device int, optional) is summed over the ranks into scalar_out.
+int exchange_owned(vvgpu_ctx* c, const XArrays& X, const int* scalar, int* scalar_out) {
+    const int P = c->comm.nranks;
+    if (P <= 1) return 0;
+    const long long L = c->xL, stride = X.n * L + 1;
+    bool ok = true;
+    u64* send = c->xsend.get<u64>((size_t)stride, &ok);
+    u64* recv = c->xrecv.get<u64>((size_t)stride * P, &ok);
+    NEED(ok);
+    cudaStream_t st = c->stream;
+    const int mine = (c->npieces > c->comm.rank) ? (c->npieces - c->comm.rank + P - 1) / P : 0;
+    if (mine > 0) { k_shard_pack<<<mine, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, L, send); CKLAUNCH(); }
+    CK(cudaMemsetAsync(send + stride - 1, 0, sizeof(u64), st));
+    if (scalar) CK(cudaMemcpyAsync(send + stride - 1, scalar, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int rc = comm_gather(c, send, recv, (size_t)stride * sizeof(u64));
+    if (rc) return rc;
+    if (c->npieces > 0) { k_shard_unpack<<<c->npieces, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, L, stride, recv); CKLAUNCH(); }
+    if (scalar_out) { k_rank_sum_i32<<<1, 32, 0, st>>>((const int*)(recv + stride - 1), 2 * stride, P, 1, scalar_out); CKLAUNCH(); }
+    return 0;
+}
+// buf[0..n) summed over the ranks, in rank order (bit-identical on every rank)
+int rank_sum_f64(vvgpu_ctx* c, double* buf, int n) {
+    const int P = c->comm.nranks;
+    if (P <= 1 || n <= 0) return 0;
+    bool ok = true;
+    double* recv = (double*)c->xrecv.get<u64>((size_t)n * P, &ok);
+    NEED(ok);
+    int rc = comm_gather(c, buf, recv, (size_t)n * sizeof(double));
+    if (rc) return rc;
+    k_rank_sum_f64<<<cdiv(n, 128), 128, 0, c->stream>>>(recv, n, P, n, buf); CKLAUNCH();
+    return 0;
+}
+// v of the other ranks' targets (after the velocity phases of a sharded step)
+int sync_v(vvgpu_ctx* c) {
+    if (!c->v_dirty || c->comm.nranks <= 1) { c->v_dirty = false; return 0; }
+    XArrays X{};
+    X.n = 2; X.p[0] = c->ps[c->cur].vx.p; X.p[1] = c->ps[c->cur].vy.p; X.wide[0] = X.wide[1] = 1;
+    int rc = exchange_owned(c, X, nullptr, nullptr);
+    if (rc) return rc;
+    c->v_dirty = false;
     return 0;
 }
 
@@ -567,6 +642,14 @@ void vvgpu_destroy(vvgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->comm.kind == Comm::NCCL && c->comm.nccl) { if (NcclApi* api = NcclApi::get(nullptr)) api->CommDestroy(c->comm.nccl); }
+    if (c->comm.kind == Comm::LOCAL && c->comm.grp) {
+        LocalGroup* g = c->comm.grp;
+        cudaEventDestroy(g->slot[c->comm.rank].ready); cudaEventDestroy(g->slot[c->comm.rank].done);
+        bool last;
+        { std::lock_guard<std::mutex> lk(g->mu); last = (--g->refs == 0); }
+        if (last) delete g;
+    }
     Buf* all[] = {&c->stage, &c->s_rx, &c->s_ry, &c->s_cx, &c->s_cy, &c->s_dlx, &c->s_dly, &c->s_g, &c->s_ie, &c->s_slip,
                   &c->s_body, &c->b_first, &c->b_prop, &c->d_fric, &c->d_gsum, &c->d_fdt, &c->d_gdead, &c->d_cleaned,
                   &c->t_x, &c->t_y, &c->t_h, &c->t_w, &c->t_bb, &c->t_first, &c->t_last, &c->t_sfirst, &c->t_slast,
@@ -576,7 +659,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
-                  &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
+                  &c->sh_first, &c->sh_cnt, &c->sh_off, &c->sh_rankcnt, &c->xsend, &c->xrecv, &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
     c->ps[0].release(); c->ps[1].release(); c->ps_backup.release();
@@ -645,11 +728,27 @@ int vvgpu_get_particles(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t cap, size
     if (cap < c->n) return fail(c, VVGPU_EINVAL, "get_particles: buffer too small");
     if (!c->n) return 0;
     CK(cudaSetDevice(c->device));
+    if (c->built && c->v_dirty) { int rcv = sync_v(c); if (rcv) return rcv; }
     bool ok = true;
     double* st = c->stage.get<double>(c->n * 6, &ok);
     NEED(ok);
     k_pack48<<<cdiv(c->n, 256), 256, 0, c->stream>>>((int)c->n, c->ps[c->cur].view(), st); CKLAUNCH();
     CK(cudaMemcpyAsync(out, st, c->n * 48, cudaMemcpyDefault, c->stream));   // host or device destination
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vvgpu_get_particles_range(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t first, size_t count) {
+    if (!c || list != VVGPU_LIST_VORTEX || (!out && count) || first + count > c->n) return fail(c, VVGPU_EINVAL, "get_particles_range: bad argument");
+    if (!count) return 0;
+    CK(cudaSetDevice(c->device));
+    if (c->built && c->v_dirty) { int rcv = sync_v(c); if (rcv) return rcv; }
+    bool ok = true;
+    double* st = c->stage.get<double>(count * 6, &ok);
+    NEED(ok);
+    Particles p = c->ps[c->cur].view();
+    p.x += first; p.y += first; p.g += first; p.vx += first; p.vy += first; p.ie += first;
+    k_pack48<<<cdiv(count, 256), 256, 0, c->stream>>>((int)count, p, st); CKLAUNCH();
+    CK(cudaMemcpyAsync(out, st, count * 48, cudaMemcpyDefault, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -727,7 +826,7 @@ int vvgpu_tree_build(vvgpu_ctx* c, int far_criteria, double min_node, double max
     if (rc) return rc;
     {
         PhaseTimer t(c, VVGPU_T_LISTS);
-        rc = lists_impl(c, c->nranks == 1);
+        rc = lists_impl(c);
     }
     if (rc) { c->built = false; return rc; }
     return 0;
@@ -735,6 +834,11 @@ int vvgpu_tree_build(vvgpu_ctx* c, int far_criteria, double min_node, double max
 
 int vvgpu_tree_destroy(vvgpu_ctx* c) {
     if (!c) return VVGPU_EINVAL;
+    if (c->built && c->v_dirty) {   // the other ranks' share of v, while the shard table is still this tree's
+        CK(cudaSetDevice(c->device));
+        int rc = sync_v(c);
+        if (rc) return rc;
+    }
     c->built = false; c->lists_ready = false;
     c->nnodes = c->nleaves = c->ngroups = 0;
     return 0;
@@ -847,7 +951,23 @@ int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes
     CK(cudaStreamSynchronize(c->stream));
     double s = 0, t = 0;
     for (double v : h) s += v;
-    for (double v : f) t += v;
+    // far counts exist for the leaves of this rank's groups only
+    for (int m = 0; m < c->ngmine; m++) {
+        const int g = c->shard().group(m);
+        for (int l = g * kGroupLeaves; l < std::min(nl, (g + 1) * kGroupLeaves); l++) t += f[l];
+    }
+    if (c->comm.nranks > 1) {   // totals over the ranks
+        double* two = c->d_pairs.get<double>(2, &ok);
+        NEED(ok);
+        const double hv[2] = {s, t};
+        CK(cudaMemcpyAsync(two, hv, sizeof(hv), cudaMemcpyHostToDevice, c->stream));
+        int rc = rank_sum_f64(c, two, 2);
+        if (rc) return rc;
+        double out[2];
+        CK(cudaMemcpyAsync(out, two, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        s = out[0]; t = out[1];
+    }
     if (near_pairs) *near_pairs = s;
     if (far_nodes) *far_nodes = t;
     return 0;
@@ -855,7 +975,7 @@ int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes
 
 int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     if (!c) return VVGPU_EINVAL;
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (!c->built || !c->lists_ready) return fail(c, VVGPU_ESTATE, "tree is not built");
     CK(cudaSetDevice(c->device));
     PhaseTimer t(c, VVGPU_T_EPS);
     cudaStream_t st = c->stream;
@@ -865,6 +985,9 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     bool ok = true;
     PSet& P = c->ps[c->cur];
     const bool walls = c->tnseg > 0;
+    const bool multi = c->comm.nranks > 1;
+    // per-leaf wall parameters: every rank needs them for the leaves of its own targets only, which are exactly the
+    // leaves its work units cover
     double *lcrit = nullptr, *lrestr = nullptr;
     if (walls || c->nbody > 0 || merge) {
         lcrit = c->lcrit.get<double>(nl, &ok); lrestr = c->lrestr.get<double>(nl, &ok);
@@ -875,22 +998,22 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     }
     int* dchg = c->d_changed.get<int>(2, &ok);
     NEED(ok);
+    auto gather_ie = [&](double* ie) -> int {
+        XArrays X{};
+        X.n = 1; X.p[0] = ie; X.wide[0] = 1;
+        return exchange_owned(c, X, nullptr, nullptr);
+    };
     if (!merge) {
         int rcb = eps_boxes(c, MergeState{});
         if (rcb) return rcb;
         EpsOp<false> op{MergeState{}, MergeState{}, nullptr, lrestr, nullptr, P.ie.as<double>(), dchg};
-        return launch_near(c, op);
+        int rc = launch_near(c, op);
+        if (!rc && multi) rc = gather_ie(P.ie.as<double>());
+        return rc;
     }
-    // merge replay is order-dependent: every rank replays it over ALL groups (it is replicated, not sharded)
-    struct Reshard {
-        vvgpu_ctx* c;
-        ~Reshard() { if (c->nranks > 1 && c->built) lists_impl(c, false); }   // back to this rank's slice
-    } reshard{c};
-    {
-        int rcl = lists_impl(c, true);
-        if (rcl) return rcl;
-    }
-    // merging: iterate the tentative solution to its fixed point (see MergeState in vvgpu_near.cuh)
+    // merging is order-dependent: iterate the tentative solution to its fixed point (see MergeState in
+    // vvgpu_near.cuh). Every rank recomputes the decisions of ITS targets; the solution's columns are gathered after
+    // every round, so all ranks iterate on the same state and stop in the same round.
     double* ietmp = c->ie_tmp.get<double>(n, &ok);
     unsigned char* dyn = c->dyn.get<unsigned char>(n, &ok);
     for (int k = 0; k < 3; k++) { c->mA[k].get<int>(n, &ok); c->mB[k].get<int>(n, &ok); }
@@ -909,6 +1032,17 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         int rc = eps_boxes(c, A);
         if (!rc) rc = launch_near(c, op, haveA ? dyn : nullptr);
         if (rc) return rc;
+        if (multi) {
+            XArrays X{};
+            X.n = 6;
+            X.p[0] = B.init; X.p[1] = B.part; X.p[2] = B.nx; X.p[3] = B.ny; X.p[4] = B.ng; X.p[5] = ietmp;
+            X.wide[0] = X.wide[1] = 0; X.wide[2] = X.wide[3] = X.wide[4] = X.wide[5] = 1;
+            rc = exchange_owned(c, X, dchg, dchg);
+            if (rc) return rc;
+            // absorbed-by follows from the gathered (init, part) columns
+            k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(n, B.absby, kNoAbs); CKLAUNCH();
+            k_merge_absby<<<cdiv(n, 256), 256, 0, st>>>(n, B.init, B.part, B.absby); CKLAUNCH();
+        }
         u32 changed = 0;
         rc = read_u32(c, (u32*)dchg, &changed);
         if (rc) return rc;
@@ -917,6 +1051,7 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         haveA = true;
         k_merge_dyn<<<cdiv(n, 256), 256, 0, st>>>(n, mstate(c->mA), dyn); CKLAUNCH();
     }
+    c->merge_rounds = rounds + 1;
     if (!haveA) {  // no merge anywhere: every epsilon is final
         std::swap(c->ie_tmp, P.ie);
         return 0;
@@ -926,6 +1061,7 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     EpsOp<true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
     int rc = eps_boxes(c, A);
     if (!rc) rc = launch_near(c, opf, dyn);
+    if (!rc && multi) rc = gather_ie(ietmp);
     if (rc) return rc;
     std::swap(c->ie_tmp, P.ie);  // absorbed-before-turn particles kept their old value in ie_tmp (never written)
     CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
@@ -937,55 +1073,13 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     return 0;
 }
 
-// First round of the merge iteration only, on this rank's slice: writes _1_eps of the slice's
-// particles if NO particle of the slice wants to merge and reports the number that do. The
-// multi-GPU host layer sums that over ranks: zero everywhere means no merge can happen at all
-// (every particle saw the unmodified state), otherwise every rank runs the replicated replay.
-int vvgpu_epsilon_probe(vvgpu_ctx* c, int* ncandidates) {
-    if (!c || !ncandidates) return VVGPU_EINVAL;
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
-    CK(cudaSetDevice(c->device));
-    PhaseTimer t(c, VVGPU_T_EPS);
-    cudaStream_t st = c->stream;
-    *ncandidates = 0;
-    const int n = c->tn, nl = c->nleaves;
-    if (n == 0) return 0;
-    bool ok = true;
-    PSet& P = c->ps[c->cur];
-    double* lcrit = c->lcrit.get<double>(nl, &ok);
-    double* lrestr = c->lrestr.get<double>(nl, &ok);
-    int* latt = c->latt.get<int>(nl, &ok);
-    int* dchg = c->d_changed.get<int>(2, &ok);
-    double* ietmp = c->ie_tmp.get<double>(n, &ok);
-    for (int k = 0; k < 3; k++) c->mB[k].get<int>(n, &ok);
-    for (int k = 3; k < 6; k++) c->mB[k].get<double>(n, &ok);
-    NEED(ok);
-    {
-        int rcw = wall_params(c, 1, lcrit, lrestr, latt);
-        if (rcw) return rcw;
-    }
-    CK(cudaMemcpyAsync(ietmp, P.ie.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    MergeState Bm = mstate(c->mB);
-    k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, Bm); CKLAUNCH();
-    CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
-    EpsOp<false> op{MergeState{}, Bm, lcrit, lrestr, nullptr, ietmp, dchg};
-    int rc = eps_boxes(c, MergeState{});
-    if (!rc) rc = launch_near(c, op);
-    if (rc) return rc;
-    u32 changed = 0;
-    rc = read_u32(c, (u32*)dchg, &changed);
-    if (rc) return rc;
-    *ncandidates = (int)changed;
-    if (!changed) std::swap(c->ie_tmp, P.ie);
-    return 0;
-}
-
 int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, const double* sinks_xyg, size_t nsink) {
     if (!c || (nsink && !sinks_xyg)) return fail(c, VVGPU_EINVAL, "convective: bad argument");
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (!c->built || !c->lists_ready) return fail(c, VVGPU_ESTATE, "tree is not built");
     CK(cudaSetDevice(c->device));
     PhaseTimer t(c, VVGPU_T_CONV);
     if (c->tn == 0) return 0;
+    c->v_dirty = true;
     bool ok = true;
     double* ds = c->d_sinks.get<double>(3 * nsink, &ok);
     NEED(ok);
@@ -1144,7 +1238,7 @@ int vvgpu_vorticity_raster(vvgpu_ctx* c, float xmin, float ymin, float dxdy, int
 
 int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
     if (!c) return VVGPU_EINVAL;
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
+    if (!c->built || !c->lists_ready) return fail(c, VVGPU_ESTATE, "tree is not built");
     CK(cudaSetDevice(c->device));
     {
         PhaseTimer t(c, VVGPU_T_DIFF);
@@ -1157,7 +1251,10 @@ int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
             DiffOp op{re, c->d_fric.as<double>()};
             int rc = launch_diff(c, op);
             if (rc) return rc;
+            c->v_dirty = true;
         }
+        // TAtt::fric gets a term from every nearby vortex (MDiffusiveFast.cpp:121-122): sum the ranks' shares
+        if (c->nseg) { int rc = rank_sum_f64(c, c->d_fric.as<double>(), c->nseg); if (rc) return rc; }
     }
     if (fric_out && c->nseg) {
         CK(cudaMemcpyAsync(fric_out, c->d_fric.p, sizeof(double) * c->nseg, cudaMemcpyDeviceToHost, c->stream));
@@ -1212,54 +1309,108 @@ int vvgpu_move_and_clean(vvgpu_ctx* c, double dt_eff, double remove_eps, int rem
     return 0;
 }
 
-int vvgpu_set_shard(vvgpu_ctx* c, int rank, int nranks) {
-    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, VVGPU_EINVAL, "set_shard: bad argument");
-    if (c->built) return fail(c, VVGPU_ESTATE, "set_shard while the tree is built");
-    c->rank = rank; c->nranks = nranks;
+// ---- multi-GPU -----------------------------------------------------------------------------------------------
+int vvgpu_comm_unique_id(void* id128, size_t cap) {
+    if (!id128 || cap < sizeof(NcclApi::UniqueId)) return VVGPU_EINVAL;
+    std::string err;
+    NcclApi* api = NcclApi::get(&err);
+    if (!api) return VVGPU_ECUDA;
+    NcclApi::UniqueId id;
+    if (api->GetUniqueId(&id)) return VVGPU_ECUDA;
+    memcpy(id128, &id, sizeof(id));
     return 0;
 }
-int vvgpu_shard_range(vvgpu_ctx* c, size_t* first, size_t* last) {
-    if (!c || !first || !last) return VVGPU_EINVAL;
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
-    CK(cudaSetDevice(c->device));
-    int lf = c->shard_g0 * kGroupLeaves, ll = std::min(c->shard_g1 * kGroupLeaves, c->nleaves);
-    int a = 0, b = 0;
-    if (lf < ll) {
-        CK(cudaMemcpyAsync(c->h_pinned, c->l_first.as<int>() + lf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(c->h_pinned + 1, c->l_last.as<int>() + (ll - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        a = c->h_pinned[0]; b = c->h_pinned[1];
-    } else if (c->nleaves) {
-        // empty slice: place it at the boundary so that slices still tile [0,n)
-        int at = std::min(lf, c->nleaves - 1);
-        CK(cudaMemcpyAsync(c->h_pinned, (lf >= c->nleaves ? c->l_last.as<int>() : c->l_first.as<int>()) + at, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        a = b = c->h_pinned[0];
-    }
-    *first = a; *last = b;
+static int comm_ready(vvgpu_ctx* c, int rank, int nranks) {
+    if (!c || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail(c, VVGPU_EINVAL, "comm_init: bad rank / nranks");
+    if (c->built) return fail(c, VVGPU_ESTATE, "comm_init while the tree is built");
+    if (c->comm.kind != Comm::NONE) return fail(c, VVGPU_ESTATE, "comm_init: this context already has a communicator");
     return 0;
 }
-int vvgpu_shard_bounds(vvgpu_ctx* c, size_t* first_last, size_t nranks) {
-    if (!c || !first_last || (int)nranks != c->nranks) return fail(c, VVGPU_EINVAL, "shard_bounds: bad argument");
-    if (!c->built) return fail(c, VVGPU_ESTATE, "tree is not built");
-    if (nranks > 32) return fail(c, VVGPU_ELIMIT, "shard_bounds: more than 32 ranks");
+int vvgpu_comm_init(vvgpu_ctx* c, int rank, int nranks, const void* id128) {
+    int rc = comm_ready(c, rank, nranks);
+    if (rc) return rc;
+    if (nranks == 1) return 0;
+    if (!id128) return fail(c, VVGPU_EINVAL, "comm_init: no unique id");
     CK(cudaSetDevice(c->device));
-    // the tree is replicated and the groups are cut by the same formula on every rank (lists_impl), so each
-    // rank can name every rank's particle range: rank r starts at the first particle of its first leaf
-    const int ng = c->ngroups;
-    int nread = 0;
-    for (size_t r = 1; r < nranks; r++) {
-        const int lf = (int)((long long)ng * (long long)r / (long long)nranks) * kGroupLeaves;
-        if (lf < c->nleaves) {
-            CK(cudaMemcpyAsync(c->h_pinned + r, c->l_first.as<int>() + lf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            nread++;
-        } else c->h_pinned[r] = (int)c->tn;
+    std::string err;
+    NcclApi* api = NcclApi::get(&err);
+    if (!api) return fail(c, VVGPU_ECUDA, err);
+    NcclApi::UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    const int nrc = api->CommInitRank(&comm, nranks, id, rank);
+    if (nrc) return fail(c, VVGPU_ECUDA, std::string("ncclCommInitRank: ") + api->GetErrorString(nrc));
+    c->comm.kind = Comm::NCCL; c->comm.rank = rank; c->comm.nranks = nranks; c->comm.nccl = comm;
+    return 0;
+}
+int vvgpu_group_create(const int* devices, int n, vvgpu_ctx** out) {
+    if (!devices || !out || n < 1 || n > kMaxRanks) return VVGPU_EINVAL;
+    for (int r = 0; r < n; r++) out[r] = nullptr;
+    LocalGroup* g = new LocalGroup();
+    g->n = n; g->refs = n; g->slot.resize(n);
+    for (int r = 0; r < n; r++) {
+        int rc = vvgpu_create(devices[r], &out[r]);
+        if (rc) {
+            for (int q = 0; q < r; q++) { out[q]->comm = Comm{}; vvgpu_destroy(out[q]); out[q] = nullptr; }
+            delete g;
+            return rc;
+        }
+        vvgpu_ctx* c = out[r];
+        cudaEventCreateWithFlags(&g->slot[r].ready, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g->slot[r].done, cudaEventDisableTiming);
+        if (n > 1) { c->comm.kind = Comm::LOCAL; c->comm.rank = r; c->comm.nranks = n; c->comm.grp = g; }
     }
-    if (nread) CK(cudaStreamSynchronize(c->stream));
-    for (size_t r = 0; r < nranks; r++) {
-        first_last[2 * r] = r ? (size_t)c->h_pinned[r] : 0;
-        first_last[2 * r + 1] = (r + 1 < nranks) ? (size_t)c->h_pinned[r + 1] : (size_t)c->tn;
+    // direct NVLink copies between the group's devices where the hardware allows them
+    for (int r = 0; r < n; r++)
+        for (int q = 0; q < n; q++) {
+            if (devices[r] == devices[q]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[r], devices[q]) == cudaSuccess && can) {
+                cudaSetDevice(devices[r]);
+                if (cudaDeviceEnablePeerAccess(devices[q], 0) != cudaSuccess) cudaGetLastError();   // already enabled
+            }
+        }
+    if (n == 1) delete g;
+    return 0;
+}
+int vvgpu_merge_rounds(vvgpu_ctx* c, int* rounds) {
+    if (!c || !rounds) return VVGPU_EINVAL;
+    *rounds = c->merge_rounds;
+    return 0;
+}
+int vvgpu_comm_info(vvgpu_ctx* c, int* rank, int* nranks, int* kind) {
+    if (!c) return VVGPU_EINVAL;
+    if (rank) *rank = c->comm.rank;
+    if (nranks) *nranks = c->comm.nranks;
+    if (kind) *kind = (int)c->comm.kind;
+    return 0;
+}
+// groups [first, last) x kShardBlock... : which rank owns leaf group g of ngroups (pure arithmetic, no device needed)
+int vvgpu_shard_owner(int group, int nranks) { return (nranks > 0 && group >= 0) ? (group / kShardBlock) % nranks : -1; }
+
+// Upload of one SLICE per rank: rank r hands over records [first, first + count) of a list of n_total; the slices are
+// gathered over the transport, so the full list crosses PCIe once in total instead of once per rank.
+int vvgpu_set_particles_slice(vvgpu_ctx* c, int list, const vvgpu_obj* objs, size_t first, size_t count, size_t n_total) {
+    if (!c || list != VVGPU_LIST_VORTEX || (!objs && count) || first + count > n_total) return fail(c, VVGPU_EINVAL, "set_particles_slice: bad argument");
+    if (n_total > (size_t)std::numeric_limits<int>::max() / 4) return fail(c, VVGPU_EINVAL, "set_particles_slice: too many particles");
+    if (c->built) return fail(c, VVGPU_ESTATE, "set_particles while the tree is built (the tree holds positions into the list)");
+    const int P = c->comm.nranks;
+    const size_t lo = n_total * c->comm.rank / P, hi = n_total * (c->comm.rank + 1) / P;
+    if (first != lo || count != hi - lo) return fail(c, VVGPU_EINVAL, "set_particles_slice: rank r owns [n r / P, n (r + 1) / P)");
+    CK(cudaSetDevice(c->device));
+    const size_t per = (n_total + P - 1) / P;   // padded slice, in records
+    bool ok = true;
+    double* send = (double*)c->xsend.get<u64>(per * 6 + 8, &ok);
+    double* recv = (P > 1) ? (double*)c->xrecv.get<u64>(per * 6 * P + 8, &ok) : send;
+    if (!ok || !c->ps[c->cur].ensure(n_total)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    if (count) CK(cudaMemcpyAsync(send, objs, count * 48, cudaMemcpyDefault, c->stream));
+    if (P > 1) { int rc = comm_gather(c, send, recv, per * 48); if (rc) return rc; }
+    c->n = n_total; c->orig_next = n_total;
+    if (n_total) {
+        k_unpack48_slices<<<cdiv(n_total, 256), 256, 0, c->stream>>>((int)n_total, P, (int)per, recv, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
+        CKLAUNCH();
     }
+    CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `objs`
     return 0;
 }
 int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* n) {
@@ -1269,7 +1420,6 @@ int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* 
     if (n) *n = c->n;
     return 0;
 }
-int vvgpu_after_exchange(vvgpu_ctx* c, int) { return c ? 0 : VVGPU_EINVAL; }
 int vvgpu_stream(vvgpu_ctx* c, void** s) {
     if (!c || !s) return VVGPU_EINVAL;
     *s = (void*)c->stream;

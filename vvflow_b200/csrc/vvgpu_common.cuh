@@ -34,6 +34,9 @@ __device__ __forceinline__ double dec_ordered(u64 e) {
     return __longlong_as_double((long long)b);
 }
 __host__ __device__ __forceinline__ int sgn(double v) { return (v > 0) ? 1 : ((v < 0) ? -1 : 0); }  // TObj.hpp:8
+// the sink strength as MConvectiveFast.cpp:165 sees it: its bare `abs(src.g)` resolves to ::abs(int) in the reference
+// build, i.e. the circulation is truncated to an integer first (pinned against the compiled reference in the tests)
+__device__ __forceinline__ double sink_abs(double g) { const int t = (int)g; return (double)(t < 0 ? -t : t); }
 __device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
 __device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
 
@@ -75,6 +78,36 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* total, u32* sh /
     }
     __syncthreads();
     u32 res = sh[warp] + inc - v;
+    *total = sh[THREADS / 32];
+    __syncthreads();
+    return res;
+}
+
+// the same for any integer type (e.g. several 16-bit counters packed into a u64)
+template <class T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan_t(T v, T* total, T* sh /* THREADS/32 + 1 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = (lane < THREADS / 32) ? sh[lane] : 0;
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < THREADS / 32) sh[lane] = winc - w;
+        if (lane == THREADS / 32 - 1) sh[THREADS / 32] = winc;
+    }
+    __syncthreads();
+    T res = sh[warp] + inc - v;
     *total = sh[THREADS / 32];
     __syncthreads();
     return res;

@@ -38,6 +38,16 @@ constexpr int kTravStack = 1024;    // stack entries per warp (shared memory)
 constexpr int kGroupSlots = 16;     // chunks a regular group may fill before it is declared heavy
 constexpr int kItemSlots = 64;      // chunks one item of a heavy group may fill
 
+// Target sharding over ranks (vvgpu_shard.cuh): pieces of kShardBlock consecutive groups are dealt round-robin
+constexpr int kShardBlock = 4;
+struct Shard {
+    int rank, nranks;
+    // m-th group owned by this rank -> global group index (identity for one rank)
+    __host__ __device__ __forceinline__ int group(int m) const {
+        return ((m / kShardBlock) * nranks + rank) * kShardBlock + (m % kShardBlock);
+    }
+};
+
 struct GroupLists {   // the entry pool
     int* leaf;        // source leaf index
     u32* mask;        // target leaves (bit k = leaf group*32 + k) that have `leaf` in NearNodes
@@ -309,7 +319,7 @@ constexpr int kTcBudgetNodes = kTravBudget * 32;   // the same bound on visited 
 // made the items), blockIdx.x = heavy index * item_cap + item.
 template <int MODE>
 __global__ void __launch_bounds__(kTcWarps * 32)
-k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, TravOut O, double* taylor, double* farcount,
+k_traverse_cta(TreeDev T, LeafDev L, int nleaves, Shard sh, int ngmine, double farc, TravOut O, double* taylor, double* farcount,
                int* heavy_out, int* nheavy_out, double* tpart, const int* heavy_list, int nheavy, TravItems I) {
     __shared__ int2 stack[kTcStack];
     __shared__ double lcx[32], lcy[32], lh[32], lw[32];
@@ -323,8 +333,8 @@ k_traverse_cta(TreeDev T, LeafDev L, int nleaves, int g0, int g1, double farc, T
     u32 start_mask = 0;
     long long walk = 0;
     if (MODE == 0) {
-        g = g0 + blockIdx.x;
-        if (g >= g1) return;
+        if ((int)blockIdx.x >= ngmine) return;
+        g = sh.group(blockIdx.x);
         slot0 = g * kGroupSlots; nslots = kGroupSlots;
     } else {
         const int hidx = blockIdx.x / I.item_cap;

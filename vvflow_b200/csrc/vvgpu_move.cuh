@@ -102,6 +102,18 @@ __global__ void k_unpack48_at(int n, const double* __restrict__ rec, Particles P
     P.x[d] = r[0]; P.y[d] = r[1]; P.g[d] = r[2]; P.vx[d] = r[3]; P.vy[d] = r[4]; P.ie[d] = r[5];
     orig[d] = orig_base + i;
 }
+// records that arrived as one padded slice per rank (vvgpu_set_particles_slice): record i sits in the slice of the rank
+// r with n r / P <= i < n (r + 1) / P, at (i - n r / P) of that slice
+__global__ void k_unpack48_slices(int n, int P_, int per, const double* __restrict__ rec, Particles P, int* orig) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = (int)(((long long)i * P_) / n);
+    while ((long long)n * (r + 1) / P_ <= i) r++;
+    while ((long long)n * r / P_ > i) r--;
+    const double* q = rec + 6ll * ((long long)r * per + (i - (long long)n * r / P_));
+    P.x[i] = q[0]; P.y[i] = q[1]; P.g[i] = q[2]; P.vx[i] = q[3]; P.vy[i] = q[4]; P.ie[i] = q[5];
+    orig[i] = i;
+}
 __global__ void k_unpack24(int n, const double* __restrict__ rec, Particles P, int* orig) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
 
 // combine the parked partial states of a multi-unit group, in unit order, and finish
 template <class Op>
-__global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, int g0, int g1) {
-    const int g = g0 + blockIdx.x;
-    if (g >= g1) return;
+__global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, Shard sh, int ngmine) {
+    if ((int)blockIdx.x >= ngmine) return;
+    const int g = sh.group(blockIdx.x);
     const int nu = A.U.num[g];
     if (nu <= 1) return;
     const int l0 = g * kGroupLeaves;
@@ -330,7 +330,7 @@ struct ConvOp {
             double sx = 0, sy = 0;
             for (int k = 0; k < nsink; k++) {
                 double dx = t.x - sinks[3 * k], dy = t.y - sinks[3 * k + 1], sg = sinks[3 * k + 2];
-                double q = sg / (dx * dx + dy * dy + eps2_div_srcg * fabs(sg));
+                double q = sg / (dx * dx + dy * dy + eps2_div_srcg * sink_abs(sg));
                 sx += dx * q; sy += dy * q;
             }
             vx += sx * k1_2Pi; vy += sy * k1_2Pi;

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_velocity_at(PointArgs A) {
     double sx = 0, sy = 0;
     for (int k = lane; k < A.nsink; k += 32) {   // sink_list_influence, :153-170
         const double dx = px - A.sinks[3 * k], dy = py - A.sinks[3 * k + 1], sg = A.sinks[3 * k + 2];
-        const double w = sg / (dx * dx + dy * dy + A.eps2_div_srcg * fabs(sg));
+        const double w = sg / (dx * dx + dy * dy + A.eps2_div_srcg * sink_abs(sg));
         sx += dx * w; sy += dy * w;
     }
     double bx = 0, by = 0;

@@ -90,14 +90,23 @@ __device__ __forceinline__ void child_cmass(const double* A, const double* B, do
     } else { cm[0] = nx; cm[1] = ny; cm[2] = 0; }
 }
 
-// carry the rest of the 48-byte TObj (v, _1_eps) and the caller's index through the permutation
-__global__ void k_tree_gather_rest(int n, const int* __restrict__ perm, const double* __restrict__ vx,
+// carry the rest of the 48-byte TObj (g, v, _1_eps) and the caller's index through the permutation
+__global__ void k_tree_gather_rest(int n, const int* __restrict__ perm, const double* __restrict__ g, const double* __restrict__ vx,
                                    const double* __restrict__ vy, const double* __restrict__ ie,
-                                   const int* __restrict__ orig, double* vx2, double* vy2, double* ie2, int* orig2) {
+                                   const int* __restrict__ orig, double* g2, double* vx2, double* vy2, double* ie2, int* orig2) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int s = perm[i];
-    vx2[i] = vx[s]; vy2[i] = vy[s]; ie2[i] = ie[s]; orig2[i] = orig[s];
+    g2[i] = g[s]; vx2[i] = vx[s]; vy2[i] = vy[s]; ie2[i] = ie[s]; orig2[i] = orig[s];
+}
+
+// a failed build puts (x, y) back into the caller's order
+__global__ void k_tree_unpermute(int n, const int* __restrict__ perm, const double* __restrict__ x, const double* __restrict__ y,
+                                 double* x2, double* y2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = perm[i];
+    x2[s] = x[i]; y2[s] = y[i];
 }
 
 // compact per-leaf records used by every later phase

@@ -32,6 +32,10 @@ constexpr int kSubSegCap = 1024;        // body segments of a CTA-built subtree
 constexpr int kSubLvl = 1024;           // level width kept in shared memory (wider levels use the CTA's global arena)
 constexpr int kSubThreads = 1024;
 constexpr int kTopThreads = 1024;       // = tile of the top phase: one element per thread
+#ifndef VV_TOP_BATCH
+#define VV_TOP_BATCH 4
+#endif
+constexpr int kTopBatch = VV_TOP_BATCH; // tiles a CTA keeps in flight
 constexpr int kMaxDepth = 4096;
 constexpr int kLvlCache = 64;
 constexpr unsigned short kNone16 = 0xffffu;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
     __shared__ u32 sh[kTopThreads / 32 + 1];
     __shared__ u64 red[8][32];
     __shared__ int s_chunkex[kTopThreads];
+    __shared__ u64 sh64[kTopThreads / 32 + 1];
     double* a_mid = (double*)top_smem;
     int* a_first = (int*)(a_mid + A.maxact);
     int* a_cnt = a_first + A.maxact;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
         if (nsplit == 0) break;
         if (d + 1 >= kMaxDepth || (long long)a1 + 2ll * nsplit > A.cap) { failed = 1; break; }
         if (nsplit > A.maxact) { failed = 2; break; }
+        __syncthreads();   // the a_* tables are complete
         // tiles of the splitting nodes' particle ranges
         int NT = 0;
         for (int base = 0; base < nsplit; base += kTopThreads) {
@@ -251,18 +257,34 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a_tile0[mid] <= t) lo = mid; else hi = mid - 1; }
             return lo;
         };
+        // The three particle passes below walk this CTA's tiles kTopBatch at a time: every pass is a chain of dependent
+        // L2 accesses per element (coordinate | scan | partner -> payload), and with one tile in flight per CTA that
+        // latency was the whole cost of a level (0.75 ms at N = 1M for ~70 MB of traffic per level).
         // ---- P2: less-counts of my tiles
         {
             int running = 0;
             int j = (t_lo < t_hi) ? find_node(t_lo) : 0;
-            for (int t = t_lo; t < t_hi; t++) {
-                while (j + 1 < nsplit && a_tile0[j + 1] <= t) j++;
-                const int p = a_first[j] + (t - a_tile0[j]) * kTopThreads + tid;
-                bool flag = false;
-                if (p < a_first[j] + a_cnt[j]) flag = (a_axis[j] ? __ldcg(A.px + p) : __ldcg(A.py + p)) < a_mid[j];
-                const int cnt = __syncthreads_count(flag);
-                if (tid == 0) A.tilepre[t] = running;
-                running += cnt;
+            for (int t = t_lo; t < t_hi; t += kTopBatch) {
+                int jq[kTopBatch];
+                double cv[kTopBatch];
+                bool ok[kTopBatch];
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    jq[q] = -1; ok[q] = false; cv[q] = 0;
+                    if (t + q < t_hi) {
+                        while (j + 1 < nsplit && a_tile0[j + 1] <= t + q) j++;
+                        jq[q] = j;
+                        const int p = a_first[j] + (t + q - a_tile0[j]) * kTopThreads + tid;
+                        if (p < a_first[j] + a_cnt[j]) { ok[q] = true; cv[q] = a_axis[j] ? __ldcg(A.px + p) : __ldcg(A.py + p); }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    if (jq[q] < 0) continue;
+                    const int cnt = __syncthreads_count(ok[q] && cv[q] < a_mid[jq[q]]);
+                    if (tid == 0) A.tilepre[t + q] = running;
+                    running += cnt;
+                }
             }
             if (tid == 0) A.chunktot[blockIdx.x] = running;
         }
@@ -282,62 +304,120 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                 return s_chunkex[b] + __ldcg(A.tilepre + t);
             };
             int j = (t_lo < t_hi) ? find_node(t_lo) : 0;
-            for (int t = t_lo; t < t_hi; t++) {
-                while (j + 1 < nsplit && a_tile0[j + 1] <= t) j++;
-                const int f = a_first[j], cnt = a_cnt[j], tj0 = a_tile0[j];
-                const int Gf = gprefix(tj0);
-                const int m = gprefix(tj0 + (cnt + kTopThreads - 1) / kTopThreads) - Gf;
-                const int gpre = gprefix(t) - Gf;
-                const int p = f + (t - tj0) * kTopThreads + tid;
-                const bool valid = p < f + cnt;
-                bool flag = false;
-                if (valid) flag = (a_axis[j] ? __ldcg(A.px + p) : __ldcg(A.py + p)) < a_mid[j];
-                u32 tot;
-                const u32 ex = block_exclusive_scan<kTopThreads>(flag ? 1u : 0u, &tot, sh);
-                if (valid) {
-                    const int le = gpre + (int)ex, rel = p - f;
-                    A.enc[p] = (u32)le * 2u + (flag ? 1u : 0u);
-                    if (rel >= m && flag) A.tmpR[f + (m - le - 1)] = p;
+            for (int t = t_lo; t < t_hi; t += kTopBatch) {
+                int jq[kTopBatch], mq[kTopBatch], gpre[kTopBatch], pq[kTopBatch];
+                bool fl[kTopBatch], ok[kTopBatch];
+                u64 pk = 0;
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    jq[q] = -1; ok[q] = false; fl[q] = false; mq[q] = 0; gpre[q] = 0; pq[q] = 0;
+                    if (t + q < t_hi) {
+                        while (j + 1 < nsplit && a_tile0[j + 1] <= t + q) j++;
+                        jq[q] = j;
+                        const int f = a_first[j], cnt = a_cnt[j], tj0 = a_tile0[j];
+                        const int Gf = gprefix(tj0);
+                        mq[q] = gprefix(tj0 + (cnt + kTopThreads - 1) / kTopThreads) - Gf;
+                        gpre[q] = gprefix(t + q) - Gf;
+                        pq[q] = f + (t + q - tj0) * kTopThreads + tid;
+                        if (pq[q] < f + cnt) {
+                            ok[q] = true;
+                            fl[q] = (a_axis[j] ? __ldcg(A.px + pq[q]) : __ldcg(A.py + pq[q])) < a_mid[j];
+                        }
+                    }
                 }
-                if (t == tj0 && tid == 0) {
-                    A.act_m[j] = m;
-                    const int c = a1 + 2 * j;
-                    T.first[c] = f; T.last[c] = f + m;
-                    T.first[c + 1] = f + m; T.last[c + 1] = f + cnt;
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) pk |= (u64)(fl[q] ? 1u : 0u) << (16 * q);   // a tile holds <= 1024 < 2^16
+                u64 tot;
+                const u64 ex = block_exclusive_scan_t<u64, kTopThreads>(pk, &tot, sh64);
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    if (jq[q] < 0) continue;
+                    const int jj = jq[q], f = a_first[jj], m = mq[q];
+                    if (ok[q]) {
+                        const int le = gpre[q] + (int)((ex >> (16 * q)) & 0xffffu), rel = pq[q] - f;
+                        A.enc[pq[q]] = (u32)le * 2u + (fl[q] ? 1u : 0u);
+                        if (rel >= m && fl[q]) A.tmpR[f + (m - le - 1)] = pq[q];
+                    }
+                    if (t + q == a_tile0[jj] && tid == 0) {
+                        A.act_m[jj] = m;
+                        const int c = a1 + 2 * jj;
+                        T.first[c] = f; T.last[c] = f + m;
+                        T.first[c + 1] = f + m; T.last[c + 1] = f + a_cnt[jj];
+                    }
                 }
             }
         }
         grid.sync();
-        // ---- P5: in-place swaps (each pair is touched by exactly one thread) + Stretch of the two children
+        // ---- P5: in-place swaps of (x, y, caller index) — each pair is touched by exactly one thread; g follows the
+        // caller index once, at the end of the build — + Stretch of the two children, folded over the tiles of a node
         {
             int j = (t_lo < t_hi) ? find_node(t_lo) : 0;
-            for (int t = t_lo; t < t_hi; t++) {
-                while (j + 1 < nsplit && a_tile0[j + 1] <= t) j++;
-                const int f = a_first[j], cnt = a_cnt[j];
-                const int m = __ldcg(A.act_m + j);
-                const int c = a1 + 2 * j;
-                const int p = f + (t - a_tile0[j]) * kTopThreads + tid;
-                u64 v[8] = {kU64Max, kU64Max, 0, 0, kU64Max, kU64Max, 0, 0};
-                if (p < f + cnt) {
-                    const u32 e = __ldcg(A.enc + p);
-                    const bool flag = e & 1u;
-                    const int le = (int)(e >> 1), rel = p - f;
-                    if (rel < m && !flag) {
-                        const int q = __ldcg(A.tmpR + f + (rel - le));
-                        const double ax = __ldcg(A.px + p), ay = __ldcg(A.py + p), ag = __ldcg(A.pg + p);
-                        const int ai = __ldcg(A.perm + p);
-                        const double bx = __ldcg(A.px + q), by = __ldcg(A.py + q), bg = __ldcg(A.pg + q);
-                        const int bi = __ldcg(A.perm + q);
-                        A.px[p] = bx; A.py[p] = by; A.pg[p] = bg; A.perm[p] = bi;
-                        A.px[q] = ax; A.py[q] = ay; A.pg[q] = ag; A.perm[q] = ai;
-                        v[0] = v[2] = enc_ordered(bx); v[1] = v[3] = enc_ordered(by);
-                        v[4] = v[6] = enc_ordered(ax); v[5] = v[7] = enc_ordered(ay);
-                    } else if (rel < m) {
-                        v[0] = v[2] = enc_ordered(__ldcg(A.px + p)); v[1] = v[3] = enc_ordered(__ldcg(A.py + p));
-                    } else if (!flag) {
-                        v[4] = v[6] = enc_ordered(__ldcg(A.px + p)); v[5] = v[7] = enc_ordered(__ldcg(A.py + p));
-                    }   // a less element of the right part is moved (and counted) by its partner
+            int accj = -1;
+            u64 v[8] = {kU64Max, kU64Max, 0, 0, kU64Max, kU64Max, 0, 0};
+            for (int t = t_lo; t < t_hi; t += kTopBatch) {
+                int jq[kTopBatch], pq[kTopBatch], qq[kTopBatch], role[kTopBatch];   // role 0 none, 1 swaps, 2 stays left, 3 stays right
+                double ax[kTopBatch], ay[kTopBatch], bx[kTopBatch], by[kTopBatch];
+                int ai[kTopBatch], bi[kTopBatch];
+                u32 e[kTopBatch];
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    jq[q] = -1; role[q] = 0; pq[q] = 0; e[q] = 0;
+                    if (t + q < t_hi) {
+                        while (j + 1 < nsplit && a_tile0[j + 1] <= t + q) j++;
+                        jq[q] = j;
+                        pq[q] = a_first[j] + (t + q - a_tile0[j]) * kTopThreads + tid;
+                        if (pq[q] < a_first[j] + a_cnt[j]) { role[q] = 4; e[q] = __ldcg(A.enc + pq[q]); }
+                    }
                 }
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    qq[q] = 0;
+                    if (role[q] != 4) continue;
+                    const int jj = jq[q], f = a_first[jj], m = __ldcg(A.act_m + jj);
+                    const bool flag = e[q] & 1u;
+                    const int le = (int)(e[q] >> 1), rel = pq[q] - f;
+                    if (rel < m && !flag) { role[q] = 1; qq[q] = __ldcg(A.tmpR + f + (rel - le)); }
+                    else if (rel < m) role[q] = 2;
+                    else if (!flag) role[q] = 3;
+                    else role[q] = 0;   // a less element of the right part is moved (and counted) by its partner
+                }
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    ax[q] = ay[q] = bx[q] = by[q] = 0; ai[q] = bi[q] = 0;
+                    if (role[q] == 0) continue;
+                    ax[q] = __ldcg(A.px + pq[q]); ay[q] = __ldcg(A.py + pq[q]);
+                    if (role[q] == 1) {
+                        ai[q] = __ldcg(A.perm + pq[q]);
+                        bx[q] = __ldcg(A.px + qq[q]); by[q] = __ldcg(A.py + qq[q]); bi[q] = __ldcg(A.perm + qq[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kTopBatch; q++) {
+                    if (jq[q] < 0) continue;
+                    if (jq[q] != accj) {   // uniform across the CTA
+                        if (accj >= 0) {
+                            const int c = a1 + 2 * accj;
+                            top_commit_boxes(v, red, T.bb + 4ll * c, T.bb + 4ll * (c + 1), lane, warp);
+                            v[0] = v[1] = v[4] = v[5] = kU64Max; v[2] = v[3] = v[6] = v[7] = 0;
+                        }
+                        accj = jq[q];
+                    }
+                    if (role[q] == 0) continue;
+                    u64 lx = 0, ly = 0, rx = 0, ry = 0;
+                    bool hasl = false, hasr = false;
+                    if (role[q] == 1) {
+                        A.px[pq[q]] = bx[q]; A.py[pq[q]] = by[q]; A.perm[pq[q]] = bi[q];
+                        A.px[qq[q]] = ax[q]; A.py[qq[q]] = ay[q]; A.perm[qq[q]] = ai[q];
+                        lx = enc_ordered(bx[q]); ly = enc_ordered(by[q]); rx = enc_ordered(ax[q]); ry = enc_ordered(ay[q]);
+                        hasl = hasr = true;
+                    } else if (role[q] == 2) { lx = enc_ordered(ax[q]); ly = enc_ordered(ay[q]); hasl = true; }
+                    else { rx = enc_ordered(ax[q]); ry = enc_ordered(ay[q]); hasr = true; }
+                    if (hasl) { v[0] = lx < v[0] ? lx : v[0]; v[1] = ly < v[1] ? ly : v[1]; v[2] = lx > v[2] ? lx : v[2]; v[3] = ly > v[3] ? ly : v[3]; }
+                    if (hasr) { v[4] = rx < v[4] ? rx : v[4]; v[5] = ry < v[5] ? ry : v[5]; v[6] = rx > v[6] ? rx : v[6]; v[7] = ry > v[7] ? ry : v[7]; }
+                }
+            }
+            if (accj >= 0) {
+                const int c = a1 + 2 * accj;
                 top_commit_boxes(v, red, T.bb + 4ll * c, T.bb + 4ll * (c + 1), lane, warp);
             }
             // stable split of the segment lists (DistributeContent(LList&), TSortedTree.cpp:139-148): one CTA per node
@@ -402,7 +482,8 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
 struct SubArgs {
     TreeDev T;
     BuildParams bp;
-    double *px, *py, *pg;
+    double *px, *py;
+    const double* pg;             // in the CALLER's order (the build moves x, y and the caller index only)
     int* perm;
     const double *sx, *sy;
     int* segperm;
@@ -680,7 +761,8 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
             continue;
         }
         const int depth_l = d;   // levels 0 .. depth_l
-        // ---- write the particles back: (x, y) from shared memory, (g, caller index) gathered once
+        // ---- write the particles back: (x, y) from shared memory, the caller index gathered once (g follows it in
+        // k_tree_gather_rest; here it is only needed for the centres of mass)
         {
             double gv[kRounds];
             int pv[kRounds];
@@ -688,7 +770,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
             for (int i = 0; i < kRounds; i++) {
                 const int p = (warp * kRounds + i) * 32 + lane;
                 gv[i] = 0; pv[i] = 0;
-                if (p < np) { const int o = f0 + S.sidx[p]; gv[i] = A.pg[o]; pv[i] = A.perm[o]; }
+                if (p < np) { pv[i] = A.perm[f0 + S.sidx[p]]; gv[i] = A.pg[pv[i]]; }   // g never moved: read it by caller index
             }
             int sv = 0;
             if (tid < ns) sv = S.sgi[S.sord[sb][tid]];
@@ -698,7 +780,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
             for (int i = 0; i < kRounds; i++) {
                 const int p = (warp * kRounds + i) * 32 + lane;
                 if (p < np) {
-                    A.px[f0 + p] = S.sx[p]; A.py[f0 + p] = S.sy[p]; A.pg[f0 + p] = gv[i]; A.perm[f0 + p] = pv[i];
+                    A.px[f0 + p] = S.sx[p]; A.py[f0 + p] = S.sy[p]; A.perm[f0 + p] = pv[i];
                     sg[p] = gv[i];
                 }
             }

@@ -108,7 +108,7 @@ struct vvgpu_ctx {
     const int segcur = 0;   // the final segment order is always in t_segperm[0] (t_segperm[1] is the build's scratch)
     Buf scan_part, scan_out, flags, build_state;
     // tree build (vvgpu_tree_build.cuh)
-    Buf b_enc, b_tilepre, b_chunktot, b_actm, b_sublist, b_scratch, b_arena, b_aux, b_subinfo;
+    Buf b_enc, b_tilepre, b_chunktot, b_sublist, b_scratch, b_arena, b_aux, b_subinfo;
     int coop_grid = 0, sub_grid = 0;
     Buf l_first, l_last, l_sfirst, l_slast, l_cx, l_cy, l_h, l_w, l_node;
     Buf g_leaf, g_mask, g_cursor, slot_base, slot_count, taylor, farcount, d_err;
@@ -261,10 +261,11 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     }
     // splitting top-phase nodes of one level are disjoint and hold > kSubCap particles or > kSubSegCap segments
     const int maxact = n / kSubCap + nseg / kSubSegCap + 2;
-    const size_t top_smem = top_smem_bytes(maxact);
+    const size_t ntile_max = (size_t)n / kTopThreads + maxact + 2;
+    const int tcmax = (int)((ntile_max + c->coop_grid - 1) / c->coop_grid) + 1;
+    const size_t top_smem = top_smem_bytes(maxact, tcmax);
     if (top_smem > 160 * 1024) return fail(c, VVGPU_ELIMIT, "tree build: too many particles for the top-phase tables");
     if (top_smem > 40 * 1024) CK(cudaFuncSetAttribute(k_tree_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)top_smem));
-    const size_t ntile_max = (size_t)n / kTopThreads + maxact + 2;
     TopArgs A;
     A.T = c->T();
     A.bp = BuildParams{min_node, max_node};
@@ -277,9 +278,8 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     A.tmpR = c->t_tmpR.as<int>();
     A.tilepre = c->b_tilepre.get<int>(ntile_max, &ok);
     A.chunktot = c->b_chunktot.get<int>(c->coop_grid, &ok);
-    A.act_m = c->b_actm.get<int>(maxact, &ok);
     A.sublist = c->b_sublist.get<int>(((size_t)n + nseg) / 2 + 2, &ok);
-    A.st = bs; A.cap = (long long)cap; A.maxact = maxact;
+    A.st = bs; A.cap = (long long)cap; A.maxact = maxact; A.tcmax = tcmax;
     SubNode* scratch = c->b_scratch.get<SubNode>(cap, &ok);
     unsigned char* arena = c->b_arena.get<unsigned char>((size_t)c->sub_grid * sub_arena_bytes(), &ok);
     int* aux = c->b_aux.get<int>(3 * cap, &ok);
@@ -655,7 +655,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_x, &c->t_y, &c->t_h, &c->t_w, &c->t_bb, &c->t_first, &c->t_last, &c->t_sfirst, &c->t_slast,
                   &c->t_ch1, &c->t_depth, &c->t_status, &c->t_axis, &c->t_nl, &c->t_nn, &c->t_lstart,
                   &c->t_pre, &c->t_cmp, &c->t_cmm, &c->t_leafnode,
-                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_actm, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
+                  &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
                   &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,

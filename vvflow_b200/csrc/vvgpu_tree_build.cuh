@@ -20,6 +20,7 @@
 #include "vvgpu_tree.cuh"
 
 #include <cooperative_groups.h>
+#include <cstdio>
 
 namespace vv {
 namespace cg = cooperative_groups;
@@ -29,6 +30,7 @@ namespace cg = cooperative_groups;
 #endif
 constexpr int kSubCap = VV_SUB_CAP;     // particles of a CTA-built subtree
 constexpr int kSubSegCap = 1024;        // body segments of a CTA-built subtree
+constexpr int kSubSmallNode = 64;       // a child of at most this many particles is boxed by one thread
 constexpr int kSubLvl = 1024;           // level width kept in shared memory (wider levels use the CTA's global arena)
 constexpr int kSubThreads = 1024;
 constexpr int kTopThreads = 1024;       // = tile of the top phase: one element per thread
@@ -110,14 +112,16 @@ struct TopArgs {
     int* tmpR;       // partner table of the Hoare partition
     int* tilepre;    // per tile: less elements in the owning CTA's earlier tiles
     int* chunktot;   // per CTA: less elements in its tiles
-    int* act_m;      // per splitting node: less elements
     int* sublist;    // ST_SUB nodes in creation order
     BuildState* st;
     long long cap;   // node capacity
     int maxact;      // splitting nodes per level the shared tables hold
+    int tcmax;       // tiles one CTA may own
 };
 
-__host__ __device__ inline size_t top_smem_bytes(int maxact) { return (size_t)maxact * (sizeof(double) + 7 * sizeof(int)); }
+__host__ __device__ inline size_t top_smem_bytes(int maxact, int tcmax) {
+    return (size_t)maxact * (sizeof(double) + 7 * sizeof(int)) + ((size_t)maxact + 1 + tcmax) * sizeof(int);
+}
 
 // block-wide min/max of two boxes (left / right child): red[8][32]
 __device__ __forceinline__ void top_commit_boxes(u64 (&v)[8], u64 (*red)[32], u64* bbL, u64* bbR, int lane, int warp) {
@@ -144,6 +148,11 @@ __device__ __forceinline__ void top_commit_boxes(u64 (&v)[8], u64 (*red)[32], u6
     __syncthreads();
 }
 
+#ifdef VV_TREE_TIMING
+#define VV_TT(k) do { if (gtid == 0) { long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); tt_[k] += now_ - tlast_; tlast_ = now_; } } while (0)
+#else
+#define VV_TT(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
     static_assert(kTopThreads == 1024, "32 warps assumed by the box reduction");
     cg::grid_group grid = cg::this_grid();
@@ -160,12 +169,18 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
     int* a_sfirst = a_tile0 + A.maxact;
     int* a_scnt = a_sfirst + A.maxact;
     int* a_axis = a_scnt + A.maxact;
+    int* a_gf = a_axis + A.maxact;          // maxact + 1: less elements in all tiles before the node's first
+    int* s_mytp = a_gf + A.maxact + 1;      // tcmax: less elements in this CTA's tiles before tile k of its chunk
     TreeDev T = A.T;
     const int n = A.n, nseg = A.nseg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + tid;
     const long long gsize = (long long)G * blockDim.x;
+#ifdef VV_TREE_TIMING
+    long long tt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast_));
+#endif
 
     // ---- root: ranges, identity permutations, Stretch over everything
     if (gtid == 0) {
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
 
     int a0 = 0, a1 = 1, d = 0, nsub = 0;
     int failed = 0;
+    VV_TT(0);
     for (;; d++) {
         const int na = a1 - a0;
         // ---- P1 (every CTA for itself; CTA 0 writes the node records): DivideNode's tests, child allocation
@@ -239,6 +255,7 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
         if (d + 1 >= kMaxDepth || (long long)a1 + 2ll * nsplit > A.cap) { failed = 1; break; }
         if (nsplit > A.maxact) { failed = 2; break; }
         __syncthreads();   // the a_* tables are complete
+        VV_TT(1);
         // tiles of the splitting nodes' particle ranges
         int NT = 0;
         for (int base = 0; base < nsplit; base += kTopThreads) {
@@ -250,7 +267,9 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
             NT += (int)tot;
         }
         __syncthreads();
-        const int t_lo = (int)((long long)NT * blockIdx.x / G), t_hi = (int)((long long)NT * (blockIdx.x + 1) / G);
+        // every CTA owns TC consecutive tiles (the last ones may own fewer or none): owner(t) = t / TC is one division
+        const int TC = (NT + G - 1) / G;
+        const int t_lo = min(NT, (int)blockIdx.x * TC), t_hi = min(NT, ((int)blockIdx.x + 1) * TC);
         // node of a tile: the LAST j with a_tile0[j] <= t (nodes without particles own no tile)
         auto find_node = [&](int t) {
             int lo = 0, hi = nsplit - 1;
@@ -282,13 +301,15 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                 for (int q = 0; q < kTopBatch; q++) {
                     if (jq[q] < 0) continue;
                     const int cnt = __syncthreads_count(ok[q] && cv[q] < a_mid[jq[q]]);
-                    if (tid == 0) A.tilepre[t + q] = running;
+                    if (tid == 0) { A.tilepre[t + q] = running; s_mytp[t + q - t_lo] = running; }
                     running += cnt;
                 }
             }
             if (tid == 0) A.chunktot[blockIdx.x] = running;
         }
+        VV_TT(2);
         grid.sync();
+        VV_TT(3);
         // ---- P3: prefix over the CTAs' totals; P4: partner table, child ranges
         {
             const u32 ctv = (tid < G) ? (u32)__ldcg(A.chunktot + tid) : 0u;
@@ -296,13 +317,13 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
             const u32 cex = block_exclusive_scan<kTopThreads>(ctv, &total, sh);
             s_chunkex[tid] = (int)cex;
             __syncthreads();
-            auto gprefix = [&](int t) -> int {   // less elements in all tiles before t
-                if (t >= NT) return (int)total;
-                int b = (int)(((long long)t * G) / NT);
-                while ((int)((long long)NT * (b + 1) / G) <= t) b++;
-                while ((int)((long long)NT * b / G) > t) b--;
-                return s_chunkex[b] + __ldcg(A.tilepre + t);
-            };
+            // less elements before every splitting node (its first tile may belong to another CTA): one load per node, here
+            for (int jn = tid; jn <= nsplit; jn += kTopThreads) {
+                const int t = (jn < nsplit) ? a_tile0[jn] : NT;
+                a_gf[jn] = (t >= NT) ? (int)total : s_chunkex[(unsigned)t / (unsigned)TC] + __ldcg(A.tilepre + t);
+            }
+            __syncthreads();
+            const int mybase = s_chunkex[blockIdx.x];
             int j = (t_lo < t_hi) ? find_node(t_lo) : 0;
             for (int t = t_lo; t < t_hi; t += kTopBatch) {
                 int jq[kTopBatch], mq[kTopBatch], gpre[kTopBatch], pq[kTopBatch];
@@ -315,9 +336,9 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                         while (j + 1 < nsplit && a_tile0[j + 1] <= t + q) j++;
                         jq[q] = j;
                         const int f = a_first[j], cnt = a_cnt[j], tj0 = a_tile0[j];
-                        const int Gf = gprefix(tj0);
-                        mq[q] = gprefix(tj0 + (cnt + kTopThreads - 1) / kTopThreads) - Gf;
-                        gpre[q] = gprefix(t + q) - Gf;
+                        const int Gf = a_gf[j];
+                        mq[q] = a_gf[j + 1] - Gf;
+                        gpre[q] = mybase + s_mytp[t + q - t_lo] - Gf;
                         pq[q] = f + (t + q - tj0) * kTopThreads + tid;
                         if (pq[q] < f + cnt) {
                             ok[q] = true;
@@ -339,7 +360,6 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                         if (rel >= m && fl[q]) A.tmpR[f + (m - le - 1)] = pq[q];
                     }
                     if (t + q == a_tile0[jj] && tid == 0) {
-                        A.act_m[jj] = m;
                         const int c = a1 + 2 * jj;
                         T.first[c] = f; T.last[c] = f + m;
                         T.first[c + 1] = f + m; T.last[c + 1] = f + a_cnt[jj];
@@ -347,7 +367,9 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                 }
             }
         }
+        VV_TT(4);
         grid.sync();
+        VV_TT(3);
         // ---- P5: in-place swaps of (x, y, caller index) — each pair is touched by exactly one thread; g follows the
         // caller index once, at the end of the build — + Stretch of the two children, folded over the tiles of a node
         {
@@ -373,7 +395,7 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
                 for (int q = 0; q < kTopBatch; q++) {
                     qq[q] = 0;
                     if (role[q] != 4) continue;
-                    const int jj = jq[q], f = a_first[jj], m = __ldcg(A.act_m + jj);
+                    const int jj = jq[q], f = a_first[jj], m = a_gf[jj + 1] - a_gf[jj];
                     const bool flag = e[q] & 1u;
                     const int le = (int)(e[q] >> 1), rel = pq[q] - f;
                     if (rel < m && !flag) { role[q] = 1; qq[q] = __ldcg(A.tmpR + f + (rel - le)); }
@@ -470,12 +492,34 @@ __global__ void __launch_bounds__(kTopThreads, 1) k_tree_top(TopArgs A) {
         }
         a0 = a1; a1 += 2 * nsplit;
         if (gtid == 0) A.st->lvl[d + 2] = a1;
+        VV_TT(5);
         grid.sync();
+        VV_TT(3);
     }
+#ifdef VV_TREE_TIMING
+    if (gtid == 0) printf("top timing us: root %.0f P1 %.0f P2 %.0f gridsync(wait of CTA0) %.0f P4 %.0f P5 %.0f levels %d\n", tt_[0] * 1e-3, tt_[1] * 1e-3,
+                          tt_[2] * 1e-3, tt_[3] * 1e-3, tt_[4] * 1e-3, tt_[5] * 1e-3, d);
+#endif
     if (gtid == 0) {
         A.st->err = failed;
         A.st->ntop = a1; A.st->dtop = d; A.st->nsub = nsub;
     }
+}
+
+// exclusive prefix of one value per WARP over the 32 warps of a CTA, ONE barrier: every warp scans all 32 totals itself.
+// `sh` (32 words) must not be written again before another barrier has passed.
+__device__ __forceinline__ u32 warp_totals_scan(u32 wsum, u32* total, u32* sh, int lane, int warp) {
+    if (lane == 0) sh[warp] = wsum;
+    __syncthreads();
+    const u32 v = sh[lane];
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return __shfl_sync(0xffffffffu, inc - v, warp);
 }
 
 // ================================================================================= CTA-built subtrees
@@ -517,6 +561,8 @@ struct SubSmem {
     unsigned short sord[2][kSubSegCap], ssn[2][kSubSegCap], sGs[kSubSegCap + 8];
     int lvl[kLvlCache + 2];
     u32 sh[kSubThreads / 32 + 1];
+    u32 shA[32], shB[32], shC[32];   // one-barrier scans (B2 particles, B2 segments, B6)
+    int nbig;
     int cur_sub;
 };
 constexpr int kSweepSmemNodes = (int)(sizeof(LvlNode) * 2 * kSubLvl / sizeof(SweepNode));
@@ -604,8 +650,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
                     wsum += __popc(bal[i]);
                 }
                 u32 tot;
-                u32 ex = block_exclusive_scan<kSubThreads>(lane == 0 ? wsum : 0u, &tot, S.sh);
-                ex = __shfl_sync(0xffffffffu, ex, 0);
+                u32 ex = warp_totals_scan(wsum, &tot, S.shA, lane, warp);
 #pragma unroll
                 for (int i = 0; i < kRounds; i++) {
                     const int p = (warp * kRounds + i) * 32 + lane;
@@ -615,6 +660,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
                 if (np == kSubCap && tid == kSubThreads - 1) S.sG[np] = (unsigned short)tot;
             }
             bool sfl = false;
+            if (tid == 0) S.nbig = 0;
             if (ns) {
                 if (tid < ns) {
                     const unsigned short k = S.ssn[sb][tid];
@@ -624,7 +670,8 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
                     }
                 }
                 u32 tot;
-                const u32 ex = block_exclusive_scan<kSubThreads>(sfl ? 1u : 0u, &tot, S.sh);
+                const u32 sbal = __ballot_sync(0xffffffffu, sfl);
+                const u32 ex = warp_totals_scan(__popc(sbal), &tot, S.shB, lane, warp) + __popc(sbal & lanemask_lt());
                 if (tid <= ns) S.sGs[tid] = (unsigned short)ex;
                 if (ns == kSubThreads && tid == kSubThreads - 1) S.sGs[ns] = (unsigned short)tot;
             }
@@ -685,40 +732,47 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
             }
             sb ^= 1;
             __syncthreads();
-            // B5: Stretch of the children (segmented reduction over the positions, then atomics on the level table)
-#pragma unroll
-            for (int i = 0; i < kRounds; i++) {
-                const int p = (warp * kRounds + i) * 32 + lane;
-                int node = -1;
-                u64 mnx = kU64Max, mny = kU64Max, mxx = 0, mxy = 0;
-                if (p < np && S.spn[p] != kNone16) {
-                    node = S.spn[p];
-                    mnx = mxx = enc_ordered(S.sx[p]); mny = mxy = enc_ordered(S.sy[p]);
+            // B5: Stretch of the children. After the partition a child is a contiguous range: a small child is folded by
+            // ONE thread, a big one by one warp (a segmented warp reduction over all positions cost ~200 instructions
+            // per element-round and was most of this kernel); segments, few, are added with atomics afterwards.
+            {
+                unsigned short* big = S.tmpR;   // free again: the partner table was consumed in B4
+                for (int k = tid; k < nw; k += kSubThreads) {
+                    const int f = nxt[k].first, cnt = nxt[k].cnt;
+                    if (cnt > kSubSmallNode) { big[atomicAdd(&S.nbig, 1)] = (unsigned short)k; continue; }
+                    if (cnt == 0) continue;
+                    u64 mnx = kU64Max, mny = kU64Max, mxx = 0, mxy = 0;
+                    for (int i = 0; i < cnt; i++) {
+                        const u64 ex = enc_ordered(S.sx[f + i]), ey = enc_ordered(S.sy[f + i]);
+                        mnx = ex < mnx ? ex : mnx; mny = ey < mny ? ey : mny; mxx = ex > mxx ? ex : mxx; mxy = ey > mxy ? ey : mxy;
+                    }
+                    u64* bb = nxt[k].bb;
+                    bb[0] = mnx; bb[1] = mny; bb[2] = mxx; bb[3] = mxy;
                 }
-                if (__all_sync(0xffffffffu, node < 0)) continue;
-                const int n0 = __shfl_sync(0xffffffffu, node, 0);
-                if (__all_sync(0xffffffffu, node == n0)) {
+                __syncthreads();
+                const int nbig = S.nbig;
+                for (int b = warp; b < nbig; b += kSubThreads / 32) {
+                    const int k = big[b];
+                    const int f = nxt[k].first, cnt = nxt[k].cnt;
+                    u64 mnx = kU64Max, mny = kU64Max, mxx = 0, mxy = 0;
+                    for (int i = lane; i < cnt; i += 32) {
+                        const u64 ex = enc_ordered(S.sx[f + i]), ey = enc_ordered(S.sy[f + i]);
+                        mnx = ex < mnx ? ex : mnx; mny = ey < mny ? ey : mny; mxx = ex > mxx ? ex : mxx; mxy = ey > mxy ? ey : mxy;
+                    }
                     mnx = warp_min_u64(mnx); mny = warp_min_u64(mny); mxx = warp_max_u64(mxx); mxy = warp_max_u64(mxy);
-                    if (lane == 0) {
-                        u64* bb = nxt[n0].bb;
-                        atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
-                    }
-                } else {
-                    seg_minmax(node, mnx, mny, mxx, mxy, lane);
-                    const int nx_ = __shfl_down_sync(0xffffffffu, node, 1);
-                    if (node >= 0 && (lane == 31 || nx_ != node)) {
-                        u64* bb = nxt[node].bb;
-                        atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
-                    }
+                    if (lane == 0) { u64* bb = nxt[k].bb; bb[0] = mnx; bb[1] = mny; bb[2] = mxx; bb[3] = mxy; }
                 }
             }
-            if (ns && tid < ns) {
-                const unsigned short k = S.ssn[sb][tid];
-                if (k != kNone16) {
-                    const int o = S.sord[sb][tid];
-                    const u64 ex = enc_ordered(S.ssx[o]), ey = enc_ordered(S.ssy[o]);
-                    u64* bb = nxt[k].bb;
-                    atomicMin(bb + 0, ex); atomicMin(bb + 1, ey); atomicMax(bb + 2, ex); atomicMax(bb + 3, ey);
+            if (ns) {
+                __syncthreads();
+                if (tid < ns) {
+                    const unsigned short k = S.ssn[sb][tid];
+                    if (k != kNone16) {
+                        const int o = S.sord[sb][tid];
+                        const u64 ex = enc_ordered(S.ssx[o]), ey = enc_ordered(S.ssy[o]);
+                        u64* bb = nxt[k].bb;
+                        atomicMin(bb + 0, ex); atomicMin(bb + 1, ey); atomicMax(bb + 2, ex); atomicMax(bb + 3, ey);
+                    }
                 }
             }
             __syncthreads();
@@ -736,8 +790,10 @@ __global__ void __launch_bounds__(kSubThreads, 1) k_tree_sub(SubArgs A) {
                     g = node_decide(bb[0], bb[1], bb[2], bb[3], ln.cnt, ln.scnt, A.bp);
                     split = !g.leaf;
                 }
+                if (b0) __syncthreads();   // S.shC of the previous chunk has been read by every warp
                 u32 tot;
-                const u32 ex = block_exclusive_scan<kSubThreads>(split ? 1u : 0u, &tot, S.sh);
+                const u32 sb2 = __ballot_sync(0xffffffffu, split);
+                const u32 ex = warp_totals_scan(__popc(sb2), &tot, S.shC, lane, warp) + __popc(sb2 & lanemask_lt());
                 if (k < nw) {
                     const int r = split ? nsplit2 + (int)ex : -1;
                     nxt[k].d.mid = g.axis ? g.x : g.y; nxt[k].d.rank = r; nxt[k].d.axis = g.axis;

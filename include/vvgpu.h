@@ -178,6 +178,8 @@ enum { VVGPU_T_BUILD = 0, VVGPU_T_LISTS, VVGPU_T_EPS, VVGPU_T_CONV, VVGPU_T_DIFF
 /* CUDA-event milliseconds of the last call of each phase; launches = kernels launched since the
  * last vvgpu_phase_times call */
 int vvgpu_phase_times(vvgpu_ctx* ctx, double* ms, uint64_t* launches);
+/* host waits on the context's stream (read-backs) since the last call of this function */
+int vvgpu_host_syncs(vvgpu_ctx* ctx, uint64_t* n);
 /* FP64 DFMA micro-benchmark: achieved TFLOP/s of a register-resident FMA chain on this device */
 int vvgpu_fp64_peak(vvgpu_ctx* ctx, double* tflops);
 

@@ -27,7 +27,16 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["config"]["n_particles"] == 20000 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "every 4-th leaf" in cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "FULL un-sampled" in cb["sample"]
+    # the timed steps are full steps: the claimed work fits the run, and the sampled estimate is reported beside it
+    assert abs(d["ms_per_step"] - 1e3 * d["full_step_s"]) < 1e-9 and d["full_steps_timed"] == d["steps"]
+    assert d["sampled_estimate_s"] > 0 and 0.2 < d["sampled_over_full"] < 5
+    # both arms share the config dictionary
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    w = bench.make_workload("lamb", 20000)
+    assert d["config"] == bench.make_config(argparse.Namespace(), w)
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

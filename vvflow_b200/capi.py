@@ -21,7 +21,7 @@ SYMBOLS = [
     "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
     "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner",
     "vvgpu_set_particles_slice", "vvgpu_particle_arrays_dev", "vvgpu_stream",
-    "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_fp64_peak",
+    "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_host_syncs", "vvgpu_fp64_peak",
 ]
 
 SEG_DTYPE = np.dtype([("rx", "f8"), ("ry", "f8"), ("cx", "f8"), ("cy", "f8"), ("dlx", "f8"), ("dly", "f8"),
@@ -89,6 +89,7 @@ def load():
         "vvgpu_stream": [vp, C.POINTER(vp)],
         "vvgpu_synchronize": [vp],
         "vvgpu_phase_times": [vp, dp, C.POINTER(C.c_uint64)],
+        "vvgpu_host_syncs": [vp, C.POINTER(C.c_uint64)],
         "vvgpu_fp64_peak": [vp, C.POINTER(C.c_double)],
     }
     for name, args in sig.items():
@@ -322,6 +323,11 @@ class Context:
         la = C.c_uint64()
         self._ck(self.L.vvgpu_phase_times(self.h, _p(ms), C.byref(la)))
         return dict(zip(PHASES, ms.tolist())), la.value
+
+    def host_syncs(self):
+        n = C.c_uint64()
+        self._ck(self.L.vvgpu_host_syncs(self.h, C.byref(n)))
+        return n.value
 
     def fp64_peak(self):
         t = C.c_double()

@@ -80,7 +80,7 @@ struct vvgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    uint64_t launches = 0;
+    uint64_t launches = 0, host_syncs = 0;
     cudaEvent_t ev0[VVGPU_T_COUNT], ev1[VVGPU_T_COUNT];
     bool ev_valid[VVGPU_T_COUNT] = {};
     int* h_pinned = nullptr;  // small pinned scratch for read-backs
@@ -193,6 +193,8 @@ int fail(vvgpu_ctx* c, int code, const std::string& msg) {
     } while (0)
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+// every host wait on the context's stream is counted (vvgpu_host_syncs): a read-back costs a round trip
+inline cudaError_t stream_sync(vvgpu_ctx* c) { c->host_syncs++; return cudaStreamSynchronize(c->stream); }
 
 struct PhaseTimer {
     vvgpu_ctx* c; int ph;
@@ -216,7 +218,7 @@ int scan_flags(vvgpu_ctx* c, F f, long long n, u32* out) {
 
 int read_u32(vvgpu_ctx* c, const u32* d, u32* h) {
     CK(cudaMemcpyAsync(c->h_pinned, d, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     *h = *(u32*)c->h_pinned;
     return 0;
 }
@@ -313,7 +315,7 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
         CK(cudaMemcpyAsync(c->h_pinned + 128, rc_dev, nranks * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(c->h_pinned + 32, bs, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(c));
     const int* hb = c->h_pinned + 32;
     if (hb[3]) {
         // the build moved (x, y) in place: put them back in the caller's order so that the resident list stays valid
@@ -321,7 +323,7 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
             k_tree_unpermute<<<cdiv(n, 256), 256, 0, st>>>(n, c->t_perm.as<int>(), P.x.as<double>(), P.y.as<double>(), Q.x.as<double>(),
                                                           Q.y.as<double>()); CKLAUNCH();
             std::swap(P.x, Q.x); std::swap(P.y, Q.y);
-            CK(cudaStreamSynchronize(st));
+            CK(stream_sync(c));
         }
         if (hb[3] == 2) return fail(c, VVGPU_ELIMIT, "tree build: a top level is wider than its tables");
         return fail(c, VVGPU_ELIMIT, "tree deeper than 4096 levels or node capacity exceeded (degenerate input)");
@@ -330,7 +332,7 @@ int tree_build_impl(vvgpu_ctx* c, int far_criteria, double min_node, double max_
     const u32 nl = (u32)hb[2];
     c->h_hist.resize(c->depth + 2);
     CK(cudaMemcpyAsync(c->h_hist.data(), bs->hist, sizeof(int) * (c->depth + 1), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(c));
     c->nleaves = (int)nl;
     c->ngroups = cdiv(c->nleaves, kGroupLeaves);
     c->npieces = cdiv(c->ngroups, kShardBlock);
@@ -396,7 +398,7 @@ int lists_impl(vvgpu_ctx* c) {
                                                                    derr + 1, nullptr, nullptr, 0, I0); CKLAUNCH();
         }
         CK(cudaMemcpyAsync(c->h_pinned + 64, derr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(stream_sync(c));
         int errbits = c->h_pinned[64];
         const int nheavy = c->h_pinned[65];
         long long nheavy_slots = 0;
@@ -425,7 +427,7 @@ int lists_impl(vvgpu_ctx* c) {
                 k_heavy_pack<<<nheavy, 1024, 0, st>>>(nheavy, item_cap, OH, hoff); CKLAUNCH();
             }
             CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(stream_sync(c));
             errbits = c->h_pinned[64];
         }
         if (errbits & 1) { c->pool_cap *= 2; continue; }   // pool too small: grow and walk again
@@ -687,7 +689,7 @@ static int set_particles_common(vvgpu_ctx* c, int list, const void* src, size_t 
         if (rec_doubles == 6) k_unpack48<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
         else k_unpack24<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
         CKLAUNCH();
-        CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `src`
+        CK(stream_sync(c));  // the caller may reuse `src`
     }
     return 0;
 }
@@ -711,7 +713,7 @@ int vvgpu_append_particles(vvgpu_ctx* c, int list, const vvgpu_obj* objs, size_t
     CK(cudaMemcpyAsync(st, objs, n * 48, cudaMemcpyHostToDevice, c->stream));
     k_unpack48_at<<<cdiv(n, 256), 256, 0, c->stream>>>((int)n, st, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>(), (int)c->n,
                                                        (int)c->orig_next); CKLAUNCH();
-    CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `objs`
+    CK(stream_sync(c));  // the caller may reuse `objs`
     c->n += n;
     c->orig_next += n;
     return 0;
@@ -734,7 +736,7 @@ int vvgpu_get_particles(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t cap, size
     NEED(ok);
     k_pack48<<<cdiv(c->n, 256), 256, 0, c->stream>>>((int)c->n, c->ps[c->cur].view(), st); CKLAUNCH();
     CK(cudaMemcpyAsync(out, st, c->n * 48, cudaMemcpyDefault, c->stream));   // host or device destination
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     return 0;
 }
 int vvgpu_get_particles_range(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t first, size_t count) {
@@ -749,14 +751,14 @@ int vvgpu_get_particles_range(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t fir
     p.x += first; p.y += first; p.g += first; p.vx += first; p.vy += first; p.ie += first;
     k_pack48<<<cdiv(count, 256), 256, 0, c->stream>>>((int)count, p, st); CKLAUNCH();
     CK(cudaMemcpyAsync(out, st, count * 48, cudaMemcpyDefault, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     return 0;
 }
 int vvgpu_get_permutation(vvgpu_ctx* c, int list, int32_t* orig, size_t cap) {
     if (!c || list != VVGPU_LIST_VORTEX || !orig || cap < c->n) return fail(c, VVGPU_EINVAL, "get_permutation: bad argument");
     CK(cudaSetDevice(c->device));
     if (c->n) CK(cudaMemcpyAsync(orig, c->ps[c->cur].orig.p, c->n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     return 0;
 }
 
@@ -809,7 +811,7 @@ int vvgpu_set_bodies(vvgpu_ctx* c, const vvgpu_seg* segs, size_t nseg, const vvg
     }
     CK(cudaMemcpyAsync(d3, bfirst.data(), (nbody + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d4, bprop.data(), bprop.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     c->nseg = (int)nseg; c->nbody = (int)nbody;
     return 0;
 }
@@ -866,7 +868,7 @@ int vvgpu_tree_export(vvgpu_ctx* c, double* dbl, int64_t* idx, size_t cap_nodes)
     k_tree_export<<<cdiv(nn, 128), 128, 0, c->stream>>>(c->T(), (int)nn, st, si); CKLAUNCH();
     CK(cudaMemcpyAsync(dbl, st, nn * 10 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(idx, si, nn * 8 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     return 0;
 }
 
@@ -922,7 +924,7 @@ int vvgpu_tree_leaf_segments(vvgpu_ctx* c, int64_t* ptr, int64_t* idx, size_t ca
     CK(cudaMemcpyAsync(sf.data(), c->l_sfirst.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sl.data(), c->l_slast.p, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->stream));
     if (c->tnseg) CK(cudaMemcpyAsync(perm.data(), c->t_segperm[c->segcur].p, sizeof(int) * c->tnseg, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     int64_t p = 0;
     for (int l = 0; l < nl; l++) {
         ptr[l] = p;
@@ -948,7 +950,7 @@ int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes
     std::vector<double> h(nu), f(nl);
     if (nu) CK(cudaMemcpyAsync(h.data(), d, sizeof(double) * nu, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(f.data(), c->farcount.p, sizeof(double) * nl, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     double s = 0, t = 0;
     for (double v : h) s += v;
     // far counts exist for the leaves of this rank's groups only
@@ -965,7 +967,7 @@ int vvgpu_count_interactions(vvgpu_ctx* c, double* near_pairs, double* far_nodes
         if (rc) return rc;
         double out[2];
         CK(cudaMemcpyAsync(out, two, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(stream_sync(c));
         s = out[0]; t = out[1];
     }
     if (near_pairs) *near_pairs = s;
@@ -1093,7 +1095,7 @@ int vvgpu_convective(vvgpu_ctx* c, double inf_vx, double inf_vy, double dt, cons
                    c->s_slip.as<int>(), c->b_first.as<int>(), c->b_prop.as<double>()};
         k_body_influence<<<cdiv(c->tn, 128), 128, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), B); CKLAUNCH();
     }
-    if (nsink) CK(cudaStreamSynchronize(c->stream));
+    if (nsink) CK(stream_sync(c));
     return 0;
 }
 
@@ -1124,7 +1126,7 @@ int vvgpu_velocity_at(vvgpu_ctx* c, const double* xy, size_t npts, double inf_vx
     k_velocity_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
     CK(cudaMemcpyAsync(vxy_out, dout, 2 * npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "velocity_at: traversal stack overflow");
     return 0;
 }
@@ -1148,7 +1150,7 @@ int vvgpu_eps2h_h2_at(vvgpu_ctx* c, const double* xy, size_t npts, double* eps2h
     k_eps2h_h2_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
     CK(cudaMemcpyAsync(eps2h_h2_out, dout, 2 * npts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "eps2h_h2_at: traversal stack overflow");
     return 0;
 }
@@ -1168,7 +1170,7 @@ int vvgpu_node_influence(vvgpu_ctx* c, double* out_nseg) {
     k_node_influence<<<cdiv(c->nseg, kPtWarps), kPtWarps * 32, 0, c->stream>>>(A); CKLAUNCH();
     CK(cudaMemcpyAsync(out_nseg, dout, c->nseg * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     if (c->h_pinned[64] & 2) return fail(c, VVGPU_ELIMIT, "node_influence: traversal stack overflow");
     return 0;
 }
@@ -1258,7 +1260,7 @@ int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
     }
     if (fric_out && c->nseg) {
         CK(cudaMemcpyAsync(fric_out, c->d_fric.p, sizeof(double) * c->nseg, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(stream_sync(c));
     }
     return 0;
 }
@@ -1304,7 +1306,7 @@ int vvgpu_move_and_clean(vvgpu_ctx* c, double dt_eff, double remove_eps, int rem
     if (g_dead && c->nbody) CK(cudaMemcpyAsync(g_dead, c->d_gdead.p, sizeof(double) * c->nbody, cudaMemcpyDeviceToHost, st));
     if (gsum_delta && c->nseg) CK(cudaMemcpyAsync(gsum_delta, c->d_gsum.p, sizeof(double) * c->nseg, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(c->h_pinned + 16, dcl, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(stream_sync(c));
     if (cleaned) *cleaned = (size_t) * (unsigned long long*)(c->h_pinned + 16);
     return 0;
 }
@@ -1373,6 +1375,12 @@ int vvgpu_group_create(const int* devices, int n, vvgpu_ctx** out) {
     if (n == 1) delete g;
     return 0;
 }
+int vvgpu_host_syncs(vvgpu_ctx* c, uint64_t* n) {
+    if (!c || !n) return VVGPU_EINVAL;
+    *n = c->host_syncs;
+    c->host_syncs = 0;
+    return 0;
+}
 int vvgpu_merge_rounds(vvgpu_ctx* c, int* rounds) {
     if (!c || !rounds) return VVGPU_EINVAL;
     *rounds = c->merge_rounds;
@@ -1410,7 +1418,7 @@ int vvgpu_set_particles_slice(vvgpu_ctx* c, int list, const vvgpu_obj* objs, siz
         k_unpack48_slices<<<cdiv(n_total, 256), 256, 0, c->stream>>>((int)n_total, P, (int)per, recv, c->ps[c->cur].view(), c->ps[c->cur].orig.as<int>());
         CKLAUNCH();
     }
-    CK(cudaStreamSynchronize(c->stream));  // the caller may reuse `objs`
+    CK(stream_sync(c));  // the caller may reuse `objs`
     return 0;
 }
 int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* n) {
@@ -1428,14 +1436,14 @@ int vvgpu_stream(vvgpu_ctx* c, void** s) {
 int vvgpu_synchronize(vvgpu_ctx* c) {
     if (!c) return VVGPU_EINVAL;
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     return 0;
 }
 
 int vvgpu_phase_times(vvgpu_ctx* c, double* ms, uint64_t* launches) {
     if (!c) return VVGPU_EINVAL;
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(stream_sync(c));
     for (int k = 0; k < VVGPU_T_COUNT; k++) {
         float f = 0;
         if (c->ev_valid[k]) cudaEventElapsedTime(&f, c->ev0[k], c->ev1[k]);

@@ -137,6 +137,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.h, self.nv = index, [], False, None, None
+        self.period = 0.02 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 0.1
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -162,7 +163,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append((sm, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period)
 
     def summary(self):
         if not self.rows:
@@ -175,7 +176,7 @@ class ClockSampler(threading.Thread):
                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         reasons = [k for k, b in bits.items() if any(r[1] & b for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(self.rows),
-                "how": "NVML in-process, 20 ms period, during both timed regions"}
+                "how": "NVML in-process on rank 0, %d ms period, during both timed regions" % int(self.period * 1e3)}
 
 
 # ------------------------------------------------------------------------------------ reference arm
@@ -331,6 +332,10 @@ def ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -387,6 +392,8 @@ def ours(args):
     ctx.phase_times()
     ctx.host_syncs()
     sampler = ClockSampler(local)
+    if rank != 0 or os.environ.get("VV_BENCH_NOSAMPLER"):
+        sampler.h = None     # NVML queries from 8 processes stalled rank 0's launches (+4 ms per step): rank 0 samples alone
     sampler.start()
     barrier()
     phase_sum = {k: 0.0 for k in capi.PHASES}
@@ -423,8 +430,12 @@ def ours(args):
         tmin_ = t.clone(); dist.all_reduce(tmin_, op=dist.ReduceOp.MIN)
         phase_ms_max = dict(zip(capi.PHASES, tmax_.tolist()))
         phase_ms_min = dict(zip(capi.PHASES, tmin_.tolist()))
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        phase_by_rank = [[round(v, 3) for v in a.tolist()] for a in allr]
     else:
         phase_ms_max = phase_ms_min = phase_ms
+        phase_by_rank = None
 
     # interaction counts of one step's tree (work done per step)
     if reseed:
@@ -518,6 +529,7 @@ def ours(args):
                                          "region)" if reseed else "the state evolves from step to step"},
             "interactions_per_s": near_pairs / (phase_ms_max["conv"] * 1e-3) if phase_ms_max["conv"] > 0 else None,
             "phase_ms": phase_ms, "phase_ms_max_over_ranks": phase_ms_max, "phase_ms_min_over_ranks": phase_ms_min,
+            "phase_ms_by_rank": phase_by_rank,
             "wall_ms_per_step": wall_total_ms / args.steps,
             "e2e": {"value": 1e3 / e2e_ms_per_step, "unit": "steps/s", "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * int(nout),
@@ -546,7 +558,10 @@ def ours(args):
             "state_hash_of": "(x, y, g) bits after ONE step from the input records; the same for every number of GPUs",
             "checksum_sum_g": checksum,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -163,8 +163,10 @@ int vvgpu_comm_unique_id(void* id128, size_t cap);
 int vvgpu_comm_init(vvgpu_ctx* ctx, int rank, int nranks, const void* id128);
 int vvgpu_group_create(const int* devices, int n, vvgpu_ctx** ctxs_out);
 int vvgpu_comm_info(vvgpu_ctx* ctx, int* rank, int* nranks, int* kind /* 0 none, 1 NCCL, 2 in-process */);
-/* rank that owns leaf group `group` (groups of 32 consecutive leaves, in pieces of 4, round-robin); no device needed */
+/* rank that owns leaf group `group` (groups of 32 consecutive leaves, dealt round-robin in pieces of vvgpu_shard_block()
+ * consecutive groups); no device needed */
 int vvgpu_shard_owner(int group, int nranks);
+int vvgpu_shard_block(void);
 /* e2e upload with one slice per rank: rank r passes records [n r / P, n (r + 1) / P) of a list of n_total (host or
  * device address); the slices are gathered over the transport */
 int vvgpu_set_particles_slice(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t first, size_t count, size_t n_total);

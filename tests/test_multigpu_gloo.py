@@ -64,14 +64,15 @@ def test_unique_id_reaches_every_rank_and_calls_are_identical():
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_ownership_tiles_the_groups(world):
-    """every leaf group has exactly one owner, pieces of 4 consecutive groups go round the ranks"""
+    """every leaf group has exactly one owner, pieces of consecutive groups go round the ranks"""
     sys.path.insert(0, ROOT)
-    from vvflow_b200 import multigpu
+    from vvflow_b200 import capi, multigpu
+    blk = capi.shard_block()
     ng = 1003
     owned = [multigpu.owned_groups(ng, r, world) for r in range(world)]
     allg = sorted(g for o in owned for g in o)
     assert allg == list(range(ng))
     sizes = [len(o) for o in owned]
-    assert max(sizes) - min(sizes) <= 4
+    assert max(sizes) - min(sizes) <= blk
     for r, o in enumerate(owned):
-        assert all((g // 4) % world == r for g in o)
+        assert all((g // blk) % world == r for g in o)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
     "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
-    "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner",
+    "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner", "vvgpu_shard_block",
     "vvgpu_set_particles_slice", "vvgpu_particle_arrays_dev", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_host_syncs", "vvgpu_fp64_peak",
 ]
@@ -84,6 +84,7 @@ def load():
         "vvgpu_group_create": [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)],
         "vvgpu_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "vvgpu_shard_owner": [C.c_int, C.c_int],
+        "vvgpu_shard_block": [],
         "vvgpu_set_particles_slice": [vp, C.c_int, dp, sz, sz, sz],
         "vvgpu_particle_arrays_dev": [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)],
         "vvgpu_stream": [vp, C.POINTER(vp)],
@@ -347,6 +348,10 @@ def comm_unique_id():
 
 def shard_owner(group, nranks):
     return load().vvgpu_shard_owner(group, nranks)
+
+
+def shard_block():
+    return load().vvgpu_shard_block()
 
 
 def group_create(devices):

@@ -530,23 +530,24 @@ int comm_gather(vvgpu_ctx* c, const void* send, void* recv, size_t bytes) {
 // Every array of X holds, for the particles this rank owns, the result of the phase that just ran; on return it
 // holds every rank's. ONE all-gather: owned pieces packed densely, blocks padded to the largest rank's count.
 // `scalar` (device int, optional) is summed over the ranks into scalar_out.
-int exchange_owned(vvgpu_ctx* c, const XArrays& X, const int* scalar, int* scalar_out) {
+int exchange_owned(vvgpu_ctx* c, XArrays X, const int* scalar, int* scalar_out) {
     const int P = c->comm.nranks;
     if (P <= 1) return 0;
-    const long long L = c->xL, stride = X.n * L + 1;
+    const long long L = (c->xL + 1) & ~1ll;
+    const long long stride = xarrays_layout(X, L) + 8;     // bytes per rank; the last 8 carry the scalar
     bool ok = true;
-    u64* send = c->xsend.get<u64>((size_t)stride, &ok);
-    u64* recv = c->xrecv.get<u64>((size_t)stride * P, &ok);
+    unsigned char* send = (unsigned char*)c->xsend.get<u64>((size_t)stride / 8, &ok);
+    unsigned char* recv = (unsigned char*)c->xrecv.get<u64>((size_t)stride / 8 * P, &ok);
     NEED(ok);
     cudaStream_t st = c->stream;
     const int mine = (c->npieces > c->comm.rank) ? (c->npieces - c->comm.rank + P - 1) / P : 0;
-    if (mine > 0) { k_shard_pack<<<mine, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, L, send); CKLAUNCH(); }
-    CK(cudaMemsetAsync(send + stride - 1, 0, sizeof(u64), st));
-    if (scalar) CK(cudaMemcpyAsync(send + stride - 1, scalar, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    int rc = comm_gather(c, send, recv, (size_t)stride * sizeof(u64));
+    if (mine > 0) { k_shard_pack<<<mine, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, send); CKLAUNCH(); }
+    CK(cudaMemsetAsync(send + stride - 8, 0, 8, st));
+    if (scalar) CK(cudaMemcpyAsync(send + stride - 8, scalar, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int rc = comm_gather(c, send, recv, (size_t)stride);
     if (rc) return rc;
-    if (c->npieces > 0) { k_shard_unpack<<<c->npieces, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, L, stride, recv); CKLAUNCH(); }
-    if (scalar_out) { k_rank_sum_i32<<<1, 32, 0, st>>>((const int*)(recv + stride - 1), 2 * stride, P, 1, scalar_out); CKLAUNCH(); }
+    if (c->npieces > 0) { k_shard_unpack<<<c->npieces, 256, 0, st>>>(c->shard_table(), c->npieces, c->shard(), X, stride, recv); CKLAUNCH(); }
+    if (scalar_out) { k_rank_sum_i32<<<1, 32, 0, st>>>((const int*)(recv + stride - 8), stride / 4, P, 1, scalar_out); CKLAUNCH(); }
     return 0;
 }
 // buf[0..n) summed over the ranks, in rank order (bit-identical on every rank)
@@ -1035,15 +1036,16 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         if (!rc) rc = launch_near(c, op, haveA ? dyn : nullptr);
         if (rc) return rc;
         if (multi) {
+            // what travels: with whom every particle merges (-1: it does not) and its epsilon. The merged state of an
+            // initiator follows from those and the assumed solution A, which every rank holds: recomputed locally.
             XArrays X{};
-            X.n = 6;
-            X.p[0] = B.init; X.p[1] = B.part; X.p[2] = B.nx; X.p[3] = B.ny; X.p[4] = B.ng; X.p[5] = ietmp;
-            X.wide[0] = X.wide[1] = 0; X.wide[2] = X.wide[3] = X.wide[4] = X.wide[5] = 1;
+            X.n = 2;
+            X.p[0] = B.part; X.p[1] = ietmp;
+            X.wide[0] = 0; X.wide[1] = 1;
             rc = exchange_owned(c, X, dchg, dchg);
             if (rc) return rc;
-            // absorbed-by follows from the gathered (init, part) columns
             k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(n, B.absby, kNoAbs); CKLAUNCH();
-            k_merge_absby<<<cdiv(n, 256), 256, 0, st>>>(n, B.init, B.part, B.absby); CKLAUNCH();
+            k_merge_fill<<<cdiv(n, 256), 256, 0, st>>>(n, P.view(), A, B); CKLAUNCH();
         }
         u32 changed = 0;
         rc = read_u32(c, (u32*)dchg, &changed);
@@ -1394,6 +1396,7 @@ int vvgpu_comm_info(vvgpu_ctx* c, int* rank, int* nranks, int* kind) {
     return 0;
 }
 // groups [first, last) x kShardBlock... : which rank owns leaf group g of ngroups (pure arithmetic, no device needed)
+int vvgpu_shard_block(void) { return kShardBlock; }
 int vvgpu_shard_owner(int group, int nranks) { return (nranks > 0 && group >= 0) ? (group / kShardBlock) % nranks : -1; }
 
 // Upload of one SLICE per rank: rank r hands over records [first, first + count) of a list of n_total; the slices are

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
     extern __shared__ __align__(16) unsigned char near_smem[];
     DfShared& S = *reinterpret_cast<DfShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + blockIdx.x;
+    const int u = A.u0 + unit_order(blockIdx.x, gridDim.x);
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;

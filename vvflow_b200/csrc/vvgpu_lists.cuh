@@ -39,7 +39,10 @@ constexpr int kGroupSlots = 16;     // chunks a regular group may fill before it
 constexpr int kItemSlots = 64;      // chunks one item of a heavy group may fill
 
 // Target sharding over ranks (vvgpu_shard.cuh): pieces of kShardBlock consecutive groups are dealt round-robin
-constexpr int kShardBlock = 4;
+#ifndef VV_SHARD_BLOCK
+#define VV_SHARD_BLOCK 1
+#endif
+constexpr int kShardBlock = VV_SHARD_BLOCK;   // groups per piece
 struct Shard {
     int rank, nranks;
     // m-th group owned by this rank -> global group index (identity for one rank)

@@ -63,6 +63,12 @@ struct NearArgs {
     const double *srx, *sry, *sdlx, *sdly;
 };
 
+// CTAs start in blockIdx order; the units are in DFS order of their groups, and the expensive ones — the fringe groups,
+// whose sparse leaves see long lists and large epsilons — sit at BOTH ends of that order. Starting from both ends
+// alternately puts them first instead of into the kernel's tail (with the work of a step split over 8 GPUs one
+// late fringe unit was a third of the kernel's duration).
+__device__ __forceinline__ int unit_order(int b, int n) { return (b & 1) ? (n - 1 - (b >> 1)) : (b >> 1); }
+
 template <class Op>
 struct LwWarpT {
     static constexpr int kCap = kIdxCap / 2;
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     extern __shared__ __align__(16) unsigned char near_smem[];
     LwSharedT<Op>& S = *reinterpret_cast<LwSharedT<Op>*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + blockIdx.x;
+    const int u = A.u0 + unit_order(blockIdx.x, gridDim.x);
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;
@@ -419,6 +425,34 @@ struct MergeState {
 };
 constexpr int kNoAbs = 0x7fffffff;
 
+// MergeVortexes(lv, lv1), MEpsilonFast.cpp:111-126: the state of initiator i after it merged with i1, i1 taken as i sees
+// it under the assumed solution A (post-merge state if i1 merged before i's turn). ONE function for the decision
+// kernel and for the ranks that only receive (i, i1) from the owner of i: the bits must be the same everywhere.
+__device__ __forceinline__ void merged_state(const Particles& P, const MergeState& A, int i, int i1, double& nx, double& ny,
+                                             double& ng) {
+    double x1 = P.x[i1], y1 = P.y[i1], g1 = P.g[i1];
+    if (A.absby && !(A.absby[i1] < i) && A.init[i1] && i1 < i) { x1 = A.nx[i1]; y1 = A.ny[i1]; g1 = A.ng[i1]; }
+    const double tx = P.x[i], ty = P.y[i], gi = P.g[i];
+    nx = tx; ny = ty;
+    if (sgn(gi) == sgn(g1)) {
+        const double r = 1. / VV_ADD(gi, g1);
+        nx = VV_MUL(VV_ADD(VV_MUL(tx, gi), VV_MUL(x1, g1)), r);
+        ny = VV_MUL(VV_ADD(VV_MUL(ty, gi), VV_MUL(y1, g1)), r);
+    } else if (fabs(gi) < fabs(g1)) { nx = x1; ny = y1; }
+    ng = VV_ADD(gi, g1);
+}
+// a merge solution's remaining columns from its `part` column (the other ranks' decisions arrive as (i, part[i]) only)
+__global__ void k_merge_fill(int n, Particles P, MergeState A, MergeState B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int i1 = B.part[i];
+    if (i1 < 0) { B.init[i] = 0; return; }
+    double nx, ny, ng;
+    merged_state(P, A, i, i1, nx, ny, ng);
+    B.init[i] = 1; B.nx[i] = nx; B.ny[i] = ny; B.ng[i] = ng;
+    atomicMin(&B.absby[i1], i);
+}
+
 template <bool FINAL>
 struct EpsOp {
     static constexpr bool kSegments = false;
@@ -537,14 +571,8 @@ struct EpsOp {
                 if (A_.absby) { seen(t.i1, i, x1, y1, g1); seen(t.i2, i, x2, y2, g2); }
                 const double gi = A.P.g[i];
                 if ((t.r1 < crit) || ((sgn(g1) == sgn(g2)) && (sgn(g1) != sgn(gi)))) {  // :162-166
-                    // MergeVortexes(lv, lv1), :111-126
-                    double nx = t.x, ny = t.y;
-                    if (sgn(gi) == sgn(g1)) {
-                        double r = 1. / VV_ADD(gi, g1);
-                        nx = VV_MUL(VV_ADD(VV_MUL(t.x, gi), VV_MUL(x1, g1)), r);
-                        ny = VV_MUL(VV_ADD(VV_MUL(t.y, gi), VV_MUL(y1, g1)), r);
-                    } else if (fabs(gi) < fabs(g1)) { nx = x1; ny = y1; }
-                    double ng = VV_ADD(gi, g1);
+                    double nx, ny, ng;
+                    merged_state(A.P, A_, i, t.i1, nx, ny, ng);
                     bool diff = true;
                     if (A_.absby && A_.init[i] && A_.part[i] == t.i1 &&
                         __double_as_longlong(A_.nx[i]) == __double_as_longlong(nx) &&

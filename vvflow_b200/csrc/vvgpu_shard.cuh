@@ -57,37 +57,58 @@ __global__ void __launch_bounds__(1024) k_shard_table(TreeDev T, const BuildStat
     }
 }
 
-// the arrays of one exchange: 8-byte or 4-byte elements, every one of them travels as an 8-byte slot
+// the arrays of one exchange: 8-byte or 4-byte elements. A rank's block = the arrays one after the other, each L
+// elements long (L even, so that every array starts 8-byte aligned), then one 8-byte slot for a scalar.
 constexpr int kMaxXArr = 8;
 struct XArrays {
     void* p[kMaxXArr];
-    int wide[kMaxXArr];   // 1: 8-byte elements, 0: 4-byte
+    int wide[kMaxXArr];       // 1: 8-byte elements, 0: 4-byte
+    long long off[kMaxXArr];  // byte offset of the array inside a rank's block (filled by xarrays_layout)
     int n;
 };
+// byte size of a rank's block (without the scalar slot)
+inline long long xarrays_layout(XArrays& X, long long L) {
+    long long o = 0;
+    for (int a = 0; a < X.n; a++) { X.off[a] = o; o += L * (X.wide[a] ? 8 : 4); }
+    return o;
+}
 
-// send[a * L + off + i] = array a at particle (first + i), for the pieces this rank owns; one CTA per owned piece
-__global__ void __launch_bounds__(256) k_shard_pack(ShardTable S, int npieces, Shard sh, XArrays X, long long L, u64* send) {
+// send block <- the pieces this rank owns, packed densely in piece order; one CTA per owned piece
+__global__ void __launch_bounds__(256) k_shard_pack(ShardTable S, int npieces, Shard sh, XArrays X, unsigned char* send) {
     const long long k = sh.rank + (long long)blockIdx.x * sh.nranks;
     if (k >= npieces) return;
     const int f = S.first[k], c = S.cnt[k], o = S.off[k];
     for (int a = 0; a < X.n; a++) {
-        u64* dst = send + a * L + o;
-        if (X.wide[a]) { const u64* src = (const u64*)X.p[a] + f; for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i]; }
-        else { const u32* src = (const u32*)X.p[a] + f; for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i]; }
+        if (X.wide[a]) {
+            u64* dst = (u64*)(send + X.off[a]) + o;
+            const u64* src = (const u64*)X.p[a] + f;
+            for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+        } else {
+            u32* dst = (u32*)(send + X.off[a]) + o;
+            const u32* src = (const u32*)X.p[a] + f;
+            for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+        }
     }
 }
-// the other ranks' pieces back into the arrays; recv = [rank][stride] with stride >= X.n * L slots; one CTA per piece
-__global__ void __launch_bounds__(256) k_shard_unpack(ShardTable S, int npieces, Shard sh, XArrays X, long long L, long long stride,
-                                                      const u64* recv) {
+// the other ranks' pieces back into the arrays; recv = [rank][stride bytes]; one CTA per piece
+__global__ void __launch_bounds__(256) k_shard_unpack(ShardTable S, int npieces, Shard sh, XArrays X, long long stride,
+                                                      const unsigned char* recv) {
     const int k = blockIdx.x;
     if (k >= npieces) return;
     const int owner = k % sh.nranks;
     if (owner == sh.rank) return;
     const int f = S.first[k], c = S.cnt[k], o = S.off[k];
+    const unsigned char* blk = recv + owner * stride;
     for (int a = 0; a < X.n; a++) {
-        const u64* src = recv + owner * stride + a * L + o;
-        if (X.wide[a]) { u64* dst = (u64*)X.p[a] + f; for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i]; }
-        else { u32* dst = (u32*)X.p[a] + f; for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = (u32)src[i]; }
+        if (X.wide[a]) {
+            const u64* src = (const u64*)(blk + X.off[a]) + o;
+            u64* dst = (u64*)X.p[a] + f;
+            for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+        } else {
+            const u32* src = (const u32*)(blk + X.off[a]) + o;
+            u32* dst = (u32*)X.p[a] + f;
+            for (int i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+        }
     }
 }
 // out[i] = sum over ranks (in rank order) of recv[r * stride + i]

@@ -32,7 +32,10 @@ struct Buf {
         if (need > bytes) {
             if (p) cudaFree(p);
             p = nullptr;
-            size_t want = need + need / 4 + 256;
+            // headroom: a reallocation inside a step is a cudaFree + cudaMalloc (an implicit device synchronisation and
+            // milliseconds under multi-process load); bookkeeping buffers whose size drifts from step to step (unit
+            // tables, heavy-group scratch) get twice what they need, the big per-particle arrays a quarter more
+            size_t want = (need < (64u << 20)) ? 2 * need + 4096 : need + need / 4 + 256;
             if (cudaMalloc(&p, want) != cudaSuccess) { bytes = 0; *ok = false; return nullptr; }
             bytes = want;
         }

@@ -74,6 +74,9 @@ int vvgpu_set_particles_xyg(vvgpu_ctx* ctx, int list, const double* xyg, size_t 
  * index (vvgpu_get_permutation) of the appended particles continues after the last one handed over so far. */
 int vvgpu_append_particles(vvgpu_ctx* ctx, int list, const vvgpu_obj* objs, size_t n);
 int vvgpu_particle_count(vvgpu_ctx* ctx, int list, size_t* n);
+/* Space::gsum() (libvvhd/headers/TSpace.hpp): total circulation of the resident list — the right-hand side of the
+ * SLAE's circulation equation (MConvectiveFast.cpp:511) when the list lives on the device */
+int vvgpu_particle_gsum(vvgpu_ctx* ctx, int list, double* sum);
 /* current device order (after tree_build: the reference's in-place permuted order) */
 int vvgpu_get_particles(vvgpu_ctx* ctx, int list, vvgpu_obj* out, size_t cap, size_t* n);
 /* records [first, first + count) of the current device order (a rank of a multi-GPU job brings back its share only) */

@@ -12,6 +12,11 @@
 //               velocity(p) on a raster and NodeInfluence() of every segment with the reference classes
 //   lockstep N  per step: clone the reference Space into the gpu Space, run the hot path on both,
 //               compare order / merge decisions bit-exactly and every floating output to 1e-10
+//   resident N  SURVEY 8(f) rows 1 + 2 together: the vortex list LIVES on the device (vvgpu::set_resident), shed vortices
+//               are appended to it, the SLAE right-hand side takes MConvectiveFast::NodeInfluence() from the device tree
+//               (the patch of INTEGRATION.md 2b, applied here between the reference's fill_matrix and its solve), so no
+//               CPU particle tree is ever built and nothing but the shed vortices crosses PCIe. Prints the same rows as
+//               `free` (so the README rows can be checked), runs an all-reference arm beside it and reports steps/s.
 // Built by oracle/Makefile into oracle/_ref/ (needs the reference headers; nothing is copied),
 // linked against oracle/_ref/libvvref.so (reference objects) and vvflow_b200/lib/libvvgpu.so.
 #include "vvgpu_adapter.hpp"
@@ -29,6 +34,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <omp.h>
 
 static void make_case(Space& S, double re, double dt, double R, size_t N) {
     S.re = re;
@@ -83,6 +89,52 @@ struct RefArm {
     }
 };
 
+// The SLAE stage without a CPU particle tree: the reference's own fill_matrix + solve, on a CPU tree that holds the BODY
+// segments only (findNode works, NodeInfluence is 0), with the free vortices' term of every slip equation
+// (MConvectiveFast.cpp:459-467) taken from the device tree. This is MConvectiveFast::calc_circulation (:235-273) with
+// the one-line patch of INTEGRATION.md 2b; the reference's sources stay unmodified (private members reached through the
+// `#define private public` above, test infrastructure only).
+static void calc_circulation_device_rhs(Space& S, MConvectiveFast& convective, TSortedTree& bodytree, const std::vector<double>& ni,
+                                        const void** collision) {
+    bool use_inverse = (*collision == nullptr) && convective.can_use_inverse() && S.time > 0;
+    Matrix& matrix = convective.matrix;
+    matrix.resize(S.total_segment_count() + S.BodyList.size() * 9);
+    const bool right_only = matrix.bodyMatrixIsOk() && use_inverse;
+    if (!right_only) {
+        unsigned eq_no = 0;
+        for (auto& libody : S.BodyList) {
+            for (auto& latt : libody->alist) matrix.setSolutionForCol(eq_no++, &latt.g);
+            matrix.setSolutionForCol(eq_no++, &libody->speed_slae.r.x);
+            matrix.setSolutionForCol(eq_no++, &libody->speed_slae.r.y);
+            matrix.setSolutionForCol(eq_no++, &libody->speed_slae.o);
+            matrix.setSolutionForCol(eq_no++, &libody->force_hydro.r.x);
+            matrix.setSolutionForCol(eq_no++, &libody->force_hydro.r.y);
+            matrix.setSolutionForCol(eq_no++, &libody->force_hydro.o);
+            matrix.setSolutionForCol(eq_no++, &libody->force_holder.r.x);
+            matrix.setSolutionForCol(eq_no++, &libody->force_holder.r.y);
+            matrix.setSolutionForCol(eq_no++, &libody->force_holder.o);
+        }
+    }
+    bodytree.build(/*IncludeVortexes=*/false, /*IncludeBody=*/true, /*IncludeHeat=*/false);
+    convective.fill_matrix(right_only, collision);
+    bodytree.destroy();
+    unsigned eq_no = 0;
+    size_t k = 0;
+    int once = 0;
+    for (auto& libody : S.BodyList) {   // the slip equations are those of every segment but the body's special one (:896-914)
+        TAtt* special = &libody->alist[libody->special_segment_no];
+        for (auto& latt : libody->alist) {
+            if (&latt != special) *matrix.getRightCol(eq_no) -= ni[k];
+            // the circulation equation (:508-512) reads Space::gsum(), the sum over the HOST list, which is empty while
+            // the list is resident: the device's sum takes its place
+            else if (libody->boundary_condition != bc_t::kutta && !once++) *matrix.getRightCol(eq_no) += S.gsum() - vvgpu::gsum(&S);
+            eq_no++; k++;
+        }
+        eq_no += 9;
+    }
+    matrix.solveUsingInverseMatrix(use_inverse);
+}
+
 struct GpuArm {
     Space& S;
     vvgpu::TSortedTree tr;
@@ -134,6 +186,74 @@ int main(int argc, char** argv) {
                 SB.time = TTime::add(SB.time, SB.dt);
             }
             return 0;
+        }
+        if (!strcmp(mode, "resident")) {
+            const bool resident = getenv("VV_DROPIN_NORESIDENT") == nullptr;   // (diagnostic: device right-hand side alone)
+            vvgpu::set_resident(&SB, resident);
+            RefArm A(SA, mn, mx);                         // the all-reference run beside it
+            TSortedTree bodytree(&SB, 8, mn, mx);         // never holds a particle
+            MConvectiveFast slae(&SB, &bodytree);
+            GpuArm B(SB, mn, mx);
+            double worst = 0, t_gpu = 0, t_ref = 0;
+            for (int k = 0; k < nsteps; k++) {
+                double t0 = omp_get_wtime();
+                A.pre();
+                TVec3D fa = SA.BodyList[0]->force_hydro;
+                SA.zero_forces();
+                size_t ca = 0;
+                A.hot(&ca);
+                SA.time = TTime::add(SA.time, SA.dt);
+                t_ref += omp_get_wtime() - t0;
+                t0 = omp_get_wtime();
+                // vvflow.cpp:216-227 on the device tree
+                B.tr.build();
+                std::vector<double> ni = B.convective.NodeInfluence();
+                if (B.collision != nullptr) calc_circulation_device_rhs(SB, slae, bodytree, ni, &B.collision);
+                calc_circulation_device_rhs(SB, slae, bodytree, ni, &B.collision);
+                B.tr.destroy();
+                B.flowmove.heat_shed();
+                B.flowmove.vortex_shed();                  // appended behind the device list
+                B.flowmove.streak_shed();
+                SB.calc_forces();
+                TVec3D f = SB.BodyList[0]->force_hydro;
+                printf("%+.6e %+.6e %+.6e %+.6e %zu\n", double(SB.time), (double)(float)f.r.x, (double)(float)f.r.y,
+                       (double)(float)f.o, vvgpu::particle_count(&SB));
+                if (getenv("VV_DROPIN_DEBUG")) {
+                    TBody &ba = *SA.BodyList[0], &bb = *SB.BodyList[0];
+                    double sga = 0, sgb = 0, fra = 0, frb = 0, gsa = 0, gsb = 0;
+                    for (size_t q = 0; q < ba.alist.size(); q++) { sga += ba.alist[q].g; sgb += bb.alist[q].g; fra += ba.alist[q].fric; frb += bb.alist[q].fric; gsa += ba.alist[q].gsum; gsb += bb.alist[q].gsum; }
+                    printf("   dbg step %d: sum g %.12e / %.12e  fric %.12e / %.12e  gsum %.12e / %.12e  friction_prev.o %.6e / %.6e\n", k, sga, sgb, fra, frb, gsa, gsb,
+                           ba.friction_prev.o, bb.friction_prev.o);
+                }
+                SB.zero_forces();
+                size_t cb = 0;
+                B.hot(&cb);
+                if (getenv("VV_DROPIN_DEBUG")) {
+                    TBody &ba = *SA.BodyList[0], &bb = *SB.BodyList[0];
+                    printf("   dbg after hot %d: g_dead %.12e / %.12e fdt_dead.o %.12e / %.12e cleaned %zu/%zu N %zu/%zu\n", k, ba.g_dead, bb.g_dead, ba.fdt_dead.o, bb.fdt_dead.o, ca, cb,
+                           SA.VortexList.size(), vvgpu::particle_count(&SB));
+                }
+                SB.time = TTime::add(SB.time, SB.dt);
+                t_gpu += omp_get_wtime() - t0;
+                if (resident && !SB.VortexList.empty()) { printf("FAIL step %d: the host list is not empty in resident mode\n", k); return 1; }
+                double fs = fabs(fa.r.x) + fabs(fa.r.y) + fabs(fa.o);
+                double e = (fabs(fa.r.x - f.r.x) + fabs(fa.r.y - f.r.y) + fabs(fa.o - f.o)) / (fs > 0 ? fs : 1);
+                worst = fmax(worst, e);
+                if (vvgpu::particle_count(&SB) != SA.VortexList.size()) {
+                    printf("FAIL step %d: particle count %zu vs %zu\n", k, vvgpu::particle_count(&SB), SA.VortexList.size());
+                    return 1;
+                }
+            }
+            // the resident list against the reference's, at the end (free-running for nsteps: round-off drifts apart slowly)
+            vvgpu::sync_to_host(&SB);
+            double pe = 0;
+            for (size_t i = 0; i < SA.VortexList.size(); i++)
+                pe = fmax(pe, fmax(fabs(SA.VortexList[i].r.x - SB.VortexList[i].r.x), fabs(SA.VortexList[i].r.y - SB.VortexList[i].r.y)));
+            printf("resident: %d steps, N=%zu, force_hydro relerr vs the reference run %.3e, final positions max diff %.3e, "
+                   "steps/s device-resident %.2f vs reference classes %.2f\n", nsteps, SA.VortexList.size(), worst, pe,
+                   nsteps / t_gpu, nsteps / t_ref);
+            printf("%s worst=%.3e\n", (worst <= 1e-8 && pe <= 1e-8) ? "OK" : "FAIL", fmax(worst, pe));
+            return (worst <= 1e-8 && pe <= 1e-8) ? 0 : 1;
         }
         // lockstep
         RefArm A(SA, mn, mx);
@@ -214,9 +334,36 @@ int main(int argc, char** argv) {
                     ns = fmax(ns, fabs(na));
                     ne = fmax(ne, fabs(na - nb[k++]));
                 }
+            // stree::getBottomNodes / findNode with the reference's signatures, on the host mirror of the device tree
+            const std::vector<TSortedNode*>& la = A.tr.getBottomNodes();
+            const std::vector<TSortedNode*>& lb = B.tr.getBottomNodes();
+            const size_t nleaves_checked = la.size();
+            if (la.size() != lb.size()) { printf("FAIL getBottomNodes: %zu vs %zu leaves\n", la.size(), lb.size()); return 1; }
+            for (size_t l = 0; l < la.size(); l++) {
+                const TSortedNode &a = *la[l], &b = *lb[l];
+                bool same = a.x == b.x && a.y == b.y && a.h == b.h && a.w == b.w && a.vRange.last - a.vRange.first == b.vRange.last - b.vRange.first &&
+                            a.bllist.size() == b.bllist.size() && a.NearNodes->size() == b.NearNodes->size() &&
+                            a.FarNodes->size() == b.FarNodes->size() && a.CMp.g == b.CMp.g && a.CMm.r.x == b.CMm.r.x;
+                for (size_t q = 0; same && q < a.NearNodes->size(); q++) same = (*a.NearNodes)[q]->x == (*b.NearNodes)[q]->x && (*a.NearNodes)[q]->y == (*b.NearNodes)[q]->y;
+                for (size_t q = 0; same && q < a.FarNodes->size(); q++) same = (*a.FarNodes)[q]->x == (*b.FarNodes)[q]->x && (*a.FarNodes)[q]->CMp.g == (*b.FarNodes)[q]->CMp.g;
+                for (size_t q = 0; same && q < a.bllist.size(); q++) same = a.bllist[q]->r.x == b.bllist[q]->r.x && a.bllist[q]->r.y == b.bllist[q]->r.y;
+                if (same && a.vRange.first < a.vRange.last) same = a.vRange.first->r.x == b.vRange.first->r.x && a.vRange.first->g == b.vRange.first->g;
+                if (!same) { printf("FAIL getBottomNodes: leaf %zu differs from the reference's\n", l); return 1; }
+            }
+            for (size_t q = 0; q < pts.size(); q++) {
+                const TSortedNode *a = A.tr.findNode(pts[q]), *b = B.tr.findNode(pts[q]);
+                if (a->x != b->x || a->y != b->y || a->h != b->h || a->w != b->w) { printf("FAIL findNode at point %zu\n", q); return 1; }
+                // the reference's own static evaluators walk the mirror like their own tree
+                if (MEpsilonFast::eps2h(*a, pts[q]) != MEpsilonFast::eps2h(*b, pts[q]) || MEpsilonFast::h2(*a, pts[q]) != MEpsilonFast::h2(*b, pts[q])) {
+                    printf("FAIL MEpsilonFast::eps2h / h2 on the mirrored node at point %zu\n", q); return 1;
+                }
+            }
             A.tr.destroy(); B.tr.destroy();
-            printf("points: velocity(p) on %zu points relerr=%.3e; NodeInfluence on %zu segments relerr=%.3e\n", pts.size(),
-                   ve / vs, nb.size(), ne / ns);
+            bool threw = false;
+            try { B.tr.findNode(pts[0]); } catch (const std::invalid_argument&) { threw = true; }
+            if (!threw) { printf("FAIL findNode on an unbuilt tree did not throw\n"); return 1; }
+            printf("points: velocity(p) on %zu points relerr=%.3e; NodeInfluence on %zu segments relerr=%.3e; getBottomNodes / findNode "
+                   "mirror identical on %zu leaves\n", pts.size(), ve / vs, nb.size(), ne / ns, nleaves_checked);
             worst = fmax(worst, fmax(ve / vs, ne / ns));
         }
         printf("%s worst=%.3e\n", worst <= 1e-10 ? "OK" : "FAIL", worst);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("VVGPU_LIB") or os.path.join(HERE, "lib", "libvvgpu.so
 # every symbol include/vvgpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "vvgpu_create", "vvgpu_destroy", "vvgpu_strerror", "vvgpu_last_error",
-    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_append_particles", "vvgpu_particle_count", "vvgpu_get_particles", "vvgpu_get_particles_range",
+    "vvgpu_set_particles", "vvgpu_set_particles_xyg", "vvgpu_append_particles", "vvgpu_particle_count", "vvgpu_particle_gsum", "vvgpu_get_particles", "vvgpu_get_particles_range",
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
@@ -59,6 +59,7 @@ def load():
         "vvgpu_set_particles_xyg": [vp, C.c_int, dp, sz],
         "vvgpu_append_particles": [vp, C.c_int, dp, sz],
         "vvgpu_particle_count": [vp, C.c_int, C.POINTER(sz)],
+        "vvgpu_particle_gsum": [vp, C.c_int, C.POINTER(C.c_double)],
         "vvgpu_get_particles": [vp, C.c_int, dp, sz, C.POINTER(sz)],
         "vvgpu_get_particles_range": [vp, C.c_int, dp, sz, sz],
         "vvgpu_get_permutation": [vp, C.c_int, ip, sz],
@@ -163,6 +164,11 @@ class Context:
         n = C.c_size_t()
         self._ck(self.L.vvgpu_get_particles(self.h, 0, C.c_void_p(ptr), cap, C.byref(n)))
         return n.value
+
+    def gsum(self):
+        v = C.c_double()
+        self._ck(self.L.vvgpu_particle_gsum(self.h, 0, C.byref(v)))
+        return v.value
 
     def get_particles_range_ptr(self, ptr, first, count):
         self._ck(self.L.vvgpu_get_particles_range(self.h, 0, C.c_void_p(ptr), first, count))

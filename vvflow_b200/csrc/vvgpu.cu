@@ -743,6 +743,19 @@ int vvgpu_get_particles(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t cap, size
     CK(stream_sync(c));
     return 0;
 }
+int vvgpu_particle_gsum(vvgpu_ctx* c, int list, double* sum) {
+    if (!c || list != VVGPU_LIST_VORTEX || !sum) return fail(c, VVGPU_EINVAL, "particle_gsum: bad argument");
+    *sum = 0;
+    if (!c->n) return 0;
+    CK(cudaSetDevice(c->device));
+    bool ok = true;
+    double* d = c->d_pairs.get<double>(2, &ok);
+    NEED(ok);
+    k_sum_g<<<1, 1024, 0, c->stream>>>((int)c->n, c->ps[c->cur].g.as<double>(), d); CKLAUNCH();
+    CK(cudaMemcpyAsync(sum, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(stream_sync(c));
+    return 0;
+}
 int vvgpu_get_particles_range(vvgpu_ctx* c, int list, vvgpu_obj* out, size_t first, size_t count) {
     if (!c || list != VVGPU_LIST_VORTEX || (!out && count) || first + count > c->n) return fail(c, VVGPU_EINVAL, "get_particles_range: bad argument");
     if (!count) return 0;

@@ -85,6 +85,21 @@ __global__ void k_move_compact(int n, const u32* __restrict__ scan, Particles in
     orig_out[d] = orig_in[i];
 }
 
+// Space::gsum() (TSpace.hpp): total circulation of the list, for the SLAE's circulation equation when the list lives on
+// the device. One CTA, fixed association order (deterministic; not the reference's sequential order: ~1e-16 relative).
+__global__ void __launch_bounds__(1024) k_sum_g(int n, const double* __restrict__ g, double* out) {
+    __shared__ double sh[1024];
+    double s = 0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += g[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
 // ---- host boundary ---------------------------------------------------------------------------
 __global__ void k_unpack48(int n, const double* __restrict__ rec, Particles P, int* orig) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -30,6 +30,7 @@
 
 #include "TSpace.hpp"
 #include "TBody.hpp"
+#include "TSortedTree.hpp"
 #include "MFlowmove.hpp"
 
 #include <cmath>
@@ -71,7 +72,31 @@ class Device {
         vvgpu_ctx* ctx;
         int index;
         bool dev_newer = false;   // the device holds a newer VortexList than the host
+        bool resident = false;    // the list LIVES on the device: the host copy is only materialised on request
 };
+
+// SURVEY 8(f) row 2. With resident = true the vortex list stays on the device from step to step: move_and_clean() does
+// not download it, vortex_shed() appends what the bodies shed (vvgpu_append_particles) and Space::VortexList stays
+// empty until sync_to_host() materialises a snapshot (a save, TSpace.cpp:64-83). Host code that READS the list every
+// step must not be in the loop then: the SLAE right-hand side comes from MConvectiveFast::NodeInfluence() on the device
+// tree (tests/host/dropin_step.cpp `resident` shows the loop).
+inline void set_resident(Space* S, bool on) { Device::of(S)->resident = on; }
+inline size_t particle_count(Space* S) {
+    Device& D = *Device::of(S);
+    if (!D.dev_newer) return S->VortexList.size();
+    size_t n = 0;
+    D.check(vvgpu_particle_count(D.ctx, VVGPU_LIST_VORTEX, &n), "vvgpu_particle_count");
+    return n;
+}
+
+// Space::gsum() of the resident list (the circulation equation of the SLAE reads it, MConvectiveFast.cpp:511)
+inline double gsum(Space* S) {
+    Device& D = *Device::of(S);
+    if (!D.dev_newer) return S->gsum();
+    double v = 0;
+    D.check(vvgpu_particle_gsum(D.ctx, VVGPU_LIST_VORTEX, &v), "vvgpu_particle_gsum");
+    return v;
+}
 
 // Space::VortexList <- device (reference order). Needed only if host code wants to look at the
 // list between build() and move_and_clean().
@@ -83,7 +108,7 @@ inline void sync_to_host(Space* S) {
     S->VortexList.resize(n);
     D.check(vvgpu_get_particles(D.ctx, VVGPU_LIST_VORTEX, reinterpret_cast<vvgpu_obj*>(S->VortexList.data()), n, &n),
             "vvgpu_get_particles");
-    D.dev_newer = false;
+    if (!D.resident) D.dev_newer = false;   // (resident: the host copy is a read-only snapshot, the device stays the owner)
 }
 
 // the TAtt/TBody state the hot path reads; the private bounding rect / disc of TBody
@@ -151,16 +176,36 @@ class stree {
         void destroy() {   // :267-273
             Device& D = *Device::of(S);
             D.check(vvgpu_tree_destroy(D.ctx), "vvgpu_tree_destroy");
+            drop_mirror();
             built = false;
         }
         bool isBuilt() const { return built; }
 
-        // leaf table in bottomNodes order (getBottomNodes, :275-282): per leaf x y h w and the
-        // [first,last) range of its vortexes in the permuted list
+        // stree::getBottomNodes / findNode (TSortedTree.hpp:86-87, TSortedTree.cpp:275-303) with the reference's own
+        // signatures: the device tree is mirrored on the host, on first use after build(), as a tree of the reference's
+        // ::TSortedNode objects — x y h w, CMp CMm, ch1 ch2, vRange into Space::VortexList (synchronised and in the
+        // tree's order), bllist into the bodies' TAtt, NearNodes / FarNodes of every bottom node — so that unchanged
+        // host code (X* evaluators, static MEpsilonFast::eps2h / h2, MConvectiveFast::NodeInfluence) can walk it.
+        const std::vector< ::TSortedNode*>& getBottomNodes() const {
+            if (!built) { fprintf(stderr, "PANIC in stree::getBottomNodes()! Tree isn't built\n"); return bottomNodes; }   // :277-281
+            materialize();
+            return bottomNodes;
+        }
+        const ::TSortedNode* findNode(TVec p) const {
+            if (!built) throw std::invalid_argument("TTree::findNode(): tree is not built");   // :286-288
+            materialize();
+            const ::TSortedNode* Node = rootNode;
+            while (Node->ch1) {   // :291-301
+                if (Node->h < Node->w) Node = (p.x < Node->x) ? Node->ch1 : Node->ch2;
+                else Node = (p.y < Node->y) ? Node->ch1 : Node->ch2;
+            }
+            return Node;
+        }
+        // the leaf table without the mirror: per leaf x y h w and the [first,last) range of its vortexes
         struct Leaf { double x, y, h, w; size_t vfirst, vlast, nseg; };
-        std::vector<Leaf> getBottomNodes() const {
+        std::vector<Leaf> leafTable() const {
             std::vector<Leaf> out;
-            if (!built) { fprintf(stderr, "PANIC in stree::getBottomNodes()! Tree isn't built\n"); return out; }   // :277-281
+            if (!built) { fprintf(stderr, "PANIC in stree::getBottomNodes()! Tree isn't built\n"); return out; }
             Device& D = *Device::of(S);
             size_t nn = 0, nl = 0, depth = 0;
             D.check(vvgpu_tree_counts(D.ctx, &nn, &nl, &depth), "vvgpu_tree_counts");
@@ -177,13 +222,68 @@ class stree {
             }
             return out;
         }
+        ~stree() { drop_mirror(); }
 
     private:
+        void drop_mirror() const {
+            delete rootNode;   // snode::~snode deletes its children and its lists (TSortedTree.cpp:28-34)
+            rootNode = nullptr;
+            bottomNodes.clear();
+        }
+        void materialize() const {
+            if (rootNode) return;
+            Device& D = *Device::of(S);
+            sync_to_host(S);   // vRange points into Space::VortexList, which has to be the tree's (permuted) list
+            size_t nn = 0, nl = 0, depth = 0;
+            D.check(vvgpu_tree_counts(D.ctx, &nn, &nl, &depth), "vvgpu_tree_counts");
+            std::vector<double> dbl(10 * nn);
+            std::vector<int64_t> idx(8 * nn);
+            D.check(vvgpu_tree_export(D.ctx, dbl.data(), idx.data(), nn), "vvgpu_tree_export");
+            std::vector< ::TSortedNode*> node(nn, nullptr);   // pre-order ids, children after their parent
+            for (size_t i = 0; i < nn; i++) node[i] = new ::TSortedNode(nullptr);
+            TObj* v0 = S->VortexList.data();
+            bottomNodes.assign(nl, nullptr);
+            for (size_t i = 0; i < nn; i++) {
+                ::TSortedNode* n = node[i];
+                n->x = dbl[10 * i]; n->y = dbl[10 * i + 1]; n->h = dbl[10 * i + 2]; n->w = dbl[10 * i + 3];
+                n->CMp.r = TVec(dbl[10 * i + 4], dbl[10 * i + 5]); n->CMp.g = dbl[10 * i + 6];
+                n->CMm.r = TVec(dbl[10 * i + 7], dbl[10 * i + 8]); n->CMm.g = dbl[10 * i + 9];
+                n->i = (int)idx[8 * i + 7]; n->j = 0;
+                if (v0) n->vRange.set(v0 + idx[8 * i], v0 + idx[8 * i + 1]);
+                if (idx[8 * i + 3] >= 0) { n->ch1 = node[(size_t)idx[8 * i + 3]]; n->ch2 = node[(size_t)idx[8 * i + 4]]; }
+                if (idx[8 * i + 5] >= 0) bottomNodes[(size_t)idx[8 * i + 5]] = n;
+            }
+            rootNode = node[0];
+            // bllist of the bottom nodes: the segments in the order DistributeContent(LList&) left them (:139-148)
+            std::vector<TObj*> att;
+            for (auto& lbody: S->BodyList) for (auto& latt: lbody->alist) att.push_back(&latt);
+            if (!att.empty()) {
+                std::vector<int64_t> sp(nl + 1), si(att.size());
+                D.check(vvgpu_tree_leaf_segments(D.ctx, sp.data(), si.data(), si.size()), "vvgpu_tree_leaf_segments");
+                for (size_t l = 0; l < nl; l++)
+                    for (int64_t k = sp[l]; k < sp[l + 1]; k++) bottomNodes[l]->bllist.push_back(att[(size_t)si[k]]);
+            }
+            // NearNodes / FarNodes exactly as snode::FindNearNodes builds them (:199-217)
+            std::vector<int64_t> np(nl + 1), fp(nl + 1);
+            D.check(vvgpu_tree_lists(D.ctx, np.data(), nullptr, 0, fp.data(), nullptr, 0), "vvgpu_tree_lists");
+            std::vector<int64_t> ni((size_t)np[nl] + 1), fi((size_t)fp[nl] + 1);
+            D.check(vvgpu_tree_lists(D.ctx, np.data(), ni.data(), ni.size(), fp.data(), fi.data(), fi.size()), "vvgpu_tree_lists");
+            for (size_t l = 0; l < nl; l++) {
+                ::TSortedNode* n = bottomNodes[l];
+                n->NearNodes = new std::vector< ::TSortedNode*>();
+                n->FarNodes = new std::vector< ::TSortedNode*>();
+                for (int64_t k = np[l]; k < np[l + 1]; k++) n->NearNodes->push_back(bottomNodes[(size_t)ni[k]]);
+                for (int64_t k = fp[l]; k < fp[l + 1]; k++) n->FarNodes->push_back(node[(size_t)fi[k]]);
+            }
+        }
+
         Space* S;
         int farCriteria;
         double minNodeSize;
         double maxNodeSize;
         bool built;
+        mutable ::TSortedNode* rootNode = nullptr;             // host mirror (see getBottomNodes)
+        mutable std::vector< ::TSortedNode*> bottomNodes;
 };
 typedef stree TSortedTree;
 
@@ -318,9 +418,20 @@ class MFlowmove {
             }
             if (cleaned_v) *cleaned_v = cleaned;
             D.dev_newer = true;
-            sync_to_host(S);   // shedding and the SLAE phase of the next step work on the host list
+            if (D.resident) S->VortexList.clear();   // the device owns the list; nothing crosses PCIe
+            else sync_to_host(S);                    // shedding and the SLAE phase of the next step work on the host list
         }
-        void vortex_shed() { host.vortex_shed(); }
+        // MFlowmove::vortex_shed, MFlowmove.cpp:217-235. Resident list: the host vector is empty, so what the reference's
+        // code pushes is exactly what is new; it goes behind the device list and the host vector is emptied again.
+        void vortex_shed() {
+            Device& D = *Device::of(S);
+            if (!(D.resident && D.dev_newer)) { host.vortex_shed(); return; }
+            S->VortexList.clear();
+            host.vortex_shed();
+            D.check(vvgpu_append_particles(D.ctx, VVGPU_LIST_VORTEX, reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()),
+                                           S->VortexList.size()), "vvgpu_append_particles");
+            S->VortexList.clear();
+        }
         void streak_shed() { host.streak_shed(); }
         void heat_shed() { host.heat_shed(); }
         void heat_crop(double scale = 16) { host.heat_crop(scale); }

@@ -509,6 +509,44 @@ def test_cylinder_200k_with_merges(ctx, port):
     assert out["merged"] > 1000
 
 
+def test_conv_tma_variant():
+    """the build of K4 that stages the source leaves with TMA bulk copies (lib/libvvgpu_tma.so, -DVV_CV_TMA=1; measured
+    slower than the default, kept as the evidence behind that choice): same convective velocities, 1e-10, on a cloud and
+    a cylinder case, in a fresh process so that the other library is the one loaded"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "vvflow_b200", "lib", "libvvgpu_tma.so")
+    if not os.path.exists(lib):
+        pytest.skip("libvvgpu_tma.so not built (vvflow_b200.build.build(variants=True))")
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import cases
+from oracle import pyport
+from vvflow_b200 import capi, vvhd
+ctx = capi.Context(0)
+for xyg, bodies in ((cases.cloud(30000, "gauss", "mixed", seed=5), []),
+                    (cases.around_cylinder(20000, sign="mixed", seed=6), [cases.cylinder(0.5, 350)])):
+    mn, mx = cases.tree_params(bodies)
+    P = pyport.Port(xyg=xyg, bodies=cases.port_bodies(pyport, bodies))
+    S = vvhd.Space(ctx=ctx); S.VortexList = xyg; S.BodyList = bodies; S.re, S.dt, S.inf_vx = 600., 0.05, 1.
+    tr = vvhd.TSortedTree(S, 8, mn, mx)
+    P.tree_build(8, mn, mx); tr.build()
+    assert P.epsilon(True) == (vvhd.MEpsilonFast(S, tr).CalcEpsilonFast(True) or True) or True
+    P.convective(1.0, 0.0, 0.05); vvhd.MConvectiveFast(S, tr).process_all_lists()
+    a, b = S.VortexList, P.rec48()
+    assert cases.same(a[:, [0, 1, 2, 5]], b[:, [0, 1, 2, 5]])
+    cases.check_close(a[:, 3:5], b[:, 3:5], 1e-10, "convective velocity, TMA variant")
+    tr.destroy(); P.tree_destroy()
+print("TMA-OK")
+""" % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, VVGPU_LIB=lib)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and "TMA-OK" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
+
+
 def test_error_behaviour(ctx):
     """call-order errors mirror the reference (TSortedTree.cpp:234,286-288; MFlowmove.cpp:20-22)"""
     from vvflow_b200 import capi, vvhd

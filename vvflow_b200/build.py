@@ -6,6 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "vvgpu.cu")
 OUT = os.path.join(HERE, "lib", "libvvgpu.so")
+OUT_TMA = os.path.join(HERE, "lib", "libvvgpu_tma.so")   # K4 with TMA-staged source tiles (a measured, slower variant)
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(HERE, "..", "include", "vvgpu.h")]
 
@@ -24,7 +25,7 @@ def stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variants=False):
     if not force and not stale():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
@@ -33,6 +34,8 @@ def build(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
+    if variants:
+        subprocess.check_call([c if c != OUT else OUT_TMA for c in cmd] + ["-DVV_CV_TMA=1"])
     return OUT
 
 

@@ -123,7 +123,7 @@ struct vvgpu_ctx {
     size_t nslots = 0;
     bool lists_ready = false;
     // epsilon
-    Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged;
+    Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged, leaf_dirty, leaf_dbox;
     Buf mA[6], mB[6];
     Buf d_sinks, d_pairs, pt_xy, pt_out, pt_v;
     PSet ps_backup;   // the resident list while a raster evaluator works on its own tree
@@ -664,7 +664,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
-                  &c->lrestr, &c->latt, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
+                  &c->lrestr, &c->latt, &c->leaf_dirty, &c->leaf_dbox, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
                   &c->sh_first, &c->sh_cnt, &c->sh_off, &c->sh_rankcnt, &c->xsend, &c->xrecv, &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
@@ -1041,13 +1041,20 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     CK(cudaMemcpyAsync(ietmp, P.ie.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     bool haveA = false;
     int rounds = 0;
+    unsigned char* ldirty = c->leaf_dirty.get<unsigned char>(nl, &ok);
+    double* ldbox = c->leaf_dbox.get<double>(4 * (size_t)nl, &ok);
+    NEED(ok);
     for (;; rounds++) {
         if (rounds > n + 2) return fail(c, VVGPU_ELIMIT, "merge fixed point did not converge");
         MergeState A = haveA ? mstate(c->mA) : MergeState{};
         MergeState B = mstate(c->mB);
-        k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH();
+        // later rounds recompute only the leaves that see a changed entry; the others keep last round's outcome
+        if (haveA) { k_merge_copy<<<cdiv(n, 256), 256, 0, st>>>(n, A, B); CKLAUNCH(); }
+        else { k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH(); }
         CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
         EpsOp<false> op{A, B, lcrit, lrestr, dyn, ietmp, dchg};
+        op.leaf_dirty = haveA ? ldirty : nullptr;
+        op.leaf_dbox = ldbox;
         int rc = eps_boxes(c, A);
         if (!rc) rc = launch_near(c, op, haveA ? dyn : nullptr);
         if (rc) return rc;
@@ -1062,11 +1069,21 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
             if (rc) return rc;
             k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(n, B.absby, kNoAbs); CKLAUNCH();
             k_merge_fill<<<cdiv(n, 256), 256, 0, st>>>(n, P.view(), A, B); CKLAUNCH();
+        } else {
+            // absorbed-by follows from the (init, part) columns
+            k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(n, B.absby, kNoAbs); CKLAUNCH();
+            k_merge_absby<<<cdiv(n, 256), 256, 0, st>>>(n, B.init, B.part, B.absby); CKLAUNCH();
         }
         u32 changed = 0;
         rc = read_u32(c, (u32*)dchg, &changed);
         if (rc) return rc;
+        if (getenv("VVGPU_DEBUG_MERGE")) {
+            u32 redo = 0;
+            read_u32(c, (u32*)dchg + 1, &redo);
+            fprintf(stderr, "[vvgpu] merge round %d: %u decisions changed, %u target batches of %d leaves recomputed (0 = all)\n", rounds, changed, redo, nl);
+        }
         if (!changed) break;  // B reproduces A
+        k_leaf_dirty<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, P.view(), A, B, ldirty, ldbox); CKLAUNCH();
         for (int k = 0; k < 6; k++) std::swap(c->mA[k], c->mB[k]);
         haveA = true;
         k_merge_dyn<<<cdiv(n, 256), 256, 0, st>>>(n, mstate(c->mA), dyn); CKLAUNCH();

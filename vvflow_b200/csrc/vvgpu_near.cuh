@@ -82,6 +82,7 @@ struct LwSharedT {
     int4 ent[kUnitEntries];      // first particle, count, first segment, segment count of the entry's leaf
     u32 emk[kUnitEntries];       // target-leaf mask
     double ebox[Op::kFilter ? kUnitEntries : 1][4];   // source-leaf box (ops with kFilter)
+    unsigned char edirty[Op::kDirty ? kUnitEntries : 1];   // source leaf holds a particle whose merge entry changed last round
     int bounds[kGroupLeaves + 1];
     int next;                    // next target leaf of the group to hand out
     int anyseg;
@@ -130,6 +131,11 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
             const double* b = A.lbox + 5ll * sl;
             S.ebox[e][0] = b[0]; S.ebox[e][1] = b[1]; S.ebox[e][2] = b[2]; S.ebox[e][3] = b[3];
         }
+        if constexpr (Op::kDirty) {
+            static_assert(!Op::kSegments, "ent.z carries the source leaf for the dirty test");
+            S.ent[e].z = sl;
+            S.edirty[e] = op.leaf_dirty ? op.leaf_dirty[sl] : 1;
+        }
     }
     __syncthreads();
     const int t0 = S.bounds[0], t1 = S.bounds[nl];
@@ -167,6 +173,28 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
                     R2 = fmax(R2, __shfl_xor_sync(kFullMask, R2, o));
                 }
                 R2 *= 1.000000001;  // the skip stays strictly conservative against rounding in the gap
+            }
+            if constexpr (Op::kDirty) {
+                // A later round of the merge fixed point. These targets decide as in the last round — whose outcome
+                // the new solution was seeded with — unless a particle whose entry changed lies within their reach at
+                // any of the positions it was or is seen at (original, old merged, new merged: the leaf's dirty box).
+                // Their own leaf is in the list at distance 0, so a change among the seeds always recomputes.
+                if (op.leaf_dirty && !multi) {
+                    bool need = false;
+                    for (int eb0 = 0; eb0 < ne && !need; eb0 += 32) {
+                        const int e = eb0 + lane;
+                        bool hit = false;
+                        if (e < ne && ((S.emk[e] >> lt) & 1u) && S.edirty[e]) {
+                            const double* b = op.leaf_dbox + 4ll * S.ent[e].z;
+                            const double gx = fmax(0., fmax(b[0] - bx1, bx0 - b[1]));
+                            const double gy = fmax(0., fmax(b[2] - by1, by0 - b[3]));
+                            hit = !(gx * gx + gy * gy > R2);
+                        }
+                        need = __any_sync(kFullMask, hit);
+                    }
+                    if (!need) continue;
+                    if (lane == 0) atomicAdd(op.changed + 1, 1);   // target batches recomputed in this round (diagnostic)
+                }
             }
             // sub-lane layout: nt x m lanes, m = 32 / nt
             static_assert(sizeof(typename Op::Tgt) <= sizeof(W.tsave[0]), "tsave slot too small");
@@ -303,6 +331,7 @@ __global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4
 struct ConvOp {
     static constexpr bool kSegments = false;
     static constexpr bool kFilter = false;
+    static constexpr bool kDirty = false;
     double inf_vx, inf_vy, eps2_div_srcg;
     const double* taylor;  // 4 per leaf
     const double* sinks;   // (x,y,g) triples
@@ -356,6 +385,7 @@ struct DiffOp {
     // only sources within 8 eps of a target contribute (:101): leaves farther than that from the whole
     // group are never staged. 1e-6 relative slack keeps the skip strictly conservative.
     static constexpr bool kFilter = true;
+    static constexpr bool kDirty = false;
     double re;
     double* fric;  // per segment, atomically accumulated (MDiffusiveFast.cpp:121-122)
     struct Tgt { double x, y, ie, ie2, lim, g, S1, S2x, S2y, S0, S3x, S3y; bool pos; };
@@ -460,6 +490,7 @@ struct EpsOp {
     // distance cannot hold a closer neighbour of any of them: exact pruning
     static constexpr bool kFilter = true;
     static constexpr int kMinBlocks = VV_EPS_MINB;
+    static constexpr bool kDirty = !FINAL;
     MergeState A_;      // assumed solution (absby == nullptr: no merges anywhere)
     MergeState B_;      // recomputed solution (decision mode only)
     const double* lcrit;   // per leaf merge_criteria_sq (NaN: never merge)
@@ -467,6 +498,8 @@ struct EpsOp {
     const unsigned char* dyn;  // per particle: has a timeline entry in A_
     double* ie_out;
     int* changed;
+    const unsigned char* leaf_dirty = nullptr;   // per leaf (decision rounds after the first): holds a changed entry
+    const double* leaf_dbox = nullptr;           // per leaf 4: box of every position its changed particles were or are seen at
     struct Tgt { double x, y, r1, r2; int i, i1, i2, pad_; };
     __device__ __forceinline__ double reach2(const Tgt& t) const { return t.r2; }
     struct Part { double r1, r2; int i1, i2; };
@@ -498,6 +531,7 @@ struct EpsOp {
             if (A_.absby[i] < i) {  // absorbed before its turn: g == 0 by then, _1_eps stays as it was
                 if (A_.init[i]) atomicAdd(changed, 1);
                 ie_out[i] = A.P.ie[i];
+                if (B_.init) { B_.init[i] = 0; B_.part[i] = -1; }
                 return false;
             }
         }
@@ -579,13 +613,13 @@ struct EpsOp {
                         __double_as_longlong(A_.ny[i]) == __double_as_longlong(ny) &&
                         __double_as_longlong(A_.ng[i]) == __double_as_longlong(ng)) diff = false;
                     B_.init[i] = 1; B_.part[i] = t.i1; B_.nx[i] = nx; B_.ny[i] = ny; B_.ng[i] = ng;
-                    atomicMin(&B_.absby[t.i1], i);
-                    if (diff) atomicAdd(changed, 1);
+                    if (diff) atomicAdd(changed, 1);   // (absorbed-by is rebuilt from (init, part) after the round)
                     return;  // its epsilon comes from the FINAL pass at the merged position
                 }
             }
         }
         if (!FINAL && A_.absby && A_.init[i]) atomicAdd(changed, 1);  // assumed a merge that does not happen
+        if (!FINAL && B_.init) { B_.init[i] = 0; B_.part[i] = -1; }   // (the new solution may have been seeded with the old one)
         ie_out[i] = 1.0 / std_max(eps, restr);  // :52
     }
 };
@@ -604,6 +638,37 @@ __global__ void k_merge_clear(int n, MergeState M) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     M.absby[i] = kNoAbs; M.init[i] = 0; M.part[i] = -1;
+}
+// the next round's solution starts as a copy of this round's: leaves that are not recomputed keep their entries
+__global__ void k_merge_copy(int n, MergeState A, MergeState B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    B.init[i] = A.init[i]; B.part[i] = A.part[i]; B.nx[i] = A.nx[i]; B.ny[i] = A.ny[i]; B.ng[i] = A.ng[i];
+}
+// per leaf: does it hold a particle whose entry differs between the old solution (A, absent before the first round)
+// and the new one (B)? Targets that see no such leaf would decide as before.
+__global__ void k_leaf_dirty(LeafDev L, int nleaves, Particles P, MergeState A, MergeState B, unsigned char* dirty, double* dbox) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaves) return;
+    bool any = false;
+    double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX;
+    for (int i = L.first[l]; i < L.last[l]; i++) {
+        const int bi = B.init[i], ba = B.absby[i];
+        const int ai = A.absby ? A.init[i] : 0, aa = A.absby ? A.absby[i] : kNoAbs;
+        bool d = bi != ai || ba != aa;
+        if (!d && bi) d = B.part[i] != A.part[i] || __double_as_longlong(B.nx[i]) != __double_as_longlong(A.nx[i]) ||
+                          __double_as_longlong(B.ny[i]) != __double_as_longlong(A.ny[i]) ||
+                          __double_as_longlong(B.ng[i]) != __double_as_longlong(A.ng[i]);
+        if (!d) continue;
+        any = true;
+        double x = P.x[i], y = P.y[i];
+        x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
+        if (ai) { x = A.nx[i]; y = A.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
+        if (bi) { x = B.nx[i]; y = B.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
+    }
+    dirty[l] = any ? 1 : 0;
+    double* b = dbox + 4ll * l;
+    b[0] = x0; b[1] = x1; b[2] = y0; b[3] = y1;
 }
 __global__ void k_merge_dyn(int n, MergeState M, unsigned char* dyn) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -140,6 +140,16 @@ int vvgpu_node_influence(vvgpu_ctx* ctx, double* out_nseg);
  * Space::average_segment_length(). out[yj * xres + xi] in double: XField::map stores the same value as float. ---- */
 int vvgpu_vorticity_raster(vvgpu_ctx* ctx, float xmin, float ymin, float dxdy, int xres, int yres, double eps_mult,
                            double dl, double* out);
+/* ---- XPressure::evaluate, XPressure.cpp:32-146 (the pressure raster of vvplot) on the resident vortex
+ * list, which must already hold what MFlowmove::vortex_shed adds (:56; append with vvgpu_append_particles), with
+ * gsum_nseg = TAtt::gsum of every segment AFTER that shed (vortex_shed adds g, MFlowmove.cpp:227). Builds its own tree
+ * (far criteria 8, minNodeSize 20 dl, maxNodeSize 0.1, :27) and runs one velocity pass (epsilon without merging,
+ * convective, diffusive, :61-64) on a copy: the resident list comes back as it was. ref frame 's': use_ref_speed = 0;
+ * 'o' / 'f' / 'b': use_ref_speed = 1 with (0,0) / inf_speed / the body's speed (:38-52). out[yj * xres + xi] in
+ * double: XField::map stores the same value as float. Single-rank contexts. ---------------------------------------- */
+int vvgpu_pressure_raster(vvgpu_ctx* ctx, float xmin, float ymin, float dxdy, int xres, int yres, double dl, double re,
+                          double dt, double inf_vx, double inf_vy, const double* sinks_xyg, size_t nsink,
+                          const double* gsum_nseg, int use_ref_speed, double ref_vx, double ref_vy, double* out);
 /* ---- MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48. fric_out (nseg, may be NULL)
  * receives the per-segment increments of TAtt::fric (:121-122) ------------------------------- */
 int vvgpu_diffusive(vvgpu_ctx* ctx, double re, double* fric_out);

@@ -657,6 +657,72 @@ void vvo_vorticity_raster(vvo_plist* p, const vvo_bodies* b, float xmin, float y
     vvo_tree_free(t);
 }
 
+/* XPressure::evaluate + XPressure::pressure (libvvhd/src/XPressure.cpp:32-146), the pressure raster of vvplot.
+ * `p` is the vortex list AFTER MFlowmove::vortex_shed (:56) and b->gsum the segments' gsum after it (vortex_shed adds g,
+ * MFlowmove.cpp:227); the list is permuted by the tree this function builds for itself (far criteria 8, minNodeSize
+ * 20 dl, maxNodeSize 0.1, :27). One ordinary velocity pass (epsilon without merging, convective, diffusive, :61-64),
+ * then per raster point (:84-92): 0 inside a body, else (:108-146)
+ *   2pi Cp = sum over segments [(rotl(K) g_s + K q_s) . Vs] - sum over segments (dl/dt . rotl(K)) (running sum of gsum)
+ *          + sum over ALL vortices (v . rotl(K(r, p))) g,      K(o, p) = (p - o) / |p - o|^2
+ *   Cp = 2pi Cp / 2pi + (|inf_speed|^2 - |velocity(p)|^2) / 2  [+ |velocity(p) - ref_speed|^2 / 2 unless ref_frame 's'].
+ * b->fric is left as it was (the diffusive pass adds to it). out[yj * xres + xi] in double. */
+void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
+void vvo_pressure_raster(vvo_plist* p, vvo_bodies* b, float xmin, float ymin, float dxdy, int xres, int yres, double dl,
+                         double re, double dt, double inf_vx, double inf_vy, const double* sinks, int64_t nsink,
+                         int use_ref_speed, double ref_vx, double ref_vy, double* out) {
+    static vvo_bodies nobody;
+    if (!b) b = &nobody;
+    vvo_tree* t = vvo_tree_build(p, b, 8, dl * 20, 0.1);
+    double* fric_keep = (double*)malloc(sizeof(double) * (size_t)(b->nseg > 0 ? b->nseg : 1));
+    for (int64_t s = 0; s < b->nseg; s++) fric_keep[s] = b->fric[s];
+    vvo_epsilon(t, p, b, 0);
+    vvo_convective(t, p, b, inf_vx, inf_vy, dt, sinks, nsink);
+    vvo_diffusive(t, p, b, re);
+    for (int64_t s = 0; s < b->nseg; s++) b->fric[s] = fric_keep[s];
+    free(fric_keep);
+    for (int yj = 0; yj < yres; yj++) {
+        for (int xi = 0; xi < xres; xi++) {
+            /* TVec p = TVec(xmin, ymin) + dxdy*TVec(xi, yj), all floats promoted (:88) */
+            const double px = (double)xmin + (double)dxdy * (double)xi, py = (double)ymin + (double)dxdy * (double)yj;
+            int inbody = 0;
+            for (int64_t ib = 0; ib < b->nbody && !inbody; ib++) inbody = vvo_point_invalid(b, ib, px, py) >= 0;
+            if (inbody) { out[(size_t)yj * xres + xi] = 0; continue; }
+            double cp = 0;
+            for (int64_t ib = 0; ib < b->nbody; ib++) {
+                const double* bp = b->bprop + 13 * ib;
+                const double ax = bp[0], ay = bp[1], sx = bp[10], sy = bp[11], so = bp[12];
+                for (int64_t s = b->bfirst[ib]; s < b->bfirst[ib + 1]; s++) {   /* first addend, :115-121 */
+                    const double ux = b->rx[s] - ax, uy = b->ry[s] - ay;
+                    const double vsx = sx + so * (-uy), vsy = sy + so * ux;        /* Vs = speed.r + speed.o * rotl(r - axis) */
+                    const double g = -(vsx * b->dlx[s] + vsy * b->dly[s]);
+                    const double q = -(-vsy * b->dlx[s] + vsx * b->dly[s]);
+                    const double drx = px - b->rx[s], dry = py - b->ry[s], r2 = drx * drx + dry * dry;
+                    const double kx = drx / r2, ky = dry / r2;
+                    cp += (-ky * g + kx * q) * vsx + (kx * g + ky * q) * vsy;
+                }
+                double gtmp = 0;
+                for (int64_t s = b->bfirst[ib]; s < b->bfirst[ib + 1]; s++) {   /* second addend, :124-130 */
+                    gtmp += b->gsum[s];
+                    const double drx = px - b->rx[s], dry = py - b->ry[s], r2 = drx * drx + dry * dry;
+                    const double kx = drx / r2, ky = dry / r2;
+                    cp -= (b->dlx[s] / dt * (-ky) + b->dly[s] / dt * kx) * gtmp;
+                }
+            }
+            for (int64_t j = 0; j < p->n; j++) {   /* :133-136 */
+                const double drx = px - p->x[j], dry = py - p->y[j], r2 = drx * drx + dry * dry;
+                const double kx = drx / r2, ky = dry / r2;
+                cp += (p->vx[j] * (-ky) + p->vy[j] * kx) * p->g[j];
+            }
+            double v[2], xy[2] = {px, py};
+            vvo_velocity_at(t, p, b, inf_vx, inf_vy, dt, sinks, nsink, xy, 1, v);
+            double res = C_1_2PI * cp + 0.5 * ((inf_vx * inf_vx + inf_vy * inf_vy) - (v[0] * v[0] + v[1] * v[1]));
+            if (use_ref_speed) res += 0.5 * (sqr(v[0] - ref_vx) + sqr(v[1] - ref_vy));
+            out[(size_t)yj * xres + xi] = res;
+        }
+    }
+    vvo_tree_free(t);
+}
+
 /* ------------------------------------------------------------------ diffusive */
 
 /* MDiffusiveFast::process_vort_list, MDiffusiveFast.cpp:8-48, with vortex_influence (:93-105)

@@ -83,6 +83,10 @@ void vvo_node_influence(const vvo_tree* t, const vvo_plist* p, const vvo_bodies*
 /* XVorticity::evaluate (XVorticity.cpp:26-97) on the post-shed list p (permuted by the tree built inside) */
 void vvo_vorticity_raster(vvo_plist* p, const vvo_bodies* b, float xmin, float ymin, float dxdy, int xres, int yres,
                           double eps_mult, double dl, double* out);
+/* XPressure::evaluate (XPressure.cpp:32-146) on the post-shed list p and gsum (permuted by the tree built inside) */
+void vvo_pressure_raster(vvo_plist* p, vvo_bodies* b, float xmin, float ymin, float dxdy, int xres, int yres, double dl,
+                         double re, double dt, double inf_vx, double inf_vy, const double* sinks, int64_t nsink,
+                         int use_ref_speed, double ref_vx, double ref_vy, double* out);
 void vvo_diffusive(const vvo_tree* t, vvo_plist* p, vvo_bodies* b, double re);
 /* advect, drop |g|<remove_eps, drop in-body (accumulating dead sums), zero v. Compacts p in place,
  * returns the new n; *cleaned = number removed by the in-body test */

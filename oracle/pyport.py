@@ -60,6 +60,9 @@ def lib():
         L.vvo_node_influence.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_void_p]
         L.vvo_vorticity_raster.argtypes = [C.POINTER(_PList), C.POINTER(_Bodies), C.c_float, C.c_float, C.c_float, C.c_int,
                                            C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.vvo_pressure_raster.argtypes = [C.POINTER(_PList), C.POINTER(_Bodies), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int64,
+                                          C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.vvo_velocity_at.argtypes = [C.POINTER(_Tree), C.POINTER(_PList), C.POINTER(_Bodies), C.c_double, C.c_double,
                                       C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.vvo_move_and_clean.restype = C.c_int64
@@ -240,6 +243,17 @@ class Port:
         assert self.tree is None or not self.tree, "destroy the tree first"
         out = np.zeros((yres, xres))
         self.L.vvo_vorticity_raster(C.byref(self.p), self._b(), xmin, ymin, dxdy, xres, yres, eps_mult, dl, _ptr(out))
+        return out
+
+    def pressure_raster(self, xmin, ymin, dxdy, xres, yres, dl, re, dt, inf_vx=0.0, inf_vy=0.0, sinks=None, ref_speed=None):
+        """XPressure::evaluate on this (post-shed) list and the bodies' post-shed gsum; the list is permuted by the tree built
+        inside. ref_speed = None is ref_frame 's'. (yres, xres) float64 — the reference stores float32 of the same values."""
+        assert self.tree is None or not self.tree, "destroy the tree first"
+        out = np.zeros((yres, xres))
+        s = np.zeros((0, 3)) if sinks is None else np.ascontiguousarray(sinks, dtype=np.float64).reshape(-1, 3)
+        rs = (0.0, 0.0) if ref_speed is None else ref_speed
+        self.L.vvo_pressure_raster(C.byref(self.p), self._b(), xmin, ymin, dxdy, xres, yres, dl, re, dt, inf_vx, inf_vy, _ptr(s),
+                                   s.shape[0], 0 if ref_speed is None else 1, rs[0], rs[1], _ptr(out))
         return out
 
     def diffusive(self, re):

@@ -63,6 +63,8 @@ def _load():
         "vvr_node_influence": (None, [C.c_void_p, _dp]),
         "vvr_vorticity_raster": (None, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double,
                                         np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]),
+        "vvr_pressure_raster": (None, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]),
         "vvr_diffusive": (None, [C.c_void_p, C.c_int, C.c_int]),
         "vvr_move_and_clean": (C.c_size_t, [C.c_void_p, C.c_int]),
         "vvr_calc_circulation": (None, [C.c_void_p]),
@@ -253,6 +255,12 @@ class Ref:
         """XVorticity(S, ...).evaluate(): (yres, xres) float32 map"""
         out = np.zeros((yres, xres), dtype=np.float32)
         self.L.vvr_vorticity_raster(self.h, xmin, ymin, dxdy, xres, yres, eps_mult, out)
+        return out
+
+    def pressure_raster(self, xmin, ymin, dxdy, xres, yres, ref_frame="s"):
+        """XPressure(S, ...).evaluate(): (yres, xres) float32 map"""
+        out = np.zeros((yres, xres), dtype=np.float32)
+        self.L.vvr_pressure_raster(self.h, xmin, ymin, dxdy, xres, yres, ord(ref_frame), out)
         return out
 
     def diffusive(self, vort=True, heat=False):

@@ -28,6 +28,7 @@
 #include "MDiffusiveFast.hpp"
 #include "MFlowmove.hpp"
 #include "XVorticity.hpp"
+#include "XPressure.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -397,6 +398,24 @@ void vvr_vorticity_raster(void* h, float xmin, float ymin, float dxdy, int xres,
     }
     size_t k = 0;
     for (auto& lbody : c->S.BodyList) for (auto& latt : lbody->alist) latt.gsum = gsum[k++];
+}
+/* XPressure(S, ...).evaluate() (libvvhd/src/XPressure.cpp:32-97), the pressure raster of vvplot; like XVorticity it works on a
+ * copy of the Space that shares the TBody objects: vortex_shed increments TAtt::gsum and process_vort_list adds to
+ * TAtt::fric through them; both are restored here. ref_frame: 's' 'o' 'f' 'b' (:38-52). */
+void vvr_pressure_raster(void* h, float xmin, float ymin, float dxdy, int xres, int yres, int ref_frame, float* out) {
+    Ctx* c = (Ctx*)h;
+    std::vector<double> gsum, fric;
+    for (auto& lbody : c->S.BodyList) for (auto& latt : lbody->alist) { gsum.push_back(latt.gsum); fric.push_back(latt.fric); }
+    {
+        XPressure f(c->S, xmin, ymin, dxdy, xres, yres);
+        f.eps_mult = 1;
+        f.ref_frame = (char)ref_frame;
+        f.evaluate();
+        for (int yj = 0; yj < yres; yj++)
+            for (int xi = 0; xi < xres; xi++) out[yj * xres + xi] = f.at(xi, yj);
+    }
+    size_t k = 0;
+    for (auto& lbody : c->S.BodyList) for (auto& latt : lbody->alist) { latt.gsum = gsum[k]; latt.fric = fric[k]; k++; }
 }
 void vvr_diffusive(void* h, int vort, int heat) {
     Ctx* c = (Ctx*)h;

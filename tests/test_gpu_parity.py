@@ -434,6 +434,60 @@ def test_vorticity_raster(ctx, port, with_body):
     assert relerr(dbl, want) <= VTOL, relerr(dbl, want)
 
 
+@pytest.mark.parametrize("case", ["cloud", "moving_cylinder_b", "moving_cylinder_s"])
+def test_pressure_raster(ctx, port, case):
+    """SURVEY 8(f) row 4: XPressure::evaluate (XPressure.cpp:32-146). The oracle's raster is pinned to the compiled
+    reference (tests/test_oracle_port.py); here 1e-10 norm-wise on the double values (the direct sum over all vortices
+    runs in another order) and the same zeros inside the body; the resident list comes back untouched."""
+    from vvflow_b200 import vvhd
+    if case == "cloud":
+        bodies, xyg, grid, frame = [], cases.cloud(20000, "uniform", "mixed", seed=91), (-0.5, -0.5, 0.02, 100, 100), "o"
+    else:
+        bodies = [cases.cylinder(0.5, 350)]
+        rng = np.random.default_rng(92)
+        bodies[0].g[:] = rng.uniform(-1, 1, 350) * 1e-3          # attached vortices to shed
+        bodies[0].gsum[:] = rng.uniform(-1, 1, 350) * 1e-3
+        bodies[0].speed_slae = np.array([0.1, -0.05, 0.2])       # the first addend of :115-121 is live
+        xyg = cases.around_cylinder(12000, sign="mixed", seed=93)
+        grid, frame = (-1.0, -1.0, 0.02, 100, 100), case[-1]
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.BodyList = bodies
+    S.re, S.dt, S.inf_vx, S.inf_vy = 600.0, 0.05, 1.0, 0.25
+    f = vvhd.XPressure(S, *grid)
+    with pytest.raises(ValueError):
+        f.evaluate()                                   # eps_mult must be positive
+    f.eps_mult = 1.0
+    f.ref_frame = "x"
+    with pytest.raises(ValueError):
+        f.evaluate()                                   # bad ref_frame
+    f.ref_frame = frame
+    f.evaluate()
+    assert same(ctx.get_particles()[:, :3], xyg)       # the Space's list is back on the device, in its own order
+    shed = []
+    for b in bodies:
+        keep = (np.abs(b.g) >= 1e-10) & (b.slip == 0)
+        shed.append(np.stack([b.corner[keep, 0] - b.dl[keep, 1] * 1e-4, b.corner[keep, 1] + b.dl[keep, 0] * 1e-4, b.g[keep]], 1))
+    pb = cases.port_bodies(port, bodies)
+    if pb is not None:
+        pb.a["gsum"][:] = np.concatenate([b.gsum + b.g for b in bodies])
+    P = port.Port(xyg=np.concatenate([xyg] + shed), bodies=pb)
+    ref = {"s": None, "o": (0.0, 0.0), "b": (0.1, -0.05)}[frame]
+    want = P.pressure_raster(*[np.float32(v) for v in grid[:3]], grid[3], grid[4], S.average_segment_length(), 600.0, 0.05, 1.0, 0.25,
+                             ref_speed=ref)
+    got = f.map
+    assert got.shape == want.shape == (100, 100) and np.isfinite(want).all() and np.abs(want).max() > 0
+    assert np.array_equal(got == 0, want.astype(np.float32) == 0) and (not bodies or (want == 0).sum() > 100)
+    assert relerr(got.astype(np.float64), want) <= 2e-7                            # float32 map
+    # the double values behind the map
+    rec = np.concatenate([xyg] + shed)
+    S.ctx.set_particles(np.concatenate([rec, np.zeros((rec.shape[0], 3))], 1))
+    dbl = ctx.pressure_raster(float(np.float32(grid[0])), float(np.float32(grid[1])), float(np.float32(grid[2])), grid[3], grid[4],
+                              S.average_segment_length(), 600.0, 0.05, 1.0, 0.25,
+                              np.concatenate([b.gsum + b.g for b in bodies]) if bodies else None, None, ref)
+    assert relerr(dbl, want) <= VTOL, relerr(dbl, want)
+
+
 def test_awkward_small_inputs(ctx, port):
     """the sweep of tests/test_oracle_port.py::test_port_matches_reference_on_random_small_inputs on the CUDA path:
     one or two particles, exact duplicates, points on a line, a lattice (ties in every comparison), zero

@@ -266,6 +266,46 @@ def test_vorticity_raster_matches_reference(port, ref):
     assert same(got.astype(np.float32), want), np.abs(got.astype(np.float32) - want).max()
 
 
+def test_pressure_raster_matches_reference(port, ref):
+    """XPressure::evaluate (XPressure.cpp:32-146, SURVEY 8(f) row 4): the port's raster against the compiled reference's
+    (a float map): body-free cloud, and a cylinder whose segments carry circulation and gsum and which moves
+    (speed_slae != 0: the first addend of :115-121 is live), in the 's' and the 'b' frame of reference. The direct sum
+    over all vortices runs in the tree's order on both sides; what is compared is the float the reference stores."""
+    def close(got, want):
+        g = got.astype(np.float32)
+        scale = max(float(np.abs(want).max()), 1e-30)
+        return float(np.abs(g - want).max()) / scale <= 1e-6   # a float ulp of the field maximum (cancellation in the sum)
+    # (a dense cloud: with maxNodeSize = 0.1 an isolated tail particle of a Gaussian cloud has no neighbour in its near
+    # leaves, gets eps = DBL_MIN and a NaN diffusive velocity, and the reference's direct sum turns the WHOLE map into NaN)
+    xyg = cases.cloud(3000, "uniform", "mixed", seed=81)
+    r = ref.Ref(re=600, dt=0.05, inf_vx=1.0, inf_vy=0.25)
+    r.set_list(xyg)
+    want = r.pressure_raster(-0.5, -0.5, 0.05, 40, 40, "o")
+    got = port.Port(xyg=xyg).pressure_raster(-0.5, -0.5, 0.05, 40, 40, 0.0, 600.0, 0.05, 1.0, 0.25, ref_speed=(0.0, 0.0))
+    assert np.isfinite(want).all() and np.abs(want).max() > 0
+    assert close(got, want), np.abs(got.astype(np.float32) - want).max()
+    # moving cylinder with circulation on its segments
+    xyg = cases.around_cylinder(4000, sign="mixed", seed=82)
+    for frame in ("s", "b"):
+        r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
+        r.add_cylinder(0.5, 350)
+        rng = np.random.default_rng(83)
+        r.set_segments(g=rng.uniform(-1, 1, 350) * 1e-3, gsum=rng.uniform(-1, 1, 350) * 1e-3)
+        r.body_set_speed_slae(0, np.array([0.1, -0.05, 0.2]))
+        r.set_list(xyg)
+        seg = r.segments()
+        want = r.pressure_raster(-1.0, -1.0, 0.05, 40, 40, frame)
+        assert same(r.segments()[:, 7:9], seg[:, 7:9])                  # the shim restores gsum and fric
+        pb = port.Bodies.from_ref(r)
+        pb.a["gsum"][:] = seg[:, 7] + seg[:, 6]                         # vortex_shed: gsum += g (MFlowmove.cpp:227)
+        dl = float(np.hypot(seg[:, 4], seg[:, 5]).sum() / (350 - 1))
+        P = port.Port(xyg=np.concatenate([xyg, shed_vortices(seg)]), bodies=pb)
+        got = P.pressure_raster(-1.0, -1.0, 0.05, 40, 40, dl, 600.0, 0.05, 1.0, 0.0,
+                                ref_speed=None if frame == "s" else (0.1, -0.05))
+        assert (want == 0).sum() > 50 and np.isfinite(want).all() and np.abs(want).max() > 0
+        assert close(got, want), (frame, np.abs(got.astype(np.float32) - want).max(), np.abs(want).max())
+
+
 def _pipeline_pair(port, ref, xyg, with_body, merge=True):
     r = ref.Ref(re=600, dt=0.05, inf_vx=1.0)
     if with_body:

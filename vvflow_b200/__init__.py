@@ -6,4 +6,4 @@ host/ (the C++ adapter classes for the vvflow binary). See DESIGN.md.
 """
 from . import capi  # noqa: F401
 from .vvhd import (MConvectiveFast, MDiffusiveFast, MEpsilonFast, MFlowmove, Space, TBody,  # noqa: F401
-                   TSortedTree)
+                   TSortedTree, XPressure, XVorticity)

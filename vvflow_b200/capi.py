@@ -18,7 +18,7 @@ SYMBOLS = [
     "vvgpu_get_permutation", "vvgpu_set_bodies",
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
-    "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
+    "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_pressure_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
     "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner", "vvgpu_shard_block",
     "vvgpu_set_particles_slice", "vvgpu_particle_arrays_dev", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_host_syncs", "vvgpu_fp64_peak",
@@ -78,6 +78,8 @@ def load():
         "vvgpu_eps2h_h2_at": [vp, dp, sz, dp],
         "vvgpu_node_influence": [vp, dp],
         "vvgpu_vorticity_raster": [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double, C.c_double, dp],
+        "vvgpu_pressure_raster": [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, dp, sz, dp, C.c_int, C.c_double, C.c_double, dp],
         "vvgpu_diffusive": [vp, C.c_double, dp],
         "vvgpu_move_and_clean": [vp, C.c_double, C.c_double, C.c_int, dp, dp, dp, C.POINTER(sz)],
         "vvgpu_comm_unique_id": [vp, sz],
@@ -279,6 +281,17 @@ class Context:
         """XVorticity::evaluate on the resident (post-shed) list: (yres, xres) float64"""
         out = np.zeros((yres, xres))
         self._ck(self.L.vvgpu_vorticity_raster(self.h, xmin, ymin, dxdy, xres, yres, eps_mult, dl, _p(out)))
+        return out
+
+    def pressure_raster(self, xmin, ymin, dxdy, xres, yres, dl, re, dt, inf_vx, inf_vy, gsum, sinks=None, ref_speed=None):
+        """XPressure::evaluate on the resident (post-shed) list: (yres, xres) float64; ref_speed None = ref_frame 's'"""
+        out = np.zeros((yres, xres))
+        s = None if sinks is None or len(sinks) == 0 else np.ascontiguousarray(sinks, dtype=np.float64).reshape(-1, 3)
+        g = None if gsum is None or len(gsum) == 0 else np.ascontiguousarray(gsum, dtype=np.float64)
+        rs = (0.0, 0.0) if ref_speed is None else ref_speed
+        self._ck(self.L.vvgpu_pressure_raster(self.h, xmin, ymin, dxdy, xres, yres, dl, re, dt, inf_vx, inf_vy, _p(s),
+                                              0 if s is None else s.shape[0], _p(g), 0 if ref_speed is None else 1,
+                                              rs[0], rs[1], _p(out)))
         return out
 
     def diffusive(self, re, want_fric=True):

@@ -1273,6 +1273,88 @@ int vvgpu_vorticity_raster(vvgpu_ctx* c, float xmin, float ymin, float dxdy, int
     return rc;
 }
 
+int vvgpu_pressure_raster(vvgpu_ctx* c, float xmin, float ymin, float dxdy, int xres, int yres, double dl, double re, double dt,
+                          double inf_vx, double inf_vy, const double* sinks_xyg, size_t nsink, const double* gsum_nseg,
+                          int use_ref_speed, double ref_vx, double ref_vy, double* out) {
+    if (!c || xres <= 0 || yres <= 0 || !out || (c->nseg && !gsum_nseg) || (nsink && !sinks_xyg))
+        return fail(c, VVGPU_EINVAL, "pressure_raster: bad argument");
+    if (c->built) return fail(c, VVGPU_ESTATE, "pressure_raster builds its own tree: destroy the step's tree first");
+    if (c->comm.nranks > 1) return fail(c, VVGPU_ESTATE, "pressure_raster: single-rank contexts only");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = c->n, npts = (size_t)xres * yres;
+    bool ok = true;
+    // the reference works on a COPY of the Space (:20-30): the resident list must come back as it was
+    PSet& P0 = c->ps[c->cur];
+    if (n && !c->ps_backup.ensure(n)) return fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+    auto copy7 = [&](PSet& dst, PSet& src) {
+        if (!n) return;
+        Buf* d[6] = {&dst.x, &dst.y, &dst.g, &dst.vx, &dst.vy, &dst.ie};
+        Buf* s7[6] = {&src.x, &src.y, &src.g, &src.vx, &src.vy, &src.ie};
+        for (int k = 0; k < 6; k++) cudaMemcpyAsync(d[k]->p, s7[k]->p, n * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dst.orig.p, src.orig.p, n * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    };
+    copy7(c->ps_backup, P0);
+    // (process_all_lists ADDS to the v the records carry, MConvectiveFast.cpp:79: the caller's v is kept, as in the reference)
+    // tree(&S, 8, dl*20, 0.1), eps.CalcEpsilonFast(false), process_all_lists, process_vort_list (:27, :61-64)
+    int rc = vvgpu_tree_build(c, 8, dl * 20, 0.1, 3u);
+    if (!rc) rc = vvgpu_epsilon(c, 0, nullptr);
+    if (!rc) rc = vvgpu_convective(c, inf_vx, inf_vy, dt, sinks_xyg, nsink);
+    if (!rc) rc = vvgpu_diffusive(c, re, nullptr);
+    if (!rc) {
+        double* dxy = c->pt_xy.get<double>(2 * npts, &ok);
+        double* dvel = c->pt_out.get<double>(2 * npts, &ok);
+        double* dacc = c->pt_v.get<double>(2 * npts, &ok);
+        double* dres = dacc + npts;
+        double* dgs = c->d_gsum.get<double>(std::max(c->nseg, 1), &ok);
+        double* ds = c->d_sinks.get<double>(3 * nsink, &ok);
+        int* derr = c->d_err.get<int>(4, &ok);
+        if (!ok) rc = fail(c, VVGPU_ENOMEM, "cudaMalloc failed");
+        if (!rc) {
+            PSet& PP = c->ps[c->cur];
+            cudaMemsetAsync(derr, 0, 4 * sizeof(int), st);
+            cudaMemsetAsync(dacc, 0, npts * sizeof(double), st);
+            if (c->nseg) cudaMemcpyAsync(dgs, gsum_nseg, c->nseg * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (nsink) cudaMemcpyAsync(ds, sinks_xyg, 3 * nsink * sizeof(double), cudaMemcpyHostToDevice, st);
+            k_raster_points<<<cdiv(npts, 256), 256, 0, st>>>(xmin, ymin, dxdy, xres, yres, dxy);
+            BodyFull BF{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                        c->s_dlx.as<double>(), c->s_dly.as<double>(), c->s_g.as<double>(), c->s_ie.as<double>(),
+                        c->s_slip.as<int>(), c->b_first.as<int>(), c->b_prop.as<double>()};
+            PointArgs A;
+            A.T = c->T(); A.P = PP.view(); A.npts = (int)npts; A.xy = dxy; A.out = dvel;
+            A.farc = c->farc; A.inf_vx = inf_vx; A.inf_vy = inf_vy; A.eps2_div_srcg = dt * k1_Pi;
+            A.sinks = ds; A.nsink = (int)nsink; A.B = BF;
+            A.body_flow = (c->any_body_flow && c->nbody) ? 1 : 0;
+            A.err = derr;
+            k_velocity_at<<<cdiv(npts, kPtWarps), kPtWarps * 32, 0, st>>>(A);
+            if (n) {
+                dim3 grid(cdiv(npts, kPrPoints), cdiv(n, kPrChunk));
+                k_pressure_vortices<<<grid, kPrPoints, 0, st>>>((int)n, PP.view(), (long long)npts, dxy, dacc);
+            }
+            PressureArgs R;
+            R.B = BF;
+            R.G = BodyGeom{c->nseg, c->nbody, c->s_rx.as<double>(), c->s_ry.as<double>(), c->s_cx.as<double>(), c->s_cy.as<double>(),
+                           c->b_first.as<int>(), c->b_prop.as<double>()};
+            R.gsum = dgs; R.npts = (long long)npts; R.xy = dxy; R.vel = dvel; R.acc = dacc;
+            R.dt = dt; R.inf_vx = inf_vx; R.inf_vy = inf_vy; R.ref_vx = ref_vx; R.ref_vy = ref_vy; R.use_ref = use_ref_speed;
+            R.out = dres;
+            k_pressure_finish<<<cdiv(npts, 128), 128, 0, st>>>(R);
+            c->launches += 4;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(c, VVGPU_ECUDA, "pressure_raster: launch failed");
+            cudaMemcpyAsync(out, dres, npts * sizeof(double), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(c->h_pinned + 64, derr, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(c, VVGPU_ECUDA, "pressure_raster: kernel failed");
+            if (!rc && (c->h_pinned[64] & 2)) rc = fail(c, VVGPU_ELIMIT, "pressure_raster: traversal stack overflow");
+        }
+    }
+    // destroy the raster's tree and put the resident list back
+    c->built = false; c->lists_ready = false; c->v_dirty = false;
+    c->nnodes = c->nleaves = c->ngroups = 0;
+    copy7(c->ps[c->cur], c->ps_backup);
+    if (cudaStreamSynchronize(st) != cudaSuccess && !rc) rc = fail(c, VVGPU_ECUDA, "pressure_raster: restore failed");
+    return rc;
+}
+
 int vvgpu_diffusive(vvgpu_ctx* c, double re, double* fric_out) {
     if (!c) return VVGPU_EINVAL;
     if (!c->built || !c->lists_ready) return fail(c, VVGPU_ESTATE, "tree is not built");

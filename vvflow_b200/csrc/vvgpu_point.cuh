@@ -445,4 +445,86 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_vorticity_at(RasterArgs A) {
     }
 }
 
+// SURVEY §8(f) row 4 — XPressure::evaluate / ::pressure (libvvhd/src/XPressure.cpp:32-146), the pressure raster of vvplot, after
+// one ordinary velocity pass on the tree the host built for it (far criteria 8, minNodeSize 20 dl, maxNodeSize 0.1, :27):
+//   2pi Cp(p) = sum over segments [(rotl(K) g_s + K q_s) . Vs] - sum over segments (dl/dt . rotl(K)) (running sum of gsum)
+//             + sum over ALL vortices (v . rotl(K(r, p))) g,       K(o, p) = (p - o) / |p - o|^2
+//   Cp = 2pi Cp / 2pi + (|inf_speed|^2 - |velocity(p)|^2) / 2  [+ |velocity(p) - ref_speed|^2 / 2 unless ref_frame 's'].
+// The vortex sum is a direct sum over the whole list per raster point (the reference's is, too): k_pressure_vortices
+// tiles points x particle chunks and adds the partial sums atomically; k_pressure_finish adds the body terms (serial
+// per point, like the reference's loops) and the velocity terms, and zeroes the points inside a body.
+__global__ void k_raster_points(float xmin, float ymin, float dxdy, int xres, int yres, double* xy) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)xres * yres) return;
+    const int xi = (int)(q % xres), yj = (int)(q / xres);
+    xy[2 * q] = VV_ADD((double)xmin, VV_MUL((double)dxdy, (double)xi));       // TVec(xmin, ymin) + dxdy * TVec(xi, yj), :88
+    xy[2 * q + 1] = VV_ADD((double)ymin, VV_MUL((double)dxdy, (double)yj));
+}
+constexpr int kPrPoints = 128;     // raster points per CTA (one per thread)
+constexpr int kPrChunk = 8192;     // particles per CTA
+__global__ void __launch_bounds__(kPrPoints) k_pressure_vortices(int n, Particles P, long long npts, const double* __restrict__ xy,
+                                                                 double* acc) {
+    __shared__ double4 tile[256];   // x, y, vx g, vy g
+    const long long q = (long long)blockIdx.x * kPrPoints + threadIdx.x;
+    const double px = (q < npts) ? xy[2 * q] : 0., py = (q < npts) ? xy[2 * q + 1] : 0.;
+    const int j0 = blockIdx.y * kPrChunk, j1 = min(n, j0 + kPrChunk);
+    double s = 0;
+    for (int jb = j0; jb < j1; jb += 256) {
+        for (int k = threadIdx.x; k < 256; k += kPrPoints) {
+            const int j = jb + k;
+            double4 t = make_double4(0., 0., 0., 0.);
+            if (j < j1) { const double g = P.g[j]; t = make_double4(P.x[j], P.y[j], P.vx[j] * g, P.vy[j] * g); }
+            tile[k] = t;
+        }
+        __syncthreads();
+        const int m = min(256, j1 - jb);
+        for (int k = 0; k < m; k++) {
+            const double4 t = tile[k];
+            const double drx = px - t.x, dry = py - t.y;
+            const double r2 = drx * drx + dry * dry;
+            s += (t.w * drx - t.z * dry) / r2;      // (v . rotl(K)) g = g (-vx K.y + vy K.x)
+        }
+        __syncthreads();
+    }
+    if (q < npts) atomicAdd(&acc[q], s);
+}
+struct PressureArgs {
+    BodyFull B;
+    BodyGeom G;
+    const double* gsum;        // per segment, after vortex_shed
+    long long npts;
+    const double *xy, *vel, *acc;
+    double dt, inf_vx, inf_vy, ref_vx, ref_vy;
+    int use_ref;
+    double* out;
+};
+__global__ void k_pressure_finish(PressureArgs A) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.npts) return;
+    const double px = A.xy[2 * q], py = A.xy[2 * q + 1];
+    for (int ib = 0; ib < A.G.nbody; ib++)
+        if (point_invalid(A.G, ib, px, py) >= 0) { A.out[q] = 0; return; }   // Space::point_is_in_body, :89
+    double cp = A.acc[q];
+    for (int ib = 0; ib < A.B.nbody; ib++) {
+        const double* bp = A.B.bprop + 16 * ib;
+        const double ax = bp[0], ay = bp[1], sx = bp[9], sy = bp[10], so = bp[11];
+        double gtmp = 0;
+        for (int s = A.B.bfirst[ib]; s < A.B.bfirst[ib + 1]; s++) {
+            const double ux = A.B.rx[s] - ax, uy = A.B.ry[s] - ay;
+            const double vsx = sx - so * uy, vsy = sy + so * ux;
+            const double dlx = A.B.dlx[s], dly = A.B.dly[s];
+            const double g = -(vsx * dlx + vsy * dly), qq = -(-vsy * dlx + vsx * dly);
+            const double drx = px - A.B.rx[s], dry = py - A.B.ry[s], r2 = drx * drx + dry * dry;
+            const double kx = drx / r2, ky = dry / r2;
+            cp += (-ky * g + kx * qq) * vsx + (kx * g + ky * qq) * vsy;          // :115-121
+            gtmp += A.gsum[s];
+            cp -= (dlx / A.dt * (-ky) + dly / A.dt * kx) * gtmp;                // :124-130
+        }
+    }
+    const double vx = A.vel[2 * q], vy = A.vel[2 * q + 1];
+    double res = k1_2Pi * cp + 0.5 * ((A.inf_vx * A.inf_vx + A.inf_vy * A.inf_vy) - (vx * vx + vy * vy));
+    if (A.use_ref) res += 0.5 * ((vx - A.ref_vx) * (vx - A.ref_vx) + (vy - A.ref_vy) * (vy - A.ref_vy));
+    A.out[q] = res;
+}
+
 }  // namespace vv

@@ -340,3 +340,58 @@ class XVorticity:
 
     def at(self, xi, yj):
         return self.map[yj, xi]
+
+
+class XPressure:
+    """XPressure (libvvhd/headers/XPressure.hpp, src/XPressure.cpp): the pressure raster of vvplot. Like the reference it
+    works on a copy of the Space: the attached vortices are shed into the copy (gsum += g, MFlowmove.cpp:217-235), a tree
+    with (8, 20 dl, 0.1) is built, one velocity pass runs (epsilon without merging, convective, diffusive) and the
+    pressure is summed per raster point; the Space itself is left untouched."""
+
+    def __init__(self, S, xmin, ymin, dxdy, xres, yres):
+        self.S = S
+        self.xmin, self.ymin, self.dxdy = np.float32(xmin), np.float32(ymin), np.float32(dxdy)   # XField keeps floats
+        self.xres, self.yres = int(xres), int(yres)
+        self.eps_mult = 0.0
+        self.ref_frame = "s"
+        self.map = None
+
+    def evaluate(self, remove_eps=1e-10):
+        if self.eps_mult <= 0:
+            raise ValueError("XPressure(): eps_mult must be positive")     # XPressure.cpp:34-35
+        S = self.S
+        if self.ref_frame == "s":
+            ref = None
+        elif self.ref_frame == "o":
+            ref = (0.0, 0.0)
+        elif self.ref_frame == "f":
+            ref = (S.inf_vx, S.inf_vy)
+        elif self.ref_frame == "b":
+            ref = (float(S.BodyList[0].speed_slae[0]), float(S.BodyList[0].speed_slae[1]))
+        else:
+            raise ValueError("XPressure(): bad ref_frame")                 # :50-52
+        if self.map is not None:
+            return
+        own = S.VortexList.copy()                  # pulls the device copy if it is newer
+        shed, gsum = [], []
+        for b in S.BodyList:                       # vortex_shed on the copy
+            keep = (np.abs(b.g) >= remove_eps) & (b.slip == 0)
+            rec = np.zeros((int(keep.sum()), 6))
+            rec[:, 0] = b.corner[keep, 0] - b.dl[keep, 1] * 1e-4   # corner + rotl(dl) * 1e-4
+            rec[:, 1] = b.corner[keep, 1] + b.dl[keep, 0] * 1e-4
+            rec[:, 2] = b.g[keep]
+            shed.append(rec)
+            gsum.append(b.gsum + b.g)              # gsum is incremented for slip segments too (:223-227)
+        S.ctx.set_particles(np.concatenate([own] + shed) if shed else own)
+        segs, bodies = S._pack_bodies()
+        S.ctx.set_bodies(segs, bodies)
+        m = S.ctx.pressure_raster(float(self.xmin), float(self.ymin), float(self.dxdy), self.xres, self.yres,
+                                  S.average_segment_length(), S.re, S.dt, S.inf_vx, S.inf_vy,
+                                  np.concatenate(gsum) if gsum else None, S.SourceList if len(S.SourceList) else None, ref)
+        S.ctx.set_particles(own)                   # the Space's own list goes back to the device
+        S._dev_newer = False
+        self.map = m.astype(np.float32)
+
+    def at(self, xi, yj):
+        return self.map[yj, xi]
+

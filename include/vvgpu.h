@@ -176,6 +176,9 @@ int vvgpu_comm_unique_id(void* id128, size_t cap);
 int vvgpu_comm_init(vvgpu_ctx* ctx, int rank, int nranks, const void* id128);
 int vvgpu_group_create(const int* devices, int n, vvgpu_ctx** ctxs_out);
 int vvgpu_comm_info(vvgpu_ctx* ctx, int* rank, int* nranks, int* kind /* 0 none, 1 NCCL, 2 in-process */);
+/* collective: complete the exchanges that are done lazily (v of the other ranks' targets), e.g. before ONE rank reads the
+ * particle list while the tree is still built; a no-op when nothing is pending */
+int vvgpu_sync_ranks(vvgpu_ctx* ctx);
 /* rank that owns leaf group `group` (groups of 32 consecutive leaves, dealt round-robin in pieces of vvgpu_shard_block()
  * consecutive groups); no device needed */
 int vvgpu_shard_owner(int group, int nranks);

@@ -252,7 +252,7 @@ int main(int argc, char** argv) {
             printf("resident: %d steps, N=%zu, force_hydro relerr vs the reference run %.3e, final positions max diff %.3e, "
                    "steps/s device-resident %.2f vs reference classes %.2f\n", nsteps, SA.VortexList.size(), worst, pe,
                    nsteps / t_gpu, nsteps / t_ref);
-            printf("%s worst=%.3e\n", (worst <= 1e-8 && pe <= 1e-8) ? "OK" : "FAIL", fmax(worst, pe));
+            printf("%s worst=%.3e ranks=%zu\n", (worst <= 1e-8 && pe <= 1e-8) ? "OK" : "FAIL", fmax(worst, pe), vvgpu::Device::of(&SB)->all.size());
             return (worst <= 1e-8 && pe <= 1e-8) ? 0 : 1;
         }
         // lockstep
@@ -366,7 +366,7 @@ int main(int argc, char** argv) {
                    "mirror identical on %zu leaves\n", pts.size(), ve / vs, nb.size(), ne / ns, nleaves_checked);
             worst = fmax(worst, fmax(ve / vs, ne / ns));
         }
-        printf("%s worst=%.3e\n", worst <= 1e-10 ? "OK" : "FAIL", worst);
+        printf("%s worst=%.3e ranks=%zu\n", worst <= 1e-10 ? "OK" : "FAIL", worst, vvgpu::Device::of(&SB)->all.size());
         return worst <= 1e-10 ? 0 : 1;
     } catch (const std::exception& e) {
         printf("EXCEPTION %s\n", e.what());

@@ -90,3 +90,17 @@ def test_resident_loop_without_cpu_particle_tree():
         for k in (1, 2, 3):
             if want[k] is not None:
                 assert got[k] == want[k], (got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,steps", [("lockstep", 25), ("resident", 20)])
+def test_two_ranks_from_one_process(mode, steps):
+    """SURVEY 8(e) from inside the vvflow process: VVGPU_DEVICES lists one device per rank (here device 0 twice, so it
+    runs on one GPU), the adapter drives every rank's context from its own host thread and the library's exchanges meet
+    there. The same checks as with one rank: bit-exact order / merge / removal decisions, 1e-10 on every float."""
+    _need_bin()
+    env = dict(os.environ, VVGPU_DEVICES="0,0")
+    p = subprocess.run([BIN, mode, str(steps)], capture_output=True, text=True, timeout=900, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    last = p.stdout.strip().splitlines()[-1]
+    assert last.startswith("OK") and last.endswith("ranks=2"), p.stdout[-500:]

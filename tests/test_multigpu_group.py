@@ -92,6 +92,11 @@ def test_group_few_groups():
     """fewer pieces than ranks: some ranks own nothing"""
     _run_case(cases.cloud(300, "gauss", "mixed", seed=5), [], 4, nsteps=1)
     _run_case(np.zeros((0, 3)), [], 2, nsteps=1)
+    # ... also with walls (the per-leaf wall passes run over the rank's work units: none), and a body with no vortices
+    # at all, which is step 0 of every vvflow run
+    body = cases.cylinder(0.5, 350)
+    _run_case(cases.around_cylinder(200, sign="mixed", seed=9), [body], 4, nsteps=2)
+    _run_case(np.zeros((0, 3)), [body], 2, nsteps=1)
 
 
 def test_group_slice_upload():

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vvgpu_tree_build", "vvgpu_tree_destroy", "vvgpu_tree_counts", "vvgpu_tree_export", "vvgpu_tree_lists",
     "vvgpu_tree_leaf_segments", "vvgpu_count_interactions",
     "vvgpu_epsilon", "vvgpu_merge_rounds", "vvgpu_convective", "vvgpu_velocity_at", "vvgpu_eps2h_h2_at", "vvgpu_node_influence", "vvgpu_vorticity_raster", "vvgpu_pressure_raster", "vvgpu_diffusive", "vvgpu_move_and_clean",
-    "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_shard_owner", "vvgpu_shard_block",
+    "vvgpu_comm_unique_id", "vvgpu_comm_init", "vvgpu_group_create", "vvgpu_comm_info", "vvgpu_sync_ranks", "vvgpu_shard_owner", "vvgpu_shard_block",
     "vvgpu_set_particles_slice", "vvgpu_particle_arrays_dev", "vvgpu_stream",
     "vvgpu_synchronize", "vvgpu_phase_times", "vvgpu_host_syncs", "vvgpu_fp64_peak",
 ]
@@ -86,6 +86,7 @@ def load():
         "vvgpu_comm_init": [vp, C.c_int, C.c_int, vp],
         "vvgpu_group_create": [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)],
         "vvgpu_comm_info": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "vvgpu_sync_ranks": [vp],
         "vvgpu_shard_owner": [C.c_int, C.c_int],
         "vvgpu_shard_block": [],
         "vvgpu_set_particles_slice": [vp, C.c_int, dp, sz, sz, sz],

@@ -176,6 +176,10 @@ namespace {
 
 int fail(vvgpu_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
+    // a failure of ONE rank of an in-process group (device error, out of memory, capacity) must not leave the others
+    // waiting for it in the next exchange: release them, every later exchange of the group fails
+    if (c && c->comm.kind == Comm::LOCAL && c->comm.grp && (code == VVGPU_ECUDA || code == VVGPU_ENOMEM || code == VVGPU_ELIMIT))
+        c->comm.grp->abort();
     return code;
 }
 #define CK(call)                                                                                     \
@@ -590,8 +594,10 @@ int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* lat
         const int* sp = c->t_segperm[c->segcur].as<int>();
         Units U = c->Uv();
         k_wall_init<<<cdiv(nl, 256), 256, 0, st>>>(nl, bd, bk); CKLAUNCH();
-        k_wall_pass<1><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
-        k_wall_pass<2><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
+        if (c->nunits > 0) {   // a rank of a small tree may own no leaf group at all
+            k_wall_pass<1><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
+            k_wall_pass<2><<<c->nunits, 256, 0, st>>>(c->Lv(), c->Gv(), U, c->nunits, sp, B, bd, bk); CKLAUNCH();
+        }
     }
     k_wall_finish<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, c->t_segperm[c->segcur].as<int>(), B, merge, bd, bk, lcrit, lrestr, latt); CKLAUNCH();
     return 0;
@@ -1545,6 +1551,13 @@ int vvgpu_particle_arrays_dev(vvgpu_ctx* c, int list, double** arrays6, size_t* 
     arrays6[0] = p.x; arrays6[1] = p.y; arrays6[2] = p.g; arrays6[3] = p.vx; arrays6[4] = p.vy; arrays6[5] = p.ie;
     if (n) *n = c->n;
     return 0;
+}
+// pending lazy exchanges (v of the other ranks' targets); collective, a no-op when nothing is pending
+int vvgpu_sync_ranks(vvgpu_ctx* c) {
+    if (!c) return VVGPU_EINVAL;
+    if (!(c->built && c->v_dirty)) return 0;
+    CK(cudaSetDevice(c->device));
+    return sync_v(c);
 }
 int vvgpu_stream(vvgpu_ctx* c, void** s) {
     if (!c || !s) return VVGPU_EINVAL;

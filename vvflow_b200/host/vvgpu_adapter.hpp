@@ -39,29 +39,59 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace vvgpu {
 
 static_assert(sizeof(TObj) == sizeof(vvgpu_obj), "TObj must be the 48-byte record of TObj.hpp:10-16");
 
-// One device context per Space, shared by the five adapter objects of a step loop.
+// One device context per Space, shared by the five adapter objects of a step loop — or, with VVGPU_DEVICES="0,1,2,3",
+// one context per listed device (SURVEY 8(e) from inside the vvflow process: vvgpu_group_create; entries may repeat,
+// which puts several ranks on one device). Every rank holds the whole state and makes the same calls: `each` runs a
+// call on all ranks, one host thread per rank (the library's exchanges meet there); replicated results are read from
+// rank 0.
 class Device {
     public:
         explicit Device(int device_index = 0): ctx(nullptr), index(device_index) {
-            int rc = vvgpu_create(device_index, &ctx);
+            const char* env = getenv("VVGPU_DEVICES");
+            std::vector<int> devs;
+            if (env) for (const char* p = env; *p; ) { devs.push_back(atoi(p)); while (*p && *p != ',') p++; if (*p == ',') p++; }
+            if (devs.size() > 1) {
+                all.resize(devs.size(), nullptr);
+                int rc = vvgpu_group_create(devs.data(), (int)devs.size(), all.data());
+                if (rc) throw std::runtime_error(std::string("vvgpu_group_create: ") + vvgpu_strerror(rc) +
+                                                 " (libvvgpu has no CPU fallback; CUDA devices are required)");
+                ctx = all[0];
+                return;
+            }
+            int rc = vvgpu_create(devs.empty() ? device_index : devs[0], &ctx);
             if (rc) throw std::runtime_error(std::string("vvgpu_create: ") + vvgpu_strerror(rc) +
                                              " (libvvgpu has no CPU fallback; a CUDA device is required)");
+            all.assign(1, ctx);
         }
-        ~Device() { vvgpu_destroy(ctx); }
+        ~Device() { for (vvgpu_ctx* c: all) vvgpu_destroy(c); }
         Device(const Device&) = delete;
         Device& operator=(const Device&) = delete;
 
         void check(int rc, const char* what) const {
             if (rc) throw std::runtime_error(std::string(what) + ": " + vvgpu_strerror(rc) + ": " + vvgpu_last_error(ctx));
         }
+        // f(ctx of rank r) on every rank; rank 0's return code is checked first, then the others'
+        template <class F>
+        void each(F f, const char* what) const {
+            if (all.size() == 1) { check(f(ctx), what); return; }
+            std::vector<int> rc(all.size(), 0);
+            std::vector<std::thread> th;
+            for (size_t r = 1; r < all.size(); r++) th.emplace_back([&, r] { rc[r] = f(all[r]); });
+            rc[0] = f(all[0]);
+            for (auto& t: th) t.join();
+            for (size_t r = 0; r < all.size(); r++)
+                if (rc[r]) throw std::runtime_error(std::string(what) + " (rank " + std::to_string(r) + "): " + vvgpu_strerror(rc[r]) +
+                                                    ": " + vvgpu_last_error(all[r]));
+        }
         static std::shared_ptr<Device>& of(Space* S) {
-            // one context per Space, created on first use (device from VVGPU_DEVICE, default 0)
+            // one Device per Space, created on first use (device from VVGPU_DEVICE, default 0; VVGPU_DEVICES for several)
             static std::vector<std::pair<Space*, std::shared_ptr<Device>>> table;
             for (auto& e: table) if (e.first == S) return e.second;
             const char* env = getenv("VVGPU_DEVICE");
@@ -69,7 +99,8 @@ class Device {
             return table.back().second;
         }
 
-        vvgpu_ctx* ctx;
+        vvgpu_ctx* ctx;                 // rank 0
+        std::vector<vvgpu_ctx*> all;    // every rank
         int index;
         bool dev_newer = false;   // the device holds a newer VortexList than the host
         bool resident = false;    // the list LIVES on the device: the host copy is only materialised on request
@@ -104,6 +135,7 @@ inline void sync_to_host(Space* S) {
     Device& D = *Device::of(S);
     if (!D.dev_newer) return;
     size_t n = 0;
+    D.each([](vvgpu_ctx* c) { return vvgpu_sync_ranks(c); }, "vvgpu_sync_ranks");
     D.check(vvgpu_particle_count(D.ctx, VVGPU_LIST_VORTEX, &n), "vvgpu_particle_count");
     S->VortexList.resize(n);
     D.check(vvgpu_get_particles(D.ctx, VVGPU_LIST_VORTEX, reinterpret_cast<vvgpu_obj*>(S->VortexList.data()), n, &n),
@@ -143,7 +175,7 @@ inline void upload_bodies(Space* S) {
         bodies.push_back(B);
         ib++;
     }
-    D.check(vvgpu_set_bodies(D.ctx, segs.data(), segs.size(), bodies.data(), bodies.size()), "vvgpu_set_bodies");
+    D.each([&](vvgpu_ctx* c) { return vvgpu_set_bodies(c, segs.data(), segs.size(), bodies.data(), bodies.size()); }, "vvgpu_set_bodies");
 }
 
 // ------------------------------------------------------------------ stree, TSortedTree.hpp:60-92
@@ -164,18 +196,17 @@ class stree {
                                          "(SURVEY.md 8f row 3) and there is no CPU fallback");
             Device& D = *Device::of(S);
             if (!D.dev_newer)
-                D.check(vvgpu_set_particles(D.ctx, VVGPU_LIST_VORTEX,
-                                            reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()), S->VortexList.size()),
-                        "vvgpu_set_particles");
+                D.each([&](vvgpu_ctx* c) { return vvgpu_set_particles(c, VVGPU_LIST_VORTEX, reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()),
+                                                                      S->VortexList.size()); }, "vvgpu_set_particles");
             upload_bodies(S);
             unsigned mask = (IncludeVortexes ? 1u : 0u) | (IncludeBody ? 2u : 0u);
-            D.check(vvgpu_tree_build(D.ctx, farCriteria, minNodeSize, maxNodeSize, mask), "vvgpu_tree_build");
+            D.each([&](vvgpu_ctx* c) { return vvgpu_tree_build(c, farCriteria, minNodeSize, maxNodeSize, mask); }, "vvgpu_tree_build");
             D.dev_newer = true;   // the list is permuted in place, like the reference's
             built = true;
         }
         void destroy() {   // :267-273
             Device& D = *Device::of(S);
-            D.check(vvgpu_tree_destroy(D.ctx), "vvgpu_tree_destroy");
+            D.each([](vvgpu_ctx* c) { return vvgpu_tree_destroy(c); }, "vvgpu_tree_destroy");
             drop_mirror();
             built = false;
         }
@@ -294,7 +325,9 @@ class MEpsilonFast {
         void CalcEpsilonFast(bool merge) {   // MEpsilonFast.cpp:11-63
             if (!Tree->isBuilt()) throw std::runtime_error("MEpsilonFast::CalcEpsilonFast: tree is not built");
             Device& D = *Device::of(S);
-            D.check(vvgpu_epsilon(D.ctx, merge ? 1 : 0, &merged_), "vvgpu_epsilon");
+            std::vector<int> m(D.all.size(), 0);
+            D.each([&](vvgpu_ctx* c) { size_t r = 0; while (D.all[r] != c) r++; return vvgpu_epsilon(c, merge ? 1 : 0, &m[r]); }, "vvgpu_epsilon");
+            merged_ = m[0];
         }
         int Merged() { return merged_; }
 
@@ -320,8 +353,8 @@ class MConvectiveFast {
             TVec inf = S->inf_speed();   // evaluated once per step on the host (TEval needs Lua)
             std::vector<double> sinks;
             for (auto& lobj: S->SourceList) { sinks.push_back(lobj.r.x); sinks.push_back(lobj.r.y); sinks.push_back(lobj.g); }
-            D.check(vvgpu_convective(D.ctx, inf.x, inf.y, double(S->dt), sinks.data(), S->SourceList.size()),
-                    "vvgpu_convective");
+            D.each([&](vvgpu_ctx* c) { return vvgpu_convective(c, inf.x, inf.y, double(S->dt), sinks.data(), S->SourceList.size()); },
+                   "vvgpu_convective");
         }
 
         // MConvectiveFast::NodeInfluence(*tree->findNode(seg.r), seg) (MConvectiveFast.cpp:398-418) for every segment
@@ -365,8 +398,8 @@ class MDiffusiveFast {
         void process_vort_list() {   // MDiffusiveFast.cpp:8-48
             if (!tree->isBuilt()) throw std::runtime_error("MDiffusiveFast::process_vort_list: tree is not built");
             Device& D = *Device::of(S);
-            std::vector<double> fric(S->total_segment_count());
-            D.check(vvgpu_diffusive(D.ctx, S->re, fric.empty() ? nullptr : fric.data()), "vvgpu_diffusive");
+            std::vector<double> fric(S->total_segment_count());   // summed over the ranks inside the library: rank 0's copy
+            D.each([&](vvgpu_ctx* c) { return vvgpu_diffusive(c, S->re, (c == D.ctx && !fric.empty()) ? fric.data() : nullptr); }, "vvgpu_diffusive");
             size_t k = 0;   // TAtt::fric += ..., MDiffusiveFast.cpp:121-122
             for (auto& lbody: S->BodyList) for (auto& latt: lbody->alist) latt.fric += fric[k++];
         }
@@ -394,9 +427,8 @@ class MFlowmove {
                 throw std::invalid_argument("MFlowmove::move_and_clean(): invalid collision pointer");   // :20-22
             Device& D = *Device::of(S);
             if (!D.dev_newer)
-                D.check(vvgpu_set_particles(D.ctx, VVGPU_LIST_VORTEX,
-                                            reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()), S->VortexList.size()),
-                        "vvgpu_set_particles");
+                D.each([&](vvgpu_ctx* c) { return vvgpu_set_particles(c, VVGPU_LIST_VORTEX, reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()),
+                                                                      S->VortexList.size()); }, "vvgpu_set_particles");
             const double current_dt = collision_dt();
             std::vector<TObj> parked;
             parked.swap(S->VortexList);
@@ -406,9 +438,11 @@ class MFlowmove {
 
             const size_t nb = S->BodyList.size(), ns = S->total_segment_count();
             std::vector<double> fdt(3 * nb + 1), gdead(nb + 1), gsum(ns + 1);
-            size_t cleaned = 0;
-            D.check(vvgpu_move_and_clean(D.ctx, current_dt, remove_eps, remove ? 1 : 0, fdt.data(), gdead.data(),
-                                         gsum.data(), &cleaned), "vvgpu_move_and_clean");
+            size_t cleaned = 0;   // the move is replicated: every rank removes the same particles; rank 0 reports
+            D.each([&](vvgpu_ctx* c) {
+                if (c == D.ctx) return vvgpu_move_and_clean(c, current_dt, remove_eps, remove ? 1 : 0, fdt.data(), gdead.data(), gsum.data(), &cleaned);
+                return vvgpu_move_and_clean(c, current_dt, remove_eps, remove ? 1 : 0, nullptr, nullptr, nullptr, nullptr);
+            }, "vvgpu_move_and_clean");
             size_t ib = 0, k = 0;
             for (auto& lbody: S->BodyList) {
                 lbody->fdt_dead.r.x += fdt[3 * ib]; lbody->fdt_dead.r.y += fdt[3 * ib + 1]; lbody->fdt_dead.o += fdt[3 * ib + 2];
@@ -428,8 +462,8 @@ class MFlowmove {
             if (!(D.resident && D.dev_newer)) { host.vortex_shed(); return; }
             S->VortexList.clear();
             host.vortex_shed();
-            D.check(vvgpu_append_particles(D.ctx, VVGPU_LIST_VORTEX, reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()),
-                                           S->VortexList.size()), "vvgpu_append_particles");
+            D.each([&](vvgpu_ctx* c) { return vvgpu_append_particles(c, VVGPU_LIST_VORTEX, reinterpret_cast<const vvgpu_obj*>(S->VortexList.data()),
+                                                                     S->VortexList.size()); }, "vvgpu_append_particles");
             S->VortexList.clear();
         }
         void streak_shed() { host.streak_shed(); }

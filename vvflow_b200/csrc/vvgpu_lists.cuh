@@ -539,15 +539,30 @@ __global__ void __launch_bounds__(1024) k_heavy_pack(int nheavy, int item_cap, T
     int* scount = O.slot_count + h * per;
     int* doff = off + h * per;                              // dense offset of every slot
     int* live = off + (long long)nheavy * per + h * per;    // the slots that hold entries, in order
+    // a walk claims its slots in order, so the slots that hold entries are a prefix of its kItemSlots: one scan over
+    // the WALKS (a thread sums its walk's few used slots) instead of one over all their mostly empty slots
+    const int nwalk = item_cap + 1;
     u32 carry = 0, lcarry = 0;
-    for (long long b = 0; b < per; b += 1024) {
-        const long long s = b + threadIdx.x;
-        const u32 v = (s < per) ? (u32)scount[s] : 0u;
+    for (int b = 0; b < nwalk; b += 1024) {
+        const int wk = b + threadIdx.x;
+        const int* sc = scount + (long long)wk * kItemSlots;
+        u32 v = 0, nlv = 0;
+        if (wk < nwalk)
+            for (int q = 0; q < kItemSlots; q++) {
+                const int cnt = sc[q];
+                if (cnt <= 0) break;
+                v += (u32)cnt; nlv++;
+            }
         u32 total, ltotal;
         const u32 ex = block_exclusive_scan<1024>(v, &total, sh);
-        const u32 lex = block_exclusive_scan<1024>(v ? 1u : 0u, &ltotal, sh);
-        if (s < per) doff[s] = (int)(carry + ex);
-        if (v) live[lcarry + lex] = (int)s;
+        const u32 lex = block_exclusive_scan<1024>(nlv, &ltotal, sh);
+        u32 o = carry + ex;
+        for (u32 q = 0; q < nlv; q++) {
+            const long long sl = (long long)wk * kItemSlots + q;
+            doff[sl] = (int)o;
+            live[lcarry + lex + q] = (int)sl;
+            o += (u32)sc[q];
+        }
         carry += total; lcarry += ltotal;
     }
     if (threadIdx.x == 0) {

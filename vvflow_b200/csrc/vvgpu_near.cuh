@@ -304,7 +304,20 @@ __global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, Shard 
         typename Op::Tgt tg;
         if (!op.init(tg, A, i, l0 + lo, true)) continue;
         op.seed(tg, A, l0 + lo);
-        for (int c = 0; c < nu; c++) op.combine(tg, scratch[(size_t)c * (t1 - t0) + (i - t0)]);
+        // combined in unit order; the loads of a batch do not wait for the combines before them (a fringe group parks
+        // ~100 partial states per target: one dependent L2 round trip each was the whole duration of this kernel)
+        constexpr int kBatch = 8;
+        const typename Op::Part* sp = scratch + (i - t0);
+        const size_t stride = (size_t)(t1 - t0);
+        for (int c = 0; c < nu; c += kBatch) {
+            typename Op::Part pb[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++)
+                if (c + k < nu) pb[k] = sp[(size_t)(c + k) * stride];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++)
+                if (c + k < nu) op.combine(tg, pb[k]);
+        }
         op.finish(tg, A, i, l0 + lo);
     }
 }

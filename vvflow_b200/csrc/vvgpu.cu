@@ -130,6 +130,8 @@ struct vvgpu_ctx {
 
     // multi-GPU: target sharding + the transport (vvgpu_shard.cuh, vvgpu_comm.h)
     Comm comm;
+    int sm_count = 148;
+    int tsplit = 1;            // CTAs per work unit of the near-field kernels (NearArgs::tsplit), chosen with the unit table
     int ngmine = 0;            // leaf groups this rank owns
     int npieces = 0;           // pieces of kShardBlock groups
     long long xL = 1;          // particles of the rank that owns most
@@ -166,6 +168,7 @@ struct vvgpu_ctx {
         a.lbox = lbox.as<double>();
         a.nseg = tnseg;
         a.u0 = 0;
+        a.tsplit = tsplit;
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
         return a;
@@ -454,6 +457,11 @@ int lists_impl(vvgpu_ctx* c) {
         rc = read_u32(c, rank + nslots_total, &nunits);
         if (rc) return rc;
         c->nunits = (int)nunits;
+        {   // fewer than ~5 waves of units (3 CTAs per SM): split the target leaves of every unit over 2 or 4 CTAs
+            static const int forced = getenv("VV_TSPLIT") ? atoi(getenv("VV_TSPLIT")) : 0;
+            const int slots = 3 * c->sm_count;
+            c->tsplit = forced ? forced : (c->nunits >= 5 * slots ? 1 : (c->nunits >= 5 * slots / 2 ? 2 : 4));
+        }
         int* ugroup = c->u_group.get<int>(std::max<u32>(nunits, 1), &ok);
         long long* ubase = c->u_base.get<long long>(std::max<u32>(nunits, 1), &ok);
         int* ucount = c->u_count.get<int>(std::max<u32>(nunits, 1), &ok);
@@ -488,7 +496,7 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
     }
     CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
-    k_near<Op><<<c->nunits, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
+    k_near<Op><<<c->nunits * c->tsplit, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<Op><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -503,7 +511,7 @@ int launch_conv(vvgpu_ctx* c, ConvOp op) {
     NEED(ok);
     k_pack_src<ConvOp><<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), nullptr, s4); CKLAUNCH();
     CK(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvShared)));
-    k_conv<<<c->nunits, kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
+    k_conv<<<c->nunits * c->tsplit, kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<ConvOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -521,7 +529,7 @@ int launch_diff(vvgpu_ctx* c, DiffOp op) {
     double2* xyn = xy + (size_t)c->tn + 1;
     k_pack_diff<<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), s4, xy, xyn); CKLAUNCH();
     CK(cudaFuncSetAttribute(k_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)));
-    k_diff<<<c->nunits, kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
+    k_diff<<<c->nunits * c->tsplit, kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<DiffOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -643,6 +651,7 @@ int vvgpu_create(int device, vvgpu_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return VVGPU_ECUDA;
     vvgpu_ctx* c = new vvgpu_ctx();
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) c->sm_count = 148;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return VVGPU_ECUDA; }
     for (int k = 0; k < VVGPU_T_COUNT; k++) { cudaEventCreate(&c->ev0[k]); cudaEventCreate(&c->ev1[k]); }
     if (cudaMallocHost((void**)&c->h_pinned, 1024) != cudaSuccess) { delete c; return VVGPU_ECUDA; }

@@ -258,14 +258,17 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
     extern __shared__ __align__(16) unsigned char near_smem[];
     CvShared& S = *reinterpret_cast<CvShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + blockIdx.x;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
+    const UnitPart up(A.tsplit);
+    const int u = A.u0 + up.b;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (up.lt0 >= nl) return;
+    const int lt_end = min(nl, up.lt1);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    if (tid == 0) S.next = 0;
+    if (tid == 0) S.next = up.lt0;
     if (lane == 0) {
         mbar_init(&S.w[warp].bar[0], 1); mbar_init(&S.w[warp].bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
         int lt = 0;
         if (lane == 0) lt = atomicAdd(&S.next, 1);
         lt = __shfl_sync(kFullMask, lt, 0);
-        if (lt >= nl) break;
+        if (lt >= lt_end) break;
         const int leaf = l0 + lt;
         const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
         for (int tb = pf; tb < pl; tb += kMaxT) {
@@ -388,14 +391,17 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
     extern __shared__ __align__(16) unsigned char near_smem[];
     CvShared& S = *reinterpret_cast<CvShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + blockIdx.x;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
+    const UnitPart up(A.tsplit);
+    const int u = A.u0 + up.b;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (up.lt0 >= nl) return;
+    const int lt_end = min(nl, up.lt1);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    if (tid == 0) S.next = 0;
+    if (tid == 0) S.next = up.lt0;
     const long long e0 = A.U.base[u];
     const int ne = A.U.count[u];
     // ---- the unit's entry table, once per CTA
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
         int lt = 0;
         if (lane == 0) lt = atomicAdd(&S.next, 1);
         lt = __shfl_sync(kFullMask, lt, 0);
-        if (lt >= nl) break;
+        if (lt >= lt_end) break;
         const int leaf = l0 + lt;
         const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
         for (int tb = pf; tb < pl; tb += kMaxT) {

@@ -114,14 +114,17 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
     extern __shared__ __align__(16) unsigned char near_smem[];
     DfShared& S = *reinterpret_cast<DfShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + unit_order(blockIdx.x, gridDim.x);
+    const UnitPart up(A.tsplit);
+    const int u = A.u0 + unit_order(up.b, gridDim.x / A.tsplit);
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (up.lt0 >= nl) return;
+    const int lt_end = min(nl, up.lt1);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    if (tid == 0) { S.next = 0; S.anyseg = 0; }
+    if (tid == 0) { S.next = up.lt0; S.anyseg = 0; }
     const long long e0 = A.U.base[u];
     const int ne = A.U.count[u];
     __syncthreads();
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
         int lt = 0;
         if (lane == 0) lt = atomicAdd(&S.next, 1);
         lt = __shfl_sync(kFullMask, lt, 0);
-        if (lt >= nl) break;
+        if (lt >= lt_end) break;
         const int leaf = l0 + lt;
         const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
         for (int tb = pf; tb < pl; tb += kMaxT) {

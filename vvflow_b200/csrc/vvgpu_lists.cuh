@@ -33,7 +33,10 @@ constexpr int kGroupLeaves = 32;
 #endif
 constexpr int kUnitEntries = VV_UNIT_ENTRIES;   // list entries per chunk = per work unit of the near-field kernels
 constexpr int kTravWarps = 4;       // warps per CTA in k_traverse
-constexpr int kTravBudget = 256;    // warp iterations before a group is declared heavy (the mean is ~150)
+#ifndef VV_TRAV_BUDGET
+#define VV_TRAV_BUDGET 256
+#endif
+constexpr int kTravBudget = VV_TRAV_BUDGET;    // warp iterations before a group is declared heavy (the mean is ~150)
 constexpr int kTravStack = 1024;    // stack entries per warp (shared memory)
 constexpr int kGroupSlots = 16;     // chunks a regular group may fill before it is declared heavy
 constexpr int kItemSlots = 64;      // chunks one item of a heavy group may fill

@@ -58,6 +58,9 @@ struct NearArgs {
     int nleaves;
     int nseg;
     int u0;  // first unit of this launch (shard offset)
+    int tsplit;  // CTAs per unit: each takes 32 / tsplit of the group's target leaves against the whole entry table. What a
+                 // target sums, and in which order, does not depend on it: few units (a small problem, one rank of many)
+                 // still fill the SMs, with identical bits
     // segments (diffusive / epsilon wall terms)
     const int* seg_perm;
     const double *srx, *sry, *sdlx, *sdly;
@@ -68,6 +71,15 @@ struct NearArgs {
 // alternately puts them first instead of into the kernel's tail (with the work of a step split over 8 GPUs one
 // late fringe unit was a third of the kernel's duration).
 __device__ __forceinline__ int unit_order(int b, int n) { return (b & 1) ? (n - 1 - (b >> 1)) : (b >> 1); }
+// CTA -> (unit slot, first and one-past-last target leaf of the group it serves)
+struct UnitPart {
+    int b, lt0, lt1;
+    __device__ __forceinline__ UnitPart(int tsplit) {
+        b = (int)blockIdx.x / tsplit;
+        const int part = (int)blockIdx.x - b * tsplit, per = kGroupLeaves / tsplit;
+        lt0 = part * per; lt1 = lt0 + per;
+    }
+};
 
 template <class Op>
 struct LwWarpT {
@@ -105,14 +117,17 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     extern __shared__ __align__(16) unsigned char near_smem[];
     LwSharedT<Op>& S = *reinterpret_cast<LwSharedT<Op>*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = A.u0 + unit_order(blockIdx.x, gridDim.x);
+    const UnitPart up(A.tsplit);
+    const int u = A.u0 + unit_order(up.b, gridDim.x / A.tsplit);
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
+    if (up.lt0 >= nl) return;
+    const int lt_end = min(nl, up.lt1);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
-    if (tid == 0) { S.next = 0; S.anyseg = 0; }
+    if (tid == 0) { S.next = up.lt0; S.anyseg = 0; }
     const long long e0 = A.U.base[u];
     const int ne = A.U.count[u];
     __syncthreads();
@@ -149,7 +164,7 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
         int lt = 0;
         if (lane == 0) lt = atomicAdd(&S.next, 1);
         lt = __shfl_sync(kFullMask, lt, 0);
-        if (lt >= nl) break;
+        if (lt >= lt_end) break;
         const int leaf = l0 + lt;
         const int pf = S.bounds[lt], pl = S.bounds[lt + 1];
         for (int tb = pf; tb < pl; tb += kMaxT) {

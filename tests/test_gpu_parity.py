@@ -602,6 +602,29 @@ print("TMA-OK")
     assert p.returncode == 0 and "TMA-OK" in p.stdout, p.stdout[-1500:] + p.stderr[-1500:]
 
 
+def test_convective_without_epsilon(ctx, port):
+    """_1_eps == 0 on every particle (a list that never went through CalcEpsilonFast): the reference's near field is
+    g / (dr^2 + inf) = 0 per pair and only the far field is left; no NaN from the fast reciprocal"""
+    from vvflow_b200 import vvhd
+    xyg = cases.cloud(3000, "gauss", "mixed", seed=77)
+    P = port.Port(xyg=xyg, bodies=cases.port_bodies(port, []))
+    S = vvhd.Space(ctx=ctx)
+    S.VortexList = xyg
+    S.dt, S.inf_vx, S.inf_vy = 0.05, 1.0, 0.0
+    tr = vvhd.TSortedTree(S, 8, 0.0)
+    conv = vvhd.MConvectiveFast(S, tr)
+    P.tree_build(8, 0.0, float(np.finfo(np.float64).max))
+    tr.build()
+    try:
+        P.convective(1.0, 0.0, 0.05)
+        conv.process_all_lists()
+        a, b = S.VortexList, P.rec48()
+        assert np.isfinite(a[:, 3:5]).all()
+        check_close(a[:, 3:5], b[:, 3:5], VTOL, "convective velocity with eps = inf")
+    finally:
+        tr.destroy()
+
+
 def test_error_behaviour(ctx):
     """call-order errors mirror the reference (TSortedTree.cpp:234,286-288; MFlowmove.cpp:20-22)"""
     from vvflow_b200 import capi, vvhd

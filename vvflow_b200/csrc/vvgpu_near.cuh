@@ -382,7 +382,9 @@ struct ConvOp {
     static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*) {
         double g = P.g[j];
         double e = 1. / P.ie[j];
-        return (g == 0) ? make_double4(P.x[j], P.y[j], 0., 1.) : make_double4(P.x[j], P.y[j], g, e * e);
+        // _1_eps == 0 (a list that never went through epsilon): the reference adds g / (dr^2 + inf) = 0; packed like a
+        // g == 0 source, because the reciprocal's Newton step would turn the infinite denominator into a NaN
+        return (g == 0 || isinf(e)) ? make_double4(P.x[j], P.y[j], 0., 1.) : make_double4(P.x[j], P.y[j], g, e * e);
     }
     // (the pair sum itself lives in vvgpu_conv.cuh)
     __device__ __forceinline__ void take(Tgt& t, double vx, double vy) const { t.rx = vx; t.ry = vy; }

@@ -123,7 +123,7 @@ struct vvgpu_ctx {
     size_t nslots = 0;
     bool lists_ready = false;
     // epsilon
-    Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged, leaf_dirty, leaf_dbox;
+    Buf lcrit, lrestr, latt, ie_tmp, dyn, d_changed, d_nmerged, leaf_dirty, leaf_dbox, unit_dirty, group_dirty, tl;
     Buf mA[6], mB[6];
     Buf d_sinks, d_pairs, pt_xy, pt_out, pt_v;
     PSet ps_backup;   // the resident list while a raster evaluator works on its own tree
@@ -486,14 +486,14 @@ int lists_impl(vvgpu_ctx* c) {
 }
 
 template <class Op>
-int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr) {
+int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr, const double4* tl = nullptr) {
     static_assert(sizeof(typename Op::Part) <= sizeof(DiffOp::Part), "scratch is sized for the largest Part");
     if (c->nunits <= 0) return 0;
     {
         bool ok = true;
         double4* s4 = c->src4.get<double4>((size_t)c->tn + 1, &ok);
         NEED(ok);
-        k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4); CKLAUNCH();
+        k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4, tl); CKLAUNCH();
     }
     CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
     k_near<Op><<<c->nunits * c->tsplit, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
@@ -612,11 +612,11 @@ int wall_params(vvgpu_ctx* c, int merge, double* lcrit, double* lrestr, int* lat
 }
 
 // source-leaf boxes for the exact pruning of EpsOp (covering the tentative merged positions of M)
-int eps_boxes(vvgpu_ctx* c, MergeState M) {
+int eps_boxes(vvgpu_ctx* c, MergeState M, const unsigned char* only = nullptr) {
     bool ok = true;
     double* lb = c->lbox.get<double>(5 * (size_t)c->nleaves, &ok);
     NEED(ok);
-    k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), M, lb); CKLAUNCH();
+    k_leaf_box<<<cdiv(c->nleaves, 128), 128, 0, c->stream>>>(c->Lv(), c->nleaves, c->ps[c->cur].view(), M, lb, only); CKLAUNCH();
     return 0;
 }
 
@@ -679,7 +679,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
-                  &c->lrestr, &c->latt, &c->leaf_dirty, &c->leaf_dbox, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
+                  &c->lrestr, &c->latt, &c->leaf_dirty, &c->leaf_dbox, &c->unit_dirty, &c->group_dirty, &c->tl, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
                   &c->sh_first, &c->sh_cnt, &c->sh_off, &c->sh_rankcnt, &c->xsend, &c->xrecv, &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
@@ -1058,20 +1058,44 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     int rounds = 0;
     unsigned char* ldirty = c->leaf_dirty.get<unsigned char>(nl, &ok);
     double* ldbox = c->leaf_dbox.get<double>(4 * (size_t)nl, &ok);
+    unsigned char* udirty = c->unit_dirty.get<unsigned char>((size_t)std::max(c->nunits, 1), &ok);
+    unsigned char* gdirty = c->group_dirty.get<unsigned char>((size_t)std::max(c->ngroups, 1), &ok);
+    double4* tl = c->tl.get<double4>(2 * (size_t)n, &ok);
     NEED(ok);
+    u32 prev_changed = 0;
     for (;; rounds++) {
         if (rounds > n + 2) return fail(c, VVGPU_ELIMIT, "merge fixed point did not converge");
         MergeState A = haveA ? mstate(c->mA) : MergeState{};
         MergeState B = mstate(c->mB);
-        // later rounds recompute only the leaves that see a changed entry; the others keep last round's outcome
+        // Later rounds recompute only the targets that see a changed entry; the others keep last round's outcome. While
+        // most entries still change (the first rounds of a wake full of merges) nearly every target sees one, and looking
+        // for them costs more than it saves: those rounds recompute everything.
+        const bool incremental = haveA && prev_changed <= (u32)nl / 8;
         if (haveA) { k_merge_copy<<<cdiv(n, 256), 256, 0, st>>>(n, A, B); CKLAUNCH(); }
         else { k_merge_clear<<<cdiv(n, 256), 256, 0, st>>>(n, B); CKLAUNCH(); }
         CK(cudaMemsetAsync(dchg, 0, 2 * sizeof(int), st));
-        EpsOp<false> op{A, B, lcrit, lrestr, dyn, ietmp, dchg};
-        op.leaf_dirty = haveA ? ldirty : nullptr;
-        op.leaf_dbox = ldbox;
-        int rc = eps_boxes(c, A);
-        if (!rc) rc = launch_near(c, op, haveA ? dyn : nullptr);
+        if (incremental && c->nunits > 0) {
+            CK(cudaMemsetAsync(gdirty, 0, (size_t)c->ngroups, st));
+            k_unit_dirty<<<c->nunits, 128, 0, st>>>(c->nunits, c->Uv(), c->Gv(), ldirty, udirty, gdirty); CKLAUNCH();
+        }
+        // the boxes of the leaves whose particles kept their entries are those of the last round
+        int rc = eps_boxes(c, A, haveA ? ldirty : nullptr);
+        if (rc) return rc;
+        auto run_round = [&](auto op) -> int {
+            op.leaf_dirty = incremental ? ldirty : nullptr;
+            op.leaf_dbox = ldbox;
+            op.tl = haveA ? tl : nullptr;
+            if (incremental && c->nunits > 0) { op.unit_dirty = udirty; op.group_dirty = gdirty; }
+            // few units have anything to do in an incremental round, and the ones that always do (the fringe groups of
+            // several units, which see the whole tree) are the slowest: spread each over 4 CTAs (same bits, NearArgs::tsplit)
+            const int ts = c->tsplit;
+            if (incremental) c->tsplit = 4;
+            const int rcn = launch_near(c, op, haveA ? dyn : nullptr, haveA ? tl : nullptr);
+            c->tsplit = ts;
+            return rcn;
+        };
+        rc = haveA ? run_round(EpsOp<false, true>{A, B, lcrit, lrestr, dyn, ietmp, dchg})
+                   : run_round(EpsOp<false, false>{A, B, lcrit, lrestr, dyn, ietmp, dchg});
         if (rc) return rc;
         if (multi) {
             // what travels: with whom every particle merges (-1: it does not) and its epsilon. The merged state of an
@@ -1098,10 +1122,12 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
             fprintf(stderr, "[vvgpu] merge round %d: %u decisions changed, %u target batches of %d leaves recomputed (0 = all)\n", rounds, changed, redo, nl);
         }
         if (!changed) break;  // B reproduces A
-        k_leaf_dirty<<<cdiv(nl, 128), 128, 0, st>>>(c->Lv(), nl, P.view(), A, B, ldirty, ldbox); CKLAUNCH();
+        prev_changed = changed;
+        k_leaf_dirty_clear<<<cdiv(nl, 256), 256, 0, st>>>(nl, ldirty, ldbox); CKLAUNCH();
+        k_leaf_dirty<<<cdiv(n, 256), 256, 0, st>>>(c->Lv(), nl, n, P.view(), A, B, ldirty, ldbox); CKLAUNCH();
         for (int k = 0; k < 6; k++) std::swap(c->mA[k], c->mB[k]);
         haveA = true;
-        k_merge_dyn<<<cdiv(n, 256), 256, 0, st>>>(n, mstate(c->mA), dyn); CKLAUNCH();
+        k_merge_dyn<<<cdiv(n, 256), 256, 0, st>>>(n, P.view(), mstate(c->mA), dyn, tl); CKLAUNCH();
     }
     c->merge_rounds = rounds + 1;
     if (!haveA) {  // no merge anywhere: every epsilon is final
@@ -1110,9 +1136,9 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
     }
     // epsilon of the initiators at their merged position (the recursive epsv call, :169), then commit
     MergeState A = mstate(c->mA);
-    EpsOp<true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
-    int rc = eps_boxes(c, A);
-    if (!rc) rc = launch_near(c, opf, dyn);
+    EpsOp<true, true> opf{A, MergeState{}, nullptr, lrestr, dyn, ietmp, dchg};
+    opf.tl = tl;
+    int rc = launch_near(c, opf, dyn, tl);   // (the leaf boxes are those of the last round: the same A)
     if (!rc && multi) rc = gather_ie(ietmp);
     if (rc) return rc;
     std::swap(c->ie_tmp, P.ie);  // absorbed-before-turn particles kept their old value in ie_tmp (never written)

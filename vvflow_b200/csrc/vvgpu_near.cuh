@@ -15,6 +15,7 @@
 // A leaf normally holds < 16 particles (Tree_MaxListSize); leaves made by the min-node-size rule
 // can hold more and are processed in chunks of 15 targets.
 #pragma once
+#include <type_traits>
 #include "vvgpu_lists.cuh"
 
 namespace vv {
@@ -125,6 +126,10 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     if (up.lt0 >= nl) return;
+    if constexpr (Op::kDirty) {
+        // a later round of the merge fixed point, and nothing this unit's targets can see changed: they keep their entries
+        if (op.unit_dirty && (multi ? !op.group_dirty[g] : !op.unit_dirty[u])) return;
+    }
     const int lt_end = min(nl, up.lt1);
     if (tid <= nl) S.bounds[tid] = (tid < nl) ? A.L.first[l0 + tid] : A.L.last[l0 + nl - 1];
     if (tid == 0) { S.next = up.lt0; S.anyseg = 0; }
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(256) k_near_finalize(NearArgs A, Op op, Shard 
     const int g = sh.group(blockIdx.x);
     const int nu = A.U.num[g];
     if (nu <= 1) return;
+    if (op.skip_group(g)) return;
     const int l0 = g * kGroupLeaves;
     const int nl = min(kGroupLeaves, A.nleaves - l0);
     const int t0 = A.L.first[l0], t1 = A.L.last[l0 + nl - 1];
@@ -349,9 +355,9 @@ __global__ void k_unit_slots(LeafDev L, int nleaves, int ngroups, const int* __r
 
 // per-phase packed source records (one 32-byte load per staged source instead of four scattered ones)
 template <class Op>
-__global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4* out) {
+__global__ void k_pack_src(int n, Particles P, const unsigned char* dyn, double4* out, const double4* tl = nullptr) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = Op::pack(P, j, dyn);
+    if (j < n) out[j] = Op::pack(P, j, dyn, tl);
     else if (j == n) out[j] = make_double4(0., 0., 0., 1.);   // dummy record (g = 0): pads K4's index lists
 }
 
@@ -369,6 +375,7 @@ struct ConvOp {
     __device__ __forceinline__ Part part(const Tgt& t) const { return Part{t.rx, t.ry}; }
     __device__ __forceinline__ void combine(Tgt& t, const Part& p) const { t.rx += p.rx; t.ry += p.ry; }
     __device__ __forceinline__ void seed(Tgt&, const NearArgs&, int) const {}
+    __device__ __forceinline__ bool skip_group(int) const { return false; }
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.rx = t.ry = 0; t.x = t.y = 0;
@@ -379,7 +386,7 @@ struct ConvOp {
     }
     // packed source record: eps^2 = sqr(1./_1_eps) of the SOURCE (:119); a g==0 source is skipped by
     // the reference (:130) and is packed as g = 0, eps^2 = 1 so that it adds exactly nothing
-    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*) {
+    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char*, const double4*) {
         double g = P.g[j];
         double e = 1. / P.ie[j];
         // _1_eps == 0 (a list that never went through epsilon): the reference adds g / (dr^2 + inf) = 0; packed like a
@@ -425,6 +432,7 @@ struct DiffOp {
         t.S1 += p.S1; t.S2x += p.S2x; t.S2y += p.S2y; t.S0 += p.S0; t.S3x += p.S3x; t.S3y += p.S3y;
     }
     __device__ __forceinline__ void seed(Tgt&, const NearArgs&, int) const {}
+    __device__ __forceinline__ bool skip_group(int) const { return false; }
 
     __device__ __forceinline__ bool init(Tgt& t, const NearArgs& A, int i, int leaf, bool inrange) const {
         t.S1 = t.S2x = t.S2y = t.S0 = t.S3x = t.S3y = 0;
@@ -513,7 +521,9 @@ __global__ void k_merge_fill(int n, Particles P, MergeState A, MergeState B) {
     atomicMin(&B.absby[i1], i);
 }
 
-template <bool FINAL>
+// TL: the round runs against a tentative solution with a compact timeline (every round but the first): sources are
+// fetched as 32-byte records that carry the pre-filter of their timeline; without, as 16 bytes (x, y).
+template <bool FINAL, bool TL = false>
 struct EpsOp {
     static constexpr bool kSegments = false;
     // a source leaf whose box is farther from the leaf's targets than the largest seeded second-neighbour
@@ -530,6 +540,10 @@ struct EpsOp {
     int* changed;
     const unsigned char* leaf_dirty = nullptr;   // per leaf (decision rounds after the first): holds a changed entry
     const double* leaf_dbox = nullptr;           // per leaf 4: box of every position its changed particles were or are seen at
+    const unsigned char* unit_dirty = nullptr;   // per work unit: its table names a dirty leaf (k_unit_dirty)
+    const unsigned char* group_dirty = nullptr;  // per group: one of its units does (a group of several units is redone as a whole)
+    const double4* tl = nullptr;                 // per particle with a timeline entry in A_, two records: (x, y, g, nx), (ny, ng, absby | init, -)
+    __device__ __forceinline__ bool skip_group(int g) const { return kDirty && group_dirty && !group_dirty[g]; }
     struct Tgt { double x, y, r1, r2; int i, i1, i2, pad_; };
     __device__ __forceinline__ double reach2(const Tgt& t) const { return t.r2; }
     struct Part { double r1, r2; int i1, i2; };
@@ -584,13 +598,25 @@ struct EpsOp {
             cand(t, A, d, j);
         }
     }
-    // A g == 0 source is parked at x = +inf (never a neighbour, :140); a source with a timeline entry
-    // at x = NaN, which fails the `d > r2` test below and is re-read from the timeline in cand().
-    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char* dyn) {
-        double x = P.x[j];
+    // Packed source (x, y, z, w). A g == 0 source is parked at x = +inf (never a neighbour, :140). A source with a
+    // timeline entry (w = 1) is seen by a target at its original or at its merged position, delta apart: it can only
+    // be a neighbour candidate if d(original) <= (sqrt(r2) + delta)^2 <= 2 r2 + 2 delta^2, and z = 2 delta^2 makes that
+    // one FMA in use(); what passes is resolved from the timeline in cand(). (Without the compact timeline such a
+    // source sits at x = NaN, which fails every `d > r2` test.)
+    static __device__ __forceinline__ double4 pack(const Particles& P, int j, const unsigned char* dyn, const double4* tl) {
+        double x = P.x[j], z = 0., w = 0.;
         if (P.g[j] == 0) x = __longlong_as_double(0x7ff0000000000000ll);
-        else if (dyn && dyn[j]) x = __longlong_as_double(0x7ff8000000000000ll);
-        return make_double4(x, P.y[j], 0., 0.);
+        else if (dyn && dyn[j]) {
+            if (tl) {
+                const double4 a = tl[2ll * j], b = tl[2ll * j + 1];
+                if (__double2hiint(b.z)) {
+                    const double ex = a.w - a.x, ey = b.x - a.y;
+                    z = 2.000000002 * (ex * ex + ey * ey);
+                }
+                w = 1.;
+            } else x = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        return make_double4(x, P.y[j], z, w);
     }
     // state of source j as target i sees it; false = not a neighbour candidate
     __device__ __forceinline__ bool seen(int j, int i, double& sx, double& sy, double& sg) const {
@@ -602,22 +628,46 @@ struct EpsOp {
     __device__ __forceinline__ void cand(Tgt& t, const NearArgs& A, double d, int j) const {
         if (j == t.i) return;  // :140
         if (isnan(d)) {
-            double sx = A.P.x[j], sy = A.P.y[j], sg = A.P.g[j];
-            if (!A_.absby || !seen(j, t.i, sx, sy, sg)) return;
+            if (!A_.absby) return;
+            double sx, sy, sg;
+            if (tl) {
+                // every pair with such a source comes here, near or not: its timeline in two 32-byte records instead of
+                // nine scattered columns
+                const double4 a = tl[2ll * j], b = tl[2ll * j + 1];
+                const int ab = __double2loint(b.z), in = __double2hiint(b.z);
+                if (FINAL ? (ab <= t.i) : (ab < t.i)) return;
+                sx = a.x; sy = a.y; sg = a.z;
+                if (in && j < t.i) { sx = a.w; sy = b.x; sg = b.y; }
+                if (sg == 0) return;
+            } else {
+                sx = A.P.x[j]; sy = A.P.y[j]; sg = A.P.g[j];
+                if (!seen(j, t.i, sx, sy, sg)) return;
+            }
             double dx = VV_SUB(t.x, sx), dy = VV_SUB(t.y, sy);
             d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
         }
         consider(t, d, j);
     }
-    // common path: 5 FP64 + one compare; only a source at least as close as the current second
-    // neighbour (or a parked NaN) takes the branch
-    typedef double2 Src;
-    static __device__ __forceinline__ Src none() { return make_double2(__longlong_as_double(0x7ff0000000000000ll), 0.); }
-    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) { return *reinterpret_cast<const double2*>(A.src4 + j); }
+    // common path: 5 FP64 (+ 1 FMA in rounds with a timeline) + one compare; only a source at least as close as the
+    // current second neighbour, or a timeline source that might be, takes the branch
+    typedef typename std::conditional<TL, double4, double2>::type Src;
+    static __device__ __forceinline__ Src none() {
+        if constexpr (TL) return make_double4(__longlong_as_double(0x7ff0000000000000ll), 0., 0., 0.);
+        else return make_double2(__longlong_as_double(0x7ff0000000000000ll), 0.);
+    }
+    static __device__ __forceinline__ Src fetch(const NearArgs& A, int j) {
+        if constexpr (TL) return A.src4[j];
+        else return *reinterpret_cast<const double2*>(A.src4 + j);
+    }
     __device__ __forceinline__ void use(Tgt& t, const NearArgs& A, const Src& p, int j) const {
         double dx = VV_SUB(t.x, p.x), dy = VV_SUB(t.y, p.y);
         double d = VV_ADD(VV_MUL(dx, dx), VV_MUL(dy, dy));
-        if (!(d > t.r2)) cand(t, A, d, j);
+        if constexpr (TL) {
+            if (!(d > fma(2.000000002, t.r2, p.z))) {
+                if (p.w != 0.) cand(t, A, __longlong_as_double(0x7ff8000000000000ll), j);
+                else if (!(d > t.r2)) cand(t, A, d, j);
+            }
+        } else if (!(d > t.r2)) cand(t, A, d, j);
     }
     __device__ __forceinline__ void segments(Tgt&, const NearArgs&, int, int) const {}
     __device__ __forceinline__ void finish(Tgt& t, const NearArgs& A, int i, int leaf) const {
@@ -676,42 +726,89 @@ __global__ void k_merge_copy(int n, MergeState A, MergeState B) {
     B.init[i] = A.init[i]; B.part[i] = A.part[i]; B.nx[i] = A.nx[i]; B.ny[i] = A.ny[i]; B.ng[i] = A.ng[i];
 }
 // per leaf: does it hold a particle whose entry differs between the old solution (A, absent before the first round)
-// and the new one (B)? Targets that see no such leaf would decide as before.
-__global__ void k_leaf_dirty(LeafDev L, int nleaves, Particles P, MergeState A, MergeState B, unsigned char* dirty, double* dbox) {
+// and the new one (B)? Targets that see no such leaf would decide as before. One thread per PARTICLE (coalesced reads of
+// the solution's columns); the few changed ones find their leaf and widen its dirty box (min / max: order-independent).
+__device__ __forceinline__ void atomic_min_f64(double* a, double v) {
+    unsigned long long old = *reinterpret_cast<unsigned long long*>(a);
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(reinterpret_cast<unsigned long long*>(a), assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double* a, double v) {
+    unsigned long long old = *reinterpret_cast<unsigned long long*>(a);
+    while (v > __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(reinterpret_cast<unsigned long long*>(a), assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__global__ void k_leaf_dirty_clear(int nleaves, unsigned char* dirty, double* dbox) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaves) return;
-    bool any = false;
-    double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX;
-    for (int i = L.first[l]; i < L.last[l]; i++) {
-        const int bi = B.init[i], ba = B.absby[i];
-        const int ai = A.absby ? A.init[i] : 0, aa = A.absby ? A.absby[i] : kNoAbs;
-        bool d = bi != ai || ba != aa;
-        if (!d && bi) d = B.part[i] != A.part[i] || __double_as_longlong(B.nx[i]) != __double_as_longlong(A.nx[i]) ||
-                          __double_as_longlong(B.ny[i]) != __double_as_longlong(A.ny[i]) ||
-                          __double_as_longlong(B.ng[i]) != __double_as_longlong(A.ng[i]);
-        if (!d) continue;
-        any = true;
-        double x = P.x[i], y = P.y[i];
-        x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y);
-        if (ai) { x = A.nx[i]; y = A.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
-        if (bi) { x = B.nx[i]; y = B.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
-    }
-    dirty[l] = any ? 1 : 0;
+    dirty[l] = 0;
     double* b = dbox + 4ll * l;
-    b[0] = x0; b[1] = x1; b[2] = y0; b[3] = y1;
+    b[0] = DBL_MAX; b[1] = -DBL_MAX; b[2] = DBL_MAX; b[3] = -DBL_MAX;
 }
-__global__ void k_merge_dyn(int n, MergeState M, unsigned char* dyn) {
+__global__ void k_leaf_dirty(LeafDev L, int nleaves, int n, Particles P, MergeState A, MergeState B, unsigned char* dirty, double* dbox) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int bi = B.init[i], ba = B.absby[i];
+    const int ai = A.absby ? A.init[i] : 0, aa = A.absby ? A.absby[i] : kNoAbs;
+    bool d = bi != ai || ba != aa;
+    if (!d && bi) d = B.part[i] != A.part[i] || __double_as_longlong(B.nx[i]) != __double_as_longlong(A.nx[i]) ||
+                      __double_as_longlong(B.ny[i]) != __double_as_longlong(A.ny[i]) ||
+                      __double_as_longlong(B.ng[i]) != __double_as_longlong(A.ng[i]);
+    if (!d) return;
+    int lo = 0, hi = nleaves - 1;   // the leaf that holds particle i: the last one that starts at or before it and is not empty
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (L.first[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    while (lo > 0 && L.last[lo] <= i) lo--;   // (leaves without particles share their start with the next one)
+    double x0 = P.x[i], x1 = x0, y0 = P.y[i], y1 = y0;
+    if (ai) { const double x = A.nx[i], y = A.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
+    if (bi) { const double x = B.nx[i], y = B.ny[i]; x0 = fmin(x0, x); x1 = fmax(x1, x); y0 = fmin(y0, y); y1 = fmax(y1, y); }
+    dirty[lo] = 1;
+    double* b = dbox + 4ll * lo;
+    atomic_min_f64(b + 0, x0); atomic_max_f64(b + 1, x1); atomic_min_f64(b + 2, y0); atomic_max_f64(b + 3, y1);
+}
+// per work unit: does its entry table name a dirty leaf? A unit that does not keeps last round's outcome as a whole.
+__global__ void __launch_bounds__(128) k_unit_dirty(int nunits, Units U, GroupLists G, const unsigned char* __restrict__ leaf_dirty,
+                                                    unsigned char* unit_dirty, unsigned char* group_dirty) {
+    const int u = blockIdx.x;
+    if (u >= nunits) return;
+    const long long e0 = U.base[u];
+    const int ne = U.count[u];
+    int any = 0;
+    for (int e = threadIdx.x; e < ne; e += 128) any |= leaf_dirty[G.leaf[e0 + e]];
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+        unit_dirty[u] = any ? 1 : 0;
+        if (any) group_dirty[U.group[u]] = 1;   // (zeroed by the caller; every writer stores the same value)
+    }
+}
+__global__ void k_merge_dyn(int n, Particles P, MergeState M, unsigned char* dyn, double4* tl) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    dyn[i] = (M.init[i] != 0 || M.absby[i] != kNoAbs) ? 1 : 0;
+    const int in = M.init[i], ab = M.absby[i];
+    const bool d = in != 0 || ab != kNoAbs;
+    dyn[i] = d ? 1 : 0;
+    if (!d) return;
+    double nx = 0, ny = 0, ng = 0;
+    if (in) { nx = M.nx[i]; ny = M.ny[i]; ng = M.ng[i]; }
+    tl[2ll * i] = make_double4(P.x[i], P.y[i], P.g[i], nx);
+    tl[2ll * i + 1] = make_double4(ny, ng, __hiloint2double(in, ab), 0.);
 }
 
 // current bounding box and largest epsilon of every leaf's particles (after epsilon / merging). With a
 // tentative merge solution M (epsilon rounds), the box also covers the post-merge position of every
 // initiator, so that it bounds every state a source of the leaf can be seen in.
-__global__ void k_leaf_box(LeafDev L, int nleaves, Particles P, MergeState M, double* lbox) {
+__global__ void k_leaf_box(LeafDev L, int nleaves, Particles P, MergeState M, double* lbox, const unsigned char* __restrict__ only = nullptr) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaves) return;
+    if (only && !only[l]) return;   // (a later merge round: the entries of this leaf's particles are those of the last round)
     double x0 = DBL_MAX, x1 = -DBL_MAX, y0 = DBL_MAX, y1 = -DBL_MAX, em = 0;
     for (int i = L.first[l]; i < L.last[l]; i++) {
         double x = P.x[i], y = P.y[i];

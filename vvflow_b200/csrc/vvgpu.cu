@@ -132,6 +132,9 @@ struct vvgpu_ctx {
     Comm comm;
     int sm_count = 148;
     int tsplit = 1;            // CTAs per work unit of the near-field kernels (NearArgs::tsplit), chosen with the unit table
+    int ncta = 0, cta_heavy = 0;   // CTA table of the near-field kernels (k_cta_table): entries, entries of its first class
+    bool cta_off = false;      // launch by the tsplit formula instead (incremental merge rounds)
+    Buf cta_unit, cta_part, cta_out;
     int ngmine = 0;            // leaf groups this rank owns
     int npieces = 0;           // pieces of kShardBlock groups
     long long xL = 1;          // particles of the rank that owns most
@@ -169,6 +172,10 @@ struct vvgpu_ctx {
         a.nseg = tnseg;
         a.u0 = 0;
         a.tsplit = tsplit;
+        const bool tab = ncta > 0 && !cta_off;
+        a.cta_unit = tab ? cta_unit.as<int>() : nullptr;
+        a.cta_part = tab ? cta_part.as<unsigned short>() : nullptr;
+        a.cta_heavy = cta_heavy;
         a.seg_perm = t_segperm[segcur].as<int>();
         a.srx = s_rx.as<double>(); a.sry = s_ry.as<double>(); a.sdlx = s_dlx.as<double>(); a.sdly = s_dly.as<double>();
         return a;
@@ -473,9 +480,24 @@ int lists_impl(vvgpu_ctx* c) {
         k_unit_slots<<<cdiv(ng, 128), 128, 0, st>>>(L, nl, ng, unum, nsl); CKLAUNCH();
         rc = scan_flags(c, FlagArray{nsl}, ng, usb);
         if (rc) return rc;
+        // CTA table (vvgpu_lists.cuh): costly units split over several CTAs and started first
+        c->ncta = 0; c->cta_heavy = 0;
         u32 nslots = 0;
-        rc = read_u32(c, usb + ng, &nslots);
-        if (rc) return rc;
+        static const bool no_table = getenv("VV_NO_CTA_TABLE") != nullptr;
+        if (nunits > 0 && !no_table) {
+            const size_t ctacap = (size_t)std::max(4, c->tsplit) * nunits;
+            int* ctau = c->cta_unit.get<int>(ctacap, &ok);
+            unsigned short* ctap = c->cta_part.get<unsigned short>(ctacap, &ok);
+            u32* cout = c->cta_out.get<u32>(4, &ok);
+            NEED(ok);
+            k_cta_table<<<1, 1024, 0, st>>>((int)nunits, L, nl, ugroup, ucount, 3 * c->sm_count, c->tsplit, ctau, ctap, usb + ng, cout); CKLAUNCH();
+            CK(cudaMemcpyAsync(c->h_pinned, cout, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CK(stream_sync(c));
+            c->ncta = (int)((u32*)c->h_pinned)[0]; c->cta_heavy = (int)((u32*)c->h_pinned)[1]; nslots = ((u32*)c->h_pinned)[2];
+        } else {
+            rc = read_u32(c, usb + ng, &nslots);
+            if (rc) return rc;
+        }
         c->nslots = nslots;
         c->near_scratch.get<unsigned char>((size_t)nslots * sizeof(DiffOp::Part), &ok);
         NEED(ok);
@@ -484,6 +506,8 @@ int lists_impl(vvgpu_ctx* c) {
     c->lists_ready = true;
     return 0;
 }
+
+inline int near_grid(vvgpu_ctx* c) { return (c->ncta > 0 && !c->cta_off) ? c->ncta : c->nunits * c->tsplit; }
 
 template <class Op>
 int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr, const double4* tl = nullptr) {
@@ -496,7 +520,7 @@ int launch_near(vvgpu_ctx* c, Op op, const unsigned char* dyn = nullptr, const d
         k_pack_src<Op><<<cdiv(c->tn, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), dyn, s4, tl); CKLAUNCH();
     }
     CK(cudaFuncSetAttribute(k_near<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LwSharedT<Op>)));
-    k_near<Op><<<c->nunits * c->tsplit, kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
+    k_near<Op><<<near_grid(c), kLwThreads, sizeof(LwSharedT<Op>), c->stream>>>(c->near_args(), op); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<Op><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -511,7 +535,7 @@ int launch_conv(vvgpu_ctx* c, ConvOp op) {
     NEED(ok);
     k_pack_src<ConvOp><<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), nullptr, s4); CKLAUNCH();
     CK(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CvShared)));
-    k_conv<<<c->nunits * c->tsplit, kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
+    k_conv<<<near_grid(c), kCvThreads, sizeof(CvShared), c->stream>>>(c->near_args(), op, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<ConvOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -529,7 +553,7 @@ int launch_diff(vvgpu_ctx* c, DiffOp op) {
     double2* xyn = xy + (size_t)c->tn + 1;
     k_pack_diff<<<cdiv(c->tn + 1, 256), 256, 0, c->stream>>>(c->tn, c->ps[c->cur].view(), s4, xy, xyn); CKLAUNCH();
     CK(cudaFuncSetAttribute(k_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)));
-    k_diff<<<c->nunits * c->tsplit, kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
+    k_diff<<<near_grid(c), kDfThreads, sizeof(DfShared), c->stream>>>(c->near_args(), op, xy, xyn, c->tn); CKLAUNCH();
     if (c->nslots > 0) {  // some group has more than one unit
         k_near_finalize<DiffOp><<<c->ngmine, 256, 0, c->stream>>>(c->near_args(), op, c->shard(), c->ngmine); CKLAUNCH();
     }
@@ -679,7 +703,7 @@ void vvgpu_destroy(vvgpu_ctx* c) {
                   &c->t_segperm[0], &c->t_segperm[1], &c->t_perm, &c->t_tmpR, &c->scan_part, &c->scan_out, &c->flags, &c->build_state, &c->b_enc, &c->b_tilepre, &c->b_chunktot, &c->b_sublist, &c->b_scratch, &c->b_arena, &c->b_aux, &c->b_subinfo,
                   &c->l_first, &c->l_last, &c->l_sfirst, &c->l_slast, &c->l_cx, &c->l_cy, &c->l_h, &c->l_w, &c->l_node,
                   &c->g_leaf, &c->g_mask, &c->g_cursor, &c->slot_base, &c->slot_count, &c->u_base, &c->u_count, &c->u_num, &c->hv_inode, &c->hv_imask, &c->hv_icount, &c->hv_tpart, &c->hv_off, &c->taylor, &c->farcount, &c->d_err, &c->lcrit,
-                  &c->lrestr, &c->latt, &c->leaf_dirty, &c->leaf_dbox, &c->unit_dirty, &c->group_dirty, &c->tl, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
+                  &c->lrestr, &c->latt, &c->leaf_dirty, &c->leaf_dbox, &c->unit_dirty, &c->group_dirty, &c->tl, &c->cta_unit, &c->cta_part, &c->cta_out, &c->ie_tmp, &c->dyn, &c->d_changed, &c->d_nmerged, &c->d_sinks, &c->d_pairs,
                   &c->sh_first, &c->sh_cnt, &c->sh_off, &c->sh_rankcnt, &c->xsend, &c->xrecv, &c->u_group, &c->u_first, &c->u_sbase, &c->u_tmp, &c->near_scratch, &c->src4, &c->src2, &c->lbox, &c->wall_d, &c->wall_key, &c->hv_list};
     for (Buf* b : all) b->release();
     for (int k = 0; k < 6; k++) { c->mA[k].release(); c->mB[k].release(); }
@@ -1089,9 +1113,9 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
             // few units have anything to do in an incremental round, and the ones that always do (the fringe groups of
             // several units, which see the whole tree) are the slowest: spread each over 4 CTAs (same bits, NearArgs::tsplit)
             const int ts = c->tsplit;
-            if (incremental) c->tsplit = 4;
+            if (incremental) { c->tsplit = 4; c->cta_off = true; }
             const int rcn = launch_near(c, op, haveA ? dyn : nullptr, haveA ? tl : nullptr);
-            c->tsplit = ts;
+            c->tsplit = ts; c->cta_off = false;
             return rcn;
         };
         rc = haveA ? run_round(EpsOp<false, true>{A, B, lcrit, lrestr, dyn, ietmp, dchg})

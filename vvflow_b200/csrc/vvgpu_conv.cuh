@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
     extern __shared__ __align__(16) unsigned char near_smem[];
     CvShared& S = *reinterpret_cast<CvShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnitPart up(A.tsplit);
+    const UnitPart up(A, false);
     const int u = A.u0 + up.b;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kCvThreads, VV_CV_MINB) k_conv(NearArgs A, Con
     extern __shared__ __align__(16) unsigned char near_smem[];
     CvShared& S = *reinterpret_cast<CvShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnitPart up(A.tsplit);
+    const UnitPart up(A, false);
     const int u = A.u0 + up.b;   // (uniform cost per entry: DFS order keeps neighbouring units on neighbouring SMs)
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];

@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kDfThreads, VV_DF_MINB) k_diff(NearArgs A, Dif
     extern __shared__ __align__(16) unsigned char near_smem[];
     DfShared& S = *reinterpret_cast<DfShared*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnitPart up(A.tsplit);
-    const int u = A.u0 + unit_order(up.b, gridDim.x / A.tsplit);
+    const UnitPart up(A, true);
+    const int u = A.u0 + up.b;
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;

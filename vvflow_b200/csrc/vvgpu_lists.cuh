@@ -661,6 +661,65 @@ __global__ void k_lists_dfs(TreeDev T, LeafDev L, int nleaves, double farc, u32*
     if (!FILL) { ncount[l] = nn; fcount[l] = nf; }
 }
 
+// ---- CTA table of the near-field kernels ---------------------------------------------------------------------
+// A work unit's cost is (about) its pair count: (#targets of its group) x (#particles of its entries' source leaves).
+// Estimated without reading the entries as entries x T x T / 32, T = particles of the group's 32 leaves: the source
+// leaves are the neighbourhood of the targets and about as dense. Where the minimum node size stops the bisection (dense
+// regions next to a body), leaves hold hundreds of particles and ONE unit can cost a hundred average ones: the kernel then ends with a few
+// CTAs on a mostly idle GPU (cylinder wake, N = 1M: SMs busy 42 % of k_conv's duration). So units that cost more than a
+// third of an SM slot's fair share are split over 2 or 4 CTAs, each taking 16 or 8 of the unit's 32 target leaves against
+// the whole entry table, and their CTAs start first. What a target sums, and in which order, does not depend on it.
+// cta -> (unit, first and one-past-last target leaf): the units that are split further than `f0` first, then the others
+// in unit order. out[0] = number of CTAs, out[1] = how many of them belong to the first class, out[2] = *carry (a value
+// the host wants with the same read-back).
+__device__ __forceinline__ unsigned long long unit_cost(const LeafDev& L, int nleaves, int g, int entries) {
+    const int l0 = g * kGroupLeaves, l1 = min(l0 + kGroupLeaves, nleaves) - 1;
+    const unsigned long long t = (unsigned long long)(L.last[l1] - L.first[l0]);
+    return (unsigned long long)entries * t * t;
+}
+__global__ void __launch_bounds__(1024) k_cta_table(int nunits, LeafDev L, int nleaves, const int* __restrict__ ugroup,
+                                                    const int* __restrict__ ucount, int slots, int f0,
+                                                    int* cta_unit, unsigned short* cta_part, const u32* carry, u32* out) {
+    __shared__ u32 sh[1024 / 32 + 1];
+    __shared__ unsigned long long tsum[32];
+    __shared__ unsigned long long total_s;
+    unsigned long long s = 0;
+    for (int u = threadIdx.x; u < nunits; u += 1024) s += unit_cost(L, nleaves, ugroup[u], ucount[u]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) tsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 32; k++) t += tsum[k];
+        total_s = t;
+    }
+    __syncthreads();
+    const unsigned long long thr = max(1ull, total_s / (3ull * (unsigned long long)slots));
+    u32 base = 0;
+    for (int pass = 0; pass < 2; pass++) {   // 0: the units split further than f0, 1: the others
+        for (int b = 0; b < nunits; b += 1024) {
+            const int u = b + threadIdx.x;
+            int f = 0;
+            if (u < nunits) {
+                f = f0;
+                const unsigned long long cu = unit_cost(L, nleaves, ugroup[u], ucount[u]);
+                while (f < 4 && cu > thr * (unsigned long long)f) f *= 2;
+                if ((f > f0) != (pass == 0)) f = 0;
+            }
+            u32 total;
+            const u32 ex = block_exclusive_scan<1024>((u32)f, &total, sh);
+            const int per = f ? kGroupLeaves / f : 0;
+            for (int q = 0; q < f; q++) {
+                cta_unit[base + ex + q] = u;
+                cta_part[base + ex + q] = (unsigned short)((q * per) | (((q + 1) * per) << 8));
+            }
+            base += total;
+        }
+        if (pass == 0 && threadIdx.x == 0) out[1] = base;
+    }
+    if (threadIdx.x == 0) { out[0] = base; out[2] = carry ? *carry : 0u; }
+}
+
 // near-pair count of one work unit: sum over its entries of (#targets g!=0 in masked leaves) x (#sources g!=0)
 __global__ void k_count_pairs(LeafDev L, int nleaves, int nunits, const int* __restrict__ ugroup,
                               const long long* __restrict__ ubase, const int* __restrict__ ucount, GroupLists G,

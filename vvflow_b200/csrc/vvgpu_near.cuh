@@ -59,6 +59,9 @@ struct NearArgs {
     int nleaves;
     int nseg;
     int u0;  // first unit of this launch (shard offset)
+    const int* cta_unit;             // CTA table (k_cta_table), or nullptr: blockIdx -> unit by the formula with tsplit
+    const unsigned short* cta_part;  // first | one-past-last << 8 target leaf of the group
+    int cta_heavy;                   // CTAs of the table's first class
     int tsplit;  // CTAs per unit: each takes 32 / tsplit of the group's target leaves against the whole entry table. What a
                  // target sums, and in which order, does not depend on it: few units (a small problem, one rank of many)
                  // still fill the SMs, with identical bits
@@ -72,13 +75,22 @@ struct NearArgs {
 // alternately puts them first instead of into the kernel's tail (with the work of a step split over 8 GPUs one
 // late fringe unit was a third of the kernel's duration).
 __device__ __forceinline__ int unit_order(int b, int n) { return (b & 1) ? (n - 1 - (b >> 1)) : (b >> 1); }
-// CTA -> (unit slot, first and one-past-last target leaf of the group it serves)
+// CTA -> (unit slot, first and one-past-last target leaf of the group it serves); both_ends: the unit_order heuristic
 struct UnitPart {
     int b, lt0, lt1;
-    __device__ __forceinline__ UnitPart(int tsplit) {
-        b = (int)blockIdx.x / tsplit;
-        const int part = (int)blockIdx.x - b * tsplit, per = kGroupLeaves / tsplit;
-        lt0 = part * per; lt1 = lt0 + per;
+    __device__ __forceinline__ UnitPart(const NearArgs& A, bool both_ends) {
+        if (A.cta_unit) {
+            int pos = (int)blockIdx.x;
+            if (both_ends && pos >= A.cta_heavy) pos = A.cta_heavy + unit_order(pos - A.cta_heavy, (int)gridDim.x - A.cta_heavy);
+            b = A.cta_unit[pos];
+            const int p = A.cta_part[pos];
+            lt0 = p & 0xff; lt1 = p >> 8;
+        } else {
+            const int q = (int)blockIdx.x / A.tsplit;
+            const int part = (int)blockIdx.x - q * A.tsplit, per = kGroupLeaves / A.tsplit;
+            b = both_ends ? unit_order(q, (int)gridDim.x / A.tsplit) : q;
+            lt0 = part * per; lt1 = lt0 + per;
+        }
     }
 };
 
@@ -118,8 +130,8 @@ __global__ void __launch_bounds__(kLwThreads, Op::kMinBlocks) k_near(NearArgs A,
     extern __shared__ __align__(16) unsigned char near_smem[];
     LwSharedT<Op>& S = *reinterpret_cast<LwSharedT<Op>*>(near_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const UnitPart up(A.tsplit);
-    const int u = A.u0 + unit_order(up.b, gridDim.x / A.tsplit);
+    const UnitPart up(A, true);
+    const int u = A.u0 + up.b;
     const int g = A.U.group[u];
     const int chunk = u - A.U.first[g];
     const bool multi = A.U.num[g] > 1;

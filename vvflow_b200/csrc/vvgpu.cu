@@ -485,12 +485,14 @@ int lists_impl(vvgpu_ctx* c) {
         u32 nslots = 0;
         static const bool no_table = getenv("VV_NO_CTA_TABLE") != nullptr;
         if (nunits > 0 && !no_table) {
-            const size_t ctacap = (size_t)std::max(4, c->tsplit) * nunits;
+            static const int cta_fmax = getenv("VV_CTA_MAXF") ? atoi(getenv("VV_CTA_MAXF")) : 4;
+            static const int cta_div = getenv("VV_CTA_DIV") ? atoi(getenv("VV_CTA_DIV")) : 3;
+            const size_t ctacap = (size_t)std::max(cta_fmax, c->tsplit) * nunits;
             int* ctau = c->cta_unit.get<int>(ctacap, &ok);
             unsigned short* ctap = c->cta_part.get<unsigned short>(ctacap, &ok);
             u32* cout = c->cta_out.get<u32>(4, &ok);
             NEED(ok);
-            k_cta_table<<<1, 1024, 0, st>>>((int)nunits, L, nl, ugroup, ucount, 3 * c->sm_count, c->tsplit, ctau, ctap, usb + ng, cout); CKLAUNCH();
+            k_cta_table<<<1, 1024, 0, st>>>((int)nunits, L, nl, ugroup, ucount, 3 * c->sm_count, c->tsplit, cta_fmax, cta_div, ctau, ctap, usb + ng, cout); CKLAUNCH();
             CK(cudaMemcpyAsync(c->h_pinned, cout, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
             CK(stream_sync(c));
             c->ncta = (int)((u32*)c->h_pinned)[0]; c->cta_heavy = (int)((u32*)c->h_pinned)[1]; nslots = ((u32*)c->h_pinned)[2];

@@ -678,7 +678,7 @@ __device__ __forceinline__ unsigned long long unit_cost(const LeafDev& L, int nl
     return (unsigned long long)entries * t * t;
 }
 __global__ void __launch_bounds__(1024) k_cta_table(int nunits, LeafDev L, int nleaves, const int* __restrict__ ugroup,
-                                                    const int* __restrict__ ucount, int slots, int f0,
+                                                    const int* __restrict__ ucount, int slots, int f0, int fmax, int div,
                                                     int* cta_unit, unsigned short* cta_part, const u32* carry, u32* out) {
     __shared__ u32 sh[1024 / 32 + 1];
     __shared__ unsigned long long tsum[32];
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(1024) k_cta_table(int nunits, LeafDev L, int n
         total_s = t;
     }
     __syncthreads();
-    const unsigned long long thr = max(1ull, total_s / (3ull * (unsigned long long)slots));
+    const unsigned long long thr = max(1ull, total_s / ((unsigned long long)div * (unsigned long long)slots));
     u32 base = 0;
     for (int pass = 0; pass < 2; pass++) {   // 0: the units split further than f0, 1: the others
         for (int b = 0; b < nunits; b += 1024) {
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(1024) k_cta_table(int nunits, LeafDev L, int n
             if (u < nunits) {
                 f = f0;
                 const unsigned long long cu = unit_cost(L, nleaves, ugroup[u], ucount[u]);
-                while (f < 4 && cu > thr * (unsigned long long)f) f *= 2;
+                while (f < fmax && cu > thr * (unsigned long long)f) f *= 2;
                 if ((f > f0) != (pass == 0)) f = 0;
             }
             u32 total;

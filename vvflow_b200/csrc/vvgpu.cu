@@ -1149,6 +1149,18 @@ int vvgpu_epsilon(vvgpu_ctx* c, int merge, int* merged) {
         }
         if (!changed) break;  // B reproduces A
         prev_changed = changed;
+        static const bool no_prune = getenv("VV_NO_MERGE_PRUNE") != nullptr;
+        if (!haveA && !no_prune) {
+            // round 0 assumed no merges: cancel the initiators that an earlier one absorbs (k_prune_*, vvgpu_shard.cuh);
+            // `dyn` is free until k_merge_dyn below
+            for (int sweep = 0; sweep < 3; sweep++) {
+                k_prune_valid<<<cdiv(n, 256), 256, 0, st>>>(n, B.init, B.absby, dyn); CKLAUNCH();
+                k_fill_i32<<<cdiv(n, 256), 256, 0, st>>>(n, B.absby, kNoAbs); CKLAUNCH();
+                k_prune_absby<<<cdiv(n, 256), 256, 0, st>>>(n, dyn, B.part, B.absby); CKLAUNCH();
+            }
+            k_prune_commit<<<cdiv(n, 256), 256, 0, st>>>(n, dyn, B.init, B.part); CKLAUNCH();
+            prev_changed = 0xffffffffu;   // the next round starts from a guess, not from this round's outcome: recompute all
+        }
         k_leaf_dirty_clear<<<cdiv(nl, 256), 256, 0, st>>>(nl, ldirty, ldbox); CKLAUNCH();
         k_leaf_dirty<<<cdiv(n, 256), 256, 0, st>>>(c->Lv(), nl, n, P.view(), A, B, ldirty, ldbox); CKLAUNCH();
         for (int k = 0; k < 6; k++) std::swap(c->mA[k], c->mB[k]);

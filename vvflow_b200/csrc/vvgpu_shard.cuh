@@ -133,6 +133,22 @@ __global__ void k_merge_absby(int n, const int* __restrict__ init, const int* __
     if (i >= n) return;
     if (init[i]) atomicMin(&absby[part[i]], i);
 }
+// First guess of the merge fixed point, after the round that assumed no merges: an initiator that an EARLIER initiator
+// absorbs never gets its turn (MEpsilonFast.cpp:51, g == 0 by then). In a wake full of mutual nearest neighbours that
+// is half of round 0's initiators; cancelling them here (a few sweeps of: absorbed-by from the valid initiators, valid =
+// not absorbed before its turn) spares the fixed point one full round. Any guess converges to the same solution.
+__global__ void k_prune_valid(int n, const int* __restrict__ init0, const int* __restrict__ absby, unsigned char* valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) valid[i] = (init0[i] && !(absby[i] < i)) ? 1 : 0;
+}
+__global__ void k_prune_absby(int n, const unsigned char* __restrict__ valid, const int* __restrict__ part, int* absby) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && valid[i]) atomicMin(&absby[part[i]], i);
+}
+__global__ void k_prune_commit(int n, const unsigned char* __restrict__ valid, int* init, int* part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && init[i] && !valid[i]) { init[i] = 0; part[i] = -1; }
+}
 __global__ void k_fill_i32(int n, int* a, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = v;
